@@ -1,0 +1,137 @@
+/* midi_b200.h -- C ABI of libmidi_b200.so: the sm_100a kernels behind the drop-in MIDIModel.
+ *
+ * The reference (SkyTNT/midi-model) has no FFI: its hot path is the Python class
+ * `MIDIModel` (midi_model.py:99-250) whose arithmetic is delegated to HF transformers /
+ * ATen.  This header is therefore the *new* boundary a maintainer binds with ctypes (see
+ * INTEGRATION.md): plain pointers and sizes, no torch types, no allocation inside, the caller's
+ * cudaStream_t last.  Each entry cites the reference call it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 (B200_OK) or a negative code; b200_last_error() gives the message
+ *     (thread-local).  Nothing is allocated or synchronised inside; workspaces are caller-owned and
+ *     sized by the *_workspace_bytes / *_parts queries.
+ *   - all device pointers: bf16 activations/weights unless typed otherwise; token ids are int64
+ *     (torch.long, the MIDITokenizerV2 tensor layout (batch, events, 8)); row-major.
+ *   - kernels are re-entrant per stream (no global mutable state).
+ */
+#ifndef MIDI_B200_H
+#define MIDI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __DRIVER_TYPES_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define B200_OK 0
+#define B200_ERR_ARG (-1)
+#define B200_ERR_CUDA (-2)
+#define B200_ERR_UNSUPPORTED (-3)
+
+/* ---- runtime ------------------------------------------------------------------------------ */
+const char* b200_last_error(void);
+int b200_abi_version(void);
+int b200_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- embeddings (midi_model.py:145-146 `embed_tokens(x).sum(-2)`; :126-131 cat([hidden, embed(x)])) */
+int b200_embed_sum_fwd(const long long* ids, const void* table, void* out, int M, int T, int H, int V, cudaStream_t s);
+int b200_inner_input_fwd(const void* hidden /*may be NULL*/, const long long* ids, const void* table, void* out,
+                         int n_events, int n_ids, int H, int V, cudaStream_t s);
+int b200_inner_input_bwd_hidden(const void* dx, void* dhidden, int n_events, int Tin, int H, cudaStream_t s);
+size_t b200_embed_bwd_workspace_bytes(int n_ids, int V, int H);
+/* id i reads gradient row (i / per_row) * row_stride + (i % per_row) * row_inner + row_off; pad row gets 0 */
+int b200_embed_bwd(const long long* ids, int n_ids, const void* dout, void* dtable, int V, int H, int per_row,
+                   int row_stride, int row_inner, int row_off, int pad_id, int accumulate, void* workspace,
+                   size_t workspace_bytes, cudaStream_t s);
+
+/* ---- RMSNorm (hf modeling_llama.py:62-67) --------------------------------------------------- */
+int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd /*may be NULL*/, int M, int H, float eps,
+                     cudaStream_t s);
+int b200_rmsnorm_bwd_parts(void);
+/* dx = dres + d(norm)/dx ; dw (+)= column sums.  workspace: float[b200_rmsnorm_bwd_parts() * H] */
+int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres /*may be NULL*/,
+                     void* dx, void* dw /*may be NULL*/, int M, int H, int accumulate_dw, void* workspace,
+                     size_t workspace_bytes, cudaStream_t s);
+
+/* ---- RoPE (hf modeling_llama.py:124-168), applied in place to the q,k thirds of packed qkv -------- */
+int b200_rope_table(const float* inv_freq, int half, int n_pos, int pos0, const int* pos0_dev /*may be NULL*/,
+                    void* cos_t, void* sin_t, cudaStream_t s);
+int b200_rope_qk(void* qkv, const void* cos_t, const void* sin_t, int rows, int S, int H, int D, int ld, int backward,
+                 cudaStream_t s);
+
+/* ---- SwiGLU (hf modeling_llama.py:183) on packed [rows, 2I] = [gate | up] ------------------------- */
+int b200_swiglu_fwd(const void* gu, void* act, long long rows, int I, cudaStream_t s);
+int b200_swiglu_bwd(const void* gu, const void* dact, void* dgu, long long rows, int I, cudaStream_t s);
+
+/* ---- tensor-core GEMM (tcgen05 / TMEM / TMA): every nn.Linear of hf modeling_llama.py:177-184,
+ *      238-264, 288 and lm_head (midi_model.py:135), plus their dgrad / wgrad.
+ *      C[M,N] = A . B^T, fp32 accumulate, bf16 out.  a_mn_major / b_mn_major = operand stored [K, rows].
+ *      R != NULL: C = bf16(bf16(acc) + R) (residual add, hf :325 / :331).
+ *      splits > 1 or accumulate: fp32 split-K partials in `workspace`, reduced (and added to C). */
+size_t b200_gemm_workspace_bytes(int M, int N, int splits);
+int b200_gemm_suggest_splits(int M, int N, int K, int block_n);
+int b200_gemm_bf16(const void* A, const void* B, void* C, const void* R, int M, int N, int K, int lda, int ldb, int ldc,
+                   int ldr, int a_mn_major, int b_mn_major, int accumulate, int block_n, int splits, void* workspace,
+                   size_t workspace_bytes, cudaStream_t s);
+
+/* ---- attention (hf integrations/sdpa_attention.py:41-104 via modeling_llama.py:251-289) ----------
+ *      outer stack: causal flash attention, head_dim 64; strides are element strides {batch,row,head}. */
+int b200_attn_causal_fwd(const void* q, const void* k, const void* v, void* o, float* lse /*may be NULL*/,
+                         const long long* strides /*4x3: q,k,v,o*/, int batch, int n_heads, int Sq, int Sk, int head_dim,
+                         float scale, cudaStream_t s);
+int b200_attn_causal_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                         float* delta /*float[batch*n_heads*Sq]*/, void* dq, void* dk, void* dv,
+                         const long long* strides /*8x3: q,k,v,o,do,dq,dk,dv*/, int batch, int n_heads, int Sq, int Sk,
+                         int head_dim, float scale, cudaStream_t s);
+/*      inner stack: L <= 8 positions per event, head_dim 256, packed qkv rows [n_events*L, ld_qkv]. */
+int b200_attn_tiny_fwd(const void* qkv, void* out, int n_events, int L, int n_heads, int head_dim, int ld_qkv, int ld_out,
+                       float scale, cudaStream_t s);
+int b200_attn_tiny_bwd(const void* qkv, const void* d_out, void* dqkv, int n_events, int L, int n_heads, int head_dim,
+                       int ld_qkv, int ld_out, float scale, cudaStream_t s);
+
+/* ---- loss (train.py:180-185: mean CE, ignore_index = pad) ----------------------------------------- */
+int b200_ce_fwd(const void* logits, const long long* targets, float* lse, float* row_loss,
+                float* loss_and_count /*float[2]: mean loss, #targets*/, long long rows, int V, int ld,
+                long long ignore_index, cudaStream_t s);
+int b200_ce_bwd(void* logits_inout, const long long* targets, const float* lse, const float* loss_and_count,
+                long long rows, int V, int ld, long long ignore_index, float grad_scale, cudaStream_t s);
+
+/* ---- optimizer (train.py:121-138 AdamW groups; :464 gradient_clip_val) ----------------------------- */
+int b200_gradnorm_parts(void);
+int b200_grad_clip_coef(const void* grads, long long n, float max_norm, float* norm_and_coef /*float[2]*/,
+                        void* workspace, size_t workspace_bytes, cudaStream_t s);
+int b200_adamw_step(void* params, const void* grads, float* exp_avg, float* exp_avg_sq,
+                    const unsigned char* nodecay_blocks /*[n/256]*/, long long n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int step, const float* norm_and_coef /*may be NULL*/, cudaStream_t s);
+
+/* ---- generate() loop (midi_model.py:167-250) ------------------------------------------------------ */
+int b200_gemv_bf16(const void* x, const void* W, const void* res /*may be NULL*/, void* y, int B, int N, int K, int ldx,
+                   int ldw, int ldr, int ldy, cudaStream_t s);
+/*      paged KV cache replacing DynamicCache.update's torch.cat (hf cache_utils.py:102-121):
+ *      pools [n_pages][n_heads][page][head_dim], block_table [batch][max_pages] */
+int b200_kv_append(const void* qkv, void* k_pool, void* v_pool, const int* block_table, int max_pages, int page,
+                   int n_heads, int head_dim, int batch, int s_new, int pos0, const int* pos0_dev, int ld, cudaStream_t s);
+size_t b200_attn_decode_workspace_bytes(int rows, int n_heads, int head_dim, int n_split);
+int b200_attn_decode(const void* q, const void* k_pool, const void* v_pool, const int* block_table, int max_pages, int page,
+                     void* out, int batch, int s_q, int n_heads, int head_dim, int past, const int* past_dev, int max_T,
+                     int ldq, int ldo, float scale, int n_split, void* workspace, size_t workspace_bytes, cudaStream_t s);
+/*      sampler: MIDIModel.sample_top_p_k (midi_model.py:152-165) on given probabilities ...            */
+int b200_sample_topp_topk(const void* probs, int is_bf16, int rows, int V, int ld, float top_p, int top_k,
+                          const float* uniforms, long long* out, cudaStream_t s);
+/*      ... and fused with temperature-softmax + grammar mask (midi_model.py:202-223)                    */
+int b200_sample_from_logits(const void* logits, int rows, int V, int ld, float temp, float top_p, int top_k, int step,
+                            const long long* event_tok, const int* lut, int n_event_types, int eos_id, int pad_id,
+                            const unsigned char* dense_mask /*may be NULL*/, const float* uniforms, long long* out,
+                            int out_stride, cudaStream_t s);
+int b200_uniform_fill(float* u, int n, unsigned long long seed, unsigned long long* counter_dev, cudaStream_t s);
+int b200_add_int(int* p, int v, cudaStream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIDI_B200_H */

@@ -1,0 +1,103 @@
+// Common device/host helpers for the sm_100a kernels of the MIDIModel hot path.
+// Everything here is plain CUDA C++ + inline PTX (no CUTLASS / no torch types).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+typedef __nv_bfloat16 bf16;
+typedef __nv_bfloat162 bf162;
+
+// ---------------------------------------------------------------------------
+// error reporting: every C-ABI entry returns 0 or a negative code; the message
+// is kept per thread and read back with b200_last_error().
+// ---------------------------------------------------------------------------
+extern "C" const char* b200_last_error(void);
+void b200_set_error(const char* fmt, ...);
+
+#define B200_OK 0
+#define B200_ERR_ARG (-1)
+#define B200_ERR_CUDA (-2)
+#define B200_ERR_UNSUPPORTED (-3)
+
+#define B200_CHECK_ARG(cond, ...)                \
+    do {                                         \
+        if (!(cond)) {                           \
+            b200_set_error(__VA_ARGS__);         \
+            return B200_ERR_ARG;                 \
+        }                                        \
+    } while (0)
+
+#define B200_CHECK_LAUNCH(name)                                                       \
+    do {                                                                              \
+        cudaError_t e__ = cudaGetLastError();                                         \
+        if (e__ != cudaSuccess) {                                                     \
+            b200_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));   \
+            return B200_ERR_CUDA;                                                     \
+        }                                                                             \
+    } while (0)
+
+#define B200_CUDA(call, name)                                                         \
+    do {                                                                              \
+        cudaError_t e__ = (call);                                                     \
+        if (e__ != cudaSuccess) {                                                     \
+            b200_set_error("%s: %s", name, cudaGetErrorString(e__));                  \
+            return B200_ERR_CUDA;                                                     \
+        }                                                                             \
+    } while (0)
+
+int b200_num_sms();
+
+// ---------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// round-to-nearest-even fp32 -> bf16 -> fp32 (a "rounding point" of the reference's eager bf16 path)
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+struct __align__(16) bf16x8 {
+    bf162 v[4];
+};
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+    const bf162* p = reinterpret_cast<const bf162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float2 t = __bfloat1622float2(p[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+    uint4 u;
+    bf162* p = reinterpret_cast<bf162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; i++) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return u;
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    bf162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+
+__device__ __forceinline__ uint4 ld_nc16(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

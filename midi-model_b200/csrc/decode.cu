@@ -1,0 +1,524 @@
+// Kernels of the generate() loop (midi_model.py:167-250): every step is a handful of rows, so
+// all of this is HBM-bound weight / KV streaming.
+//  * skinny GEMM  y[B<=16, N] = x . W^T     -- one warp per output column streams the weight row
+//    with 16-byte loads, activations staged in shared memory, fp32 accumulate (nn.Linear rounding)
+//  * paged KV cache (pages of PAGE positions, per-row block table): append + single-query attention
+//    with split-T partials and a combine pass (replaces DynamicCache's torch.cat, hf cache_utils.py:119)
+//  * fused sampler: temperature, full-vocab softmax, grammar range / mask, top-p, top-k, draw
+//    (midi_model.py:222-223 + 152-165), one CTA per row, bitonic sort of the non-zero entries only.
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// skinny GEMM
+// ---------------------------------------------------------------------------------------------
+constexpr int GV_WARPS = 8;
+
+template <int B>
+__global__ void __launch_bounds__(GV_WARPS * 32)
+gemv_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, const bf16* __restrict__ res, bf16* __restrict__ y,
+            int N, int K, int ldx, int ldw, int ldr, int ldy) {
+    extern __shared__ __align__(16) uint8_t gv_smem[];
+    bf16* xs = reinterpret_cast<bf16*>(gv_smem);   // [B][K]
+    const int nvec = K / 8;
+    for (int i = threadIdx.x; i < B * nvec; i += blockDim.x) {
+        const int b = i / nvec, v = i % nvec;
+        *reinterpret_cast<uint4*>(xs + b * K + v * 8) = *reinterpret_cast<const uint4*>(x + (size_t)b * ldx + v * 8);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int n = blockIdx.x * GV_WARPS + warp; n < N; n += gridDim.x * GV_WARPS) {
+        float acc[B];
+#pragma unroll
+        for (int b = 0; b < B; b++) acc[b] = 0.f;
+        const bf16* wrow = W + (size_t)n * ldw;
+        for (int v = lane; v < nvec; v += 32) {
+            float wf[8];
+            unpack8(ld_nc16(wrow + v * 8), wf);
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                float xf[8];
+                unpack8(*reinterpret_cast<const uint4*>(xs + b * K + v * 8), xf);
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[b] = fmaf(wf[j], xf[j], acc[b]);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < B; b++) acc[b] = warp_sum(acc[b]);
+        if (lane == 0) {
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                float o = acc[b];
+                if (res) o = bf16_round(o) + __bfloat162float(res[(size_t)b * ldr + n]);
+                y[(size_t)b * ldy + n] = __float2bfloat16_rn(o);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// paged KV cache
+// ---------------------------------------------------------------------------------------------
+struct KVLayout {
+    bf16* k_pool;          // [n_pages][n_heads][page][D]
+    bf16* v_pool;
+    const int* block_table;   // [batch][max_pages]
+    int max_pages, page, n_heads, D;
+};
+__device__ __forceinline__ size_t kv_off(const KVLayout& L, int b, int h, int t) {
+    const int pg = L.block_table[b * L.max_pages + t / L.page];
+    return (((size_t)pg * L.n_heads + h) * L.page + (t % L.page)) * L.D;
+}
+
+// copy the k / v thirds of packed qkv rows [batch*s_new, 3H] into the cache at positions pos0 .. pos0+s_new-1
+__global__ void kv_append_kernel(const bf16* __restrict__ qkv, KVLayout L, int s_new, int pos0, const int* pos0_dev, int ld) {
+    const int r = blockIdx.x;
+    const int b = r / s_new, i = r % s_new;
+    const int t = (pos0_dev ? *pos0_dev : pos0) + i;
+    const int H = L.n_heads * L.D;
+    const int vec_per_head = L.D / 8;
+    for (int c = threadIdx.x; c < H / 8; c += blockDim.x) {
+        const int h = c / vec_per_head, dv = c % vec_per_head;
+        const size_t o = kv_off(L, b, h, t) + dv * 8;
+        *reinterpret_cast<uint4*>(L.k_pool + o) = *reinterpret_cast<const uint4*>(qkv + (size_t)r * ld + H + c * 8);
+        *reinterpret_cast<uint4*>(L.v_pool + o) = *reinterpret_cast<const uint4*>(qkv + (size_t)r * ld + 2 * H + c * 8);
+    }
+}
+
+// single-query attention over the cache.  Row r = b * s_q + i attends to keys 0 .. past + i.
+// grid (rows * n_heads, n_split); partial: [rows*n_heads][n_split][D + 2] = (m, l, o[D])
+template <int D>
+__global__ void __launch_bounds__(128)
+decode_attn_kernel(const bf16* __restrict__ q, KVLayout L, float* __restrict__ partial, int s_q, int past,
+                   const int* past_dev, int ldq, float scale, int n_split) {
+    constexpr int CHUNK_MAX = 1024;
+    __shared__ float s_sc[CHUNK_MAX];
+    __shared__ __align__(16) bf16 s_q_sh[D];
+    __shared__ float s_red[8];
+    __shared__ float s_out[2][D];
+    const int rh = blockIdx.x;
+    const int r = rh / L.n_heads, h = rh % L.n_heads;
+    const int b = r / s_q, i = r % s_q;
+    const int T = (past_dev ? *past_dev : past) + i + 1;
+    const int chunk = (T + n_split - 1) / n_split;
+    const int t0 = blockIdx.y * chunk;
+    const int t1 = min(T, t0 + chunk);
+    float* pout = partial + ((size_t)rh * n_split + blockIdx.y) * (D + 2);
+    if (t0 >= t1) {
+        if (threadIdx.x == 0) { pout[0] = -INFINITY; pout[1] = 0.f; }
+        for (int d = threadIdx.x; d < D; d += blockDim.x) pout[2 + d] = 0.f;
+        return;
+    }
+    for (int d = threadIdx.x; d < D / 8; d += blockDim.x)
+        *reinterpret_cast<uint4*>(s_q_sh + d * 8) = *reinterpret_cast<const uint4*>(q + (size_t)r * ldq + h * D + d * 8);
+    __syncthreads();
+    // scores: one thread per key
+    float mx = -INFINITY;
+    for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
+        const bf16* kp = L.k_pool + kv_off(L, b, h, t);
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d < D / 8; d++) {
+            float kf[8], qf[8];
+            unpack8(ld_nc16(kp + d * 8), kf);
+            unpack8(*reinterpret_cast<const uint4*>(s_q_sh + d * 8), qf);
+#pragma unroll
+            for (int j = 0; j < 8; j++) s = fmaf(kf[j], qf[j], s);
+        }
+        s *= scale;
+        s_sc[t - t0] = s;
+        mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+    float sum = 0.f;
+    for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
+        const float p = __expf(s_sc[t - t0] - mx);
+        sum += p;
+        s_sc[t - t0] = bf16_round(p);   // P rounded to bf16 before P.V (flash semantics)
+    }
+    sum = warp_sum(sum);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[4 + (threadIdx.x >> 5)] = sum;
+    __syncthreads();
+    sum = s_red[4] + s_red[5] + s_red[6] + s_red[7];
+    // output: threads split (key parity group, d)
+    constexpr int GROUPS = (D >= 128) ? 1 : 128 / D;   // D=64 -> 2 groups of 64 threads ; D=256 -> 1 group, 2 d per thread
+    constexpr int DPT = (D >= 128) ? D / 128 : 1;
+    const int grp = (D >= 128) ? 0 : threadIdx.x / D;
+    const int d0 = (D >= 128) ? threadIdx.x * DPT : threadIdx.x % D;
+    float acc[DPT];
+#pragma unroll
+    for (int j = 0; j < DPT; j++) acc[j] = 0.f;
+    for (int t = t0 + grp; t < t1; t += GROUPS) {
+        const bf16* vp = L.v_pool + kv_off(L, b, h, t);
+        const float p = s_sc[t - t0];
+#pragma unroll
+        for (int j = 0; j < DPT; j++) acc[j] = fmaf(p, __bfloat162float(vp[d0 + j]), acc[j]);
+    }
+    if (GROUPS == 2) {
+        s_out[grp][d0] = acc[0];
+        __syncthreads();
+        if (grp == 0) pout[2 + d0] = s_out[0][d0] + s_out[1][d0];
+    } else {
+#pragma unroll
+        for (int j = 0; j < DPT; j++) pout[2 + d0 + j] = acc[j];
+    }
+    if (threadIdx.x == 0) { pout[0] = mx; pout[1] = sum; }
+}
+
+template <int D>
+__global__ void decode_attn_combine_kernel(const float* __restrict__ partial, bf16* __restrict__ out, int n_heads,
+                                           int n_split, int ldo) {
+    const int rh = blockIdx.x;
+    const int r = rh / n_heads, h = rh % n_heads;
+    const float* p = partial + (size_t)rh * n_split * (D + 2);
+    float mx = -INFINITY;
+    for (int s = 0; s < n_split; s++) mx = fmaxf(mx, p[s * (D + 2)]);
+    float l = 0.f;
+    for (int s = 0; s < n_split; s++) {
+        const float m = p[s * (D + 2)];
+        if (m > -INFINITY) l += p[s * (D + 2) + 1] * __expf(m - mx);
+    }
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float o = 0.f;
+        for (int s = 0; s < n_split; s++) {
+            const float m = p[s * (D + 2)];
+            if (m > -INFINITY) o += p[s * (D + 2) + 2 + d] * __expf(m - mx);
+        }
+        out[(size_t)r * ldo + h * D + d] = __float2bfloat16_rn(o / l);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// sampler
+// ---------------------------------------------------------------------------------------------
+constexpr int SMP_THREADS = 256;
+constexpr int SMP_MAXV = 4096;
+
+__device__ __forceinline__ bool key_before(float pa, int ia, float pb, int ib) {   // sort order: prob desc, id asc
+    return (pa > pb) || (pa == pb && ia < ib);
+}
+
+// Shared tail: s_p/s_i hold `n` candidate (prob, id) pairs (prob > 0), unsorted.  Sort, apply top-p on the
+// un-renormalised mass and top-k, renormalise, draw with uniform u.  Returns the chosen id (all threads).
+__device__ int sample_tail(float* s_p, int* s_i, int n, float top_p, int top_k, float u, bool bf16_sem) {
+    int n_sort = 32;
+    while (n_sort < n) n_sort <<= 1;
+    for (int i = n + threadIdx.x; i < n_sort; i += blockDim.x) { s_p[i] = -1.f; s_i[i] = 0x7fffffff; }
+    __syncthreads();
+    for (int k = 2; k <= n_sort; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n_sort; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const bool up = (i & k) == 0;
+                    const float pa = s_p[i], pb = s_p[ixj];
+                    const int ia = s_i[i], ib = s_i[ixj];
+                    const bool a_first = key_before(pa, ia, pb, ib);
+                    if (up ? !a_first : a_first) { s_p[i] = pb; s_p[ixj] = pa; s_i[i] = ib; s_i[ixj] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // Only ranks < kk can survive.  Sequential scan by one thread over <= kk entries is cheap for the
+    // usual top_k (20); large k falls back to the same loop (still correct).
+    const int kk = min(n, top_k);
+    __shared__ int s_choice;
+    if (threadIdx.x == 0) {
+        float cum = 0.f, total = 0.f;
+        const float pth = bf16_sem ? bf16_round(top_p) : top_p;
+        int last = 0;
+        for (int i = 0; i < kk; i++) {
+            const float pi = s_p[i];
+            cum += pi;
+            const float cs = bf16_sem ? bf16_round(cum) : cum;
+            const float before = bf16_sem ? bf16_round(cs - pi) : cs - pi;
+            const float w = (before > pth) ? 0.f : pi;   // midi_model.py:155-156
+            s_p[i] = w;   // weights overwrite the sorted probabilities in place
+            total += w;
+            if (w > 0.f) last = i;
+        }
+        int choice = 0;
+        if (total > 0.f) {
+            const float target = u * total;
+            float run = 0.f;
+            choice = last;
+            for (int i = 0; i <= last; i++) {
+                run += s_p[i];
+                if (s_p[i] > 0.f && run > target) { choice = i; break; }
+            }
+        }
+        s_choice = (n > 0) ? s_i[choice] : 0;
+    }
+    __syncthreads();
+    return s_choice;
+}
+
+// compact the non-zero entries of s_p (indexed by id) into the front of (s_p, s_i); returns count.
+__device__ int compact_nonzero(float* s_p, int* s_i, int V, int* s_cnt) {
+    const int per = (V + SMP_THREADS - 1) / SMP_THREADS;
+    const int beg = threadIdx.x * per;
+    const int end = min(V, beg + per);
+    float loc_p[SMP_MAXV / SMP_THREADS];
+    int c = 0;
+    for (int i = beg; i < end; i++) {
+        const float p = s_p[i];
+        loc_p[i - beg] = p;
+        if (p > 0.f) c++;
+    }
+    s_cnt[threadIdx.x] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < SMP_THREADS; i++) { const int t = s_cnt[i]; s_cnt[i] = run; run += t; }
+        s_cnt[SMP_THREADS] = run;
+    }
+    __syncthreads();
+    int pos = s_cnt[threadIdx.x];
+    const int total = s_cnt[SMP_THREADS];
+    __syncthreads();   // everyone has read its chunk of s_p into registers before it is overwritten
+    for (int i = beg; i < end; i++) {
+        const float p = loc_p[i - beg];
+        if (p > 0.f) { s_p[pos] = p; s_i[pos] = i; pos++; }
+    }
+    __syncthreads();
+    return total;
+}
+
+// probs: [rows, V] (bf16 or fp32) already softmaxed and masked (public sample_top_p_k API)
+template <typename T>
+__global__ void __launch_bounds__(SMP_THREADS)
+sample_probs_kernel(const T* __restrict__ probs, int V, int ld, float top_p, int top_k, const float* __restrict__ uniforms,
+                    long long* __restrict__ out, bool bf16_sem) {
+    __shared__ float s_p[SMP_MAXV];
+    __shared__ int s_i[SMP_MAXV];
+    __shared__ int s_cnt[SMP_THREADS + 1];
+    const int r = blockIdx.x;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) {
+        float p = (float)probs[(size_t)r * ld + i];
+        s_p[i] = (p > 0.f) ? p : 0.f;   // NaN / negative -> 0
+    }
+    __syncthreads();
+    const int n = compact_nonzero(s_p, s_i, V, s_cnt);
+    const int id = sample_tail(s_p, s_i, n, top_p, top_k, uniforms[r], bf16_sem);
+    if (threadIdx.x == 0) out[r] = id;
+}
+
+// Fused generate-step sampler: logits [rows, ld] bf16 -> token id.
+// Allowed ids of row r at inner step `step` (midi_model.py:202-215):
+//   step 0            : [eos_id, eos_id + n_event_types]  (eos + the event-type ids, contiguous)
+//   step i > 0        : lut[(ev - first_event) * 8 + (i-1)] = (lo, hi) of that parameter; pad only if exhausted / ended
+// `event_tok` [rows] holds the step-0 token of the current event; `dense_mask` (optional, [rows, V] uint8) is ANDed.
+__global__ void __launch_bounds__(SMP_THREADS)
+sample_logits_kernel(const bf16* __restrict__ logits, int V, int ld, float temp, float top_p, int top_k, int step,
+                     const long long* __restrict__ event_tok, const int* __restrict__ lut, int n_event_types, int eos_id,
+                     int pad_id, const unsigned char* __restrict__ dense_mask, const float* __restrict__ uniforms,
+                     long long* __restrict__ out, int out_stride) {
+    __shared__ float s_p[SMP_MAXV];
+    __shared__ int s_i[SMP_MAXV];
+    __shared__ int s_cnt[SMP_THREADS + 1];
+    __shared__ float s_red[16];
+    const int r = blockIdx.x;
+    int lo, hi;
+    if (step == 0) {
+        lo = eos_id; hi = eos_id + 1 + n_event_types;
+    } else {
+        const long long ev = event_tok[r];
+        const int e = (int)ev - (eos_id + 1);
+        if (ev == eos_id || e < 0 || e >= n_event_types) { lo = pad_id; hi = pad_id + 1; }
+        else {
+            lo = lut[(e * 8 + (step - 1)) * 2];
+            hi = lut[(e * 8 + (step - 1)) * 2 + 1];
+            if (hi <= lo) { lo = pad_id; hi = pad_id + 1; }
+        }
+    }
+    // softmax(logits / temp) in bf16 semantics: x = bf16(l / temp); p = bf16(exp(x - max) / sum)
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) {
+        const float x = bf16_round(__bfloat162float(logits[(size_t)r * ld + i]) / temp);
+        s_p[i] = x;
+        mx = fmaxf(mx, x);
+    }
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = s_red[0];
+    for (int w = 1; w < SMP_THREADS / 32; w++) mx = fmaxf(mx, s_red[w]);
+    float sum = 0.f;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) sum += __expf(s_p[i] - mx);
+    sum = warp_sum(sum);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[8 + (threadIdx.x >> 5)] = sum;
+    __syncthreads();
+    sum = 0.f;
+    for (int w = 0; w < SMP_THREADS / 32; w++) sum += s_red[8 + w];
+    const float inv = 1.f / sum;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) {
+        bool ok = (i >= lo && i < hi);
+        if (ok && dense_mask) ok = dense_mask[(size_t)r * V + i] != 0;
+        s_p[i] = ok ? bf16_round(__expf(s_p[i] - mx) * inv) : 0.f;
+    }
+    __syncthreads();
+    int n = compact_nonzero(s_p, s_i, V, s_cnt);
+    int id;
+    if (n == 0) {
+        // every allowed probability underflowed: the reference would raise inside multinomial (Appendix E.3);
+        // fall back to the lowest allowed id instead of crashing.
+        id = lo;
+    } else {
+        id = sample_tail(s_p, s_i, n, top_p, top_k, uniforms[r], true);
+    }
+    if (threadIdx.x == 0) out[(size_t)r * out_stride] = id;
+}
+
+// counter-based uniform generator for graph-captured loops: u[r] = hash(seed, counter, r) in [0,1)
+__global__ void philox_uniform_kernel(float* __restrict__ u, int n, unsigned long long seed, unsigned long long* counter) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long c = *counter;
+    if (i < n) {
+        unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (c * 4096ULL + (unsigned long long)i + 1ULL);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        z = z ^ (z >> 31);
+        u[i] = (float)(z >> 40) * (1.0f / 16777216.0f);
+    }
+    __syncthreads();
+    if (i == 0) *counter = c + 1;
+}
+
+__global__ void add_int_kernel(int* p, int v) { *p += v; }
+
+}   // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" int b200_gemv_bf16(const void* x, const void* W, const void* res, void* y, int B, int N, int K, int ldx, int ldw,
+                              int ldr, int ldy, cudaStream_t stream) {
+    B200_CHECK_ARG(B >= 1 && B <= 16, "gemv: batch %d outside 1..16 (use the tensor-core GEMM)", B);
+    B200_CHECK_ARG(K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "gemv: K, ldx, ldw must be multiples of 8");
+    const size_t smem = (size_t)B * K * 2;
+    B200_CHECK_ARG(smem <= 200 * 1024, "gemv: B*K too large for shared memory");
+    int grid = (N + GV_WARPS - 1) / GV_WARPS;
+    const int cap = b200_num_sms() * 4;
+    if (grid > cap) grid = cap;
+#define B200_GEMV(BB)                                                                                              \
+    do {                                                                                                           \
+        static bool configured = false;                                                                            \
+        if (!configured) {                                                                                         \
+            B200_CUDA(cudaFuncSetAttribute(gemv_kernel<BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), \
+                      "gemv smem attr");                                                                           \
+            configured = true;                                                                                     \
+        }                                                                                                          \
+        gemv_kernel<BB><<<grid, GV_WARPS * 32, smem, stream>>>((const bf16*)x, (const bf16*)W, (const bf16*)res,   \
+                                                               (bf16*)y, N, K, ldx, ldw, ldr, ldy);                \
+    } while (0)
+    switch (B) {
+        case 1: B200_GEMV(1); break;
+        case 2: B200_GEMV(2); break;
+        case 3: B200_GEMV(3); break;
+        case 4: B200_GEMV(4); break;
+        case 5: B200_GEMV(5); break;
+        case 6: B200_GEMV(6); break;
+        case 7: B200_GEMV(7); break;
+        case 8: B200_GEMV(8); break;
+        case 9: B200_GEMV(9); break;
+        case 10: B200_GEMV(10); break;
+        case 11: B200_GEMV(11); break;
+        case 12: B200_GEMV(12); break;
+        case 13: B200_GEMV(13); break;
+        case 14: B200_GEMV(14); break;
+        case 15: B200_GEMV(15); break;
+        default: B200_GEMV(16); break;
+    }
+#undef B200_GEMV
+    B200_CHECK_LAUNCH("gemv");
+    return B200_OK;
+}
+
+extern "C" int b200_kv_append(const void* qkv, void* k_pool, void* v_pool, const int* block_table, int max_pages, int page,
+                              int n_heads, int head_dim, int batch, int s_new, int pos0, const int* pos0_dev, int ld,
+                              cudaStream_t stream) {
+    B200_CHECK_ARG(head_dim % 8 == 0, "kv_append: head_dim must be a multiple of 8");
+    if (batch * s_new == 0) return B200_OK;
+    KVLayout L{(bf16*)k_pool, (bf16*)v_pool, block_table, max_pages, page, n_heads, head_dim};
+    kv_append_kernel<<<batch * s_new, 128, 0, stream>>>((const bf16*)qkv, L, s_new, pos0, pos0_dev, ld);
+    B200_CHECK_LAUNCH("kv_append");
+    return B200_OK;
+}
+
+extern "C" size_t b200_attn_decode_workspace_bytes(int rows, int n_heads, int head_dim, int n_split) {
+    return (size_t)rows * n_heads * n_split * (head_dim + 2) * sizeof(float);
+}
+
+// q: [batch*s_q, ldq] (q third of the packed qkv row, post-RoPE); out: [batch*s_q, ldo]
+extern "C" int b200_attn_decode(const void* q, const void* k_pool, const void* v_pool, const int* block_table, int max_pages,
+                                int page, void* out, int batch, int s_q, int n_heads, int head_dim, int past,
+                                const int* past_dev, int max_T, int ldq, int ldo, float scale, int n_split, void* workspace,
+                                size_t workspace_bytes, cudaStream_t stream) {
+    B200_CHECK_ARG(head_dim == 64 || head_dim == 256, "attn_decode: head_dim %d unsupported", head_dim);
+    const int rows = batch * s_q;
+    if (rows == 0) return B200_OK;
+    if (n_split < 1) n_split = 1;
+    B200_CHECK_ARG((max_T + n_split - 1) / n_split <= 1024, "attn_decode: chunk per split exceeds 1024 keys (raise n_split)");
+    B200_CHECK_ARG(workspace_bytes >= b200_attn_decode_workspace_bytes(rows, n_heads, head_dim, n_split),
+                   "attn_decode: workspace too small");
+    KVLayout L{(bf16*)k_pool, (bf16*)v_pool, block_table, max_pages, page, n_heads, head_dim};
+    dim3 grid(rows * n_heads, n_split);
+    if (head_dim == 64) {
+        decode_attn_kernel<64><<<grid, 128, 0, stream>>>((const bf16*)q, L, (float*)workspace, s_q, past, past_dev, ldq, scale, n_split);
+        decode_attn_combine_kernel<64><<<rows * n_heads, 64, 0, stream>>>((const float*)workspace, (bf16*)out, n_heads, n_split, ldo);
+    } else {
+        decode_attn_kernel<256><<<grid, 128, 0, stream>>>((const bf16*)q, L, (float*)workspace, s_q, past, past_dev, ldq, scale, n_split);
+        decode_attn_combine_kernel<256><<<rows * n_heads, 128, 0, stream>>>((const float*)workspace, (bf16*)out, n_heads, n_split, ldo);
+    }
+    B200_CHECK_LAUNCH("attn_decode");
+    return B200_OK;
+}
+
+extern "C" int b200_sample_topp_topk(const void* probs, int is_bf16, int rows, int V, int ld, float top_p, int top_k,
+                                     const float* uniforms, long long* out, cudaStream_t stream) {
+    B200_CHECK_ARG(V <= SMP_MAXV, "sample_topp_topk: vocabulary %d exceeds %d", V, SMP_MAXV);
+    if (rows == 0) return B200_OK;
+    if (top_k < 1) top_k = 1;
+    if (is_bf16)
+        sample_probs_kernel<bf16><<<rows, SMP_THREADS, 0, stream>>>((const bf16*)probs, V, ld, top_p, top_k, uniforms, out, true);
+    else
+        sample_probs_kernel<float><<<rows, SMP_THREADS, 0, stream>>>((const float*)probs, V, ld, top_p, top_k, uniforms, out, false);
+    B200_CHECK_LAUNCH("sample_topp_topk");
+    return B200_OK;
+}
+
+extern "C" int b200_sample_from_logits(const void* logits, int rows, int V, int ld, float temp, float top_p, int top_k,
+                                       int step, const long long* event_tok, const int* lut, int n_event_types, int eos_id,
+                                       int pad_id, const unsigned char* dense_mask, const float* uniforms, long long* out,
+                                       int out_stride, cudaStream_t stream) {
+    B200_CHECK_ARG(V <= SMP_MAXV, "sample_from_logits: vocabulary %d exceeds %d", V, SMP_MAXV);
+    B200_CHECK_ARG(temp > 0.f, "sample_from_logits: temperature must be positive");
+    if (rows == 0) return B200_OK;
+    if (top_k < 1) top_k = 1;
+    sample_logits_kernel<<<rows, SMP_THREADS, 0, stream>>>((const bf16*)logits, V, ld, temp, top_p, top_k, step,
+                                                          event_tok, lut, n_event_types, eos_id, pad_id, dense_mask,
+                                                          uniforms, out, out_stride);
+    B200_CHECK_LAUNCH("sample_from_logits");
+    return B200_OK;
+}
+
+extern "C" int b200_uniform_fill(float* u, int n, unsigned long long seed, unsigned long long* counter_dev,
+                                 cudaStream_t stream) {
+    B200_CHECK_ARG(n >= 1 && n <= 1024, "uniform_fill: n outside 1..1024");
+    philox_uniform_kernel<<<1, 1024, 0, stream>>>(u, n, seed, counter_dev);
+    B200_CHECK_LAUNCH("uniform_fill");
+    return B200_OK;
+}
+
+extern "C" int b200_add_int(int* p, int v, cudaStream_t stream) {
+    add_int_kernel<<<1, 1, 0, stream>>>(p, v);
+    B200_CHECK_LAUNCH("add_int");
+    return B200_OK;
+}

@@ -1,0 +1,504 @@
+// HBM-bound kernels of the MIDIModel hot path: embedding gather-sum (midi_model.py:145-146),
+// inner-input builder (midi_model.py:126-131), RMSNorm (hf modeling_llama.py:62-67), RoPE
+// (hf :124-168), SwiGLU (hf :183), and their backward passes.  All arithmetic is fp32 on
+// bf16 storage with the reference's rounding points.  16-byte vector
+// accesses, one 128-thread CTA per row (rows are 2 KB at hidden=1024), grids sized in rows.
+#include "common.cuh"
+
+namespace {
+
+constexpr int ROW_THREADS = 128;
+constexpr int MAXV = 8;   // vectors of 8 bf16 per thread: hidden <= 128*8*8 = 8192
+
+// ---------------------------------------------------------------------------
+// embedding
+// ---------------------------------------------------------------------------
+// out[m, :] = bf16( sum_t fp32(table[ids[m, t], :]) )   -- one rounding (Appendix A.1)
+__global__ void embed_sum_fwd_kernel(const long long* __restrict__ ids, const bf16* __restrict__ table,
+                                     bf16* __restrict__ out, int T, int H, int V) {
+    const int m = blockIdx.x;
+    const long long* row_ids = ids + (size_t)m * T;
+    for (int v = threadIdx.x; v < H / 8; v += blockDim.x) {
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int t = 0; t < T; t++) {
+            long long id = row_ids[t];
+            if (id < 0 || id >= V) continue;
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4*>(table + (size_t)id * H + v * 8), f);
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[j] += f[j];
+        }
+        *reinterpret_cast<uint4*>(out + (size_t)m * H + v * 8) = pack8(acc);
+    }
+}
+
+// out[(e*Tin + 0), :] = hidden[e, :] ; out[(e*Tin + j), :] = table[ids[e, j-1], :]   (cat([hidden, embed(x)]))
+__global__ void inner_input_fwd_kernel(const bf16* __restrict__ hidden, const long long* __restrict__ ids,
+                                       const bf16* __restrict__ table, bf16* __restrict__ out, int Tin, int n_ids,
+                                       int has_hidden, int H, int V) {
+    const int r = blockIdx.x;
+    const int e = r / Tin, j = r % Tin;
+    const bf16* src;
+    if (has_hidden && j == 0) {
+        src = hidden + (size_t)e * H;
+    } else {
+        long long id = ids[(size_t)e * n_ids + (j - has_hidden)];
+        if (id < 0 || id >= V) id = 0;
+        src = table + (size_t)id * H;
+    }
+    for (int v = threadIdx.x; v < H / 8; v += blockDim.x)
+        *reinterpret_cast<uint4*>(out + (size_t)r * H + v * 8) = *reinterpret_cast<const uint4*>(src + v * 8);
+}
+
+// dhidden[e,:] (+)= dx[e*Tin, :]
+__global__ void inner_input_bwd_hidden_kernel(const bf16* __restrict__ dx, bf16* __restrict__ dhidden, int Tin, int H) {
+    const int e = blockIdx.x;
+    for (int v = threadIdx.x; v < H / 8; v += blockDim.x)
+        *reinterpret_cast<uint4*>(dhidden + (size_t)e * H + v * 8) =
+            *reinterpret_cast<const uint4*>(dx + (size_t)e * Tin * H + v * 8);
+}
+
+// ---- embedding backward: counting sort of the ids, then one segment-sum per (id, slice) ----
+// id i (flat index) reads gradient row  (i / per_row) * row_stride + (i % per_row) * row_inner + row_off
+__global__ void embed_hist_kernel(const long long* __restrict__ ids, int n, int V, int* __restrict__ counts) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        long long id = ids[i];
+        if (id >= 0 && id < V) atomicAdd(&counts[id], 1);
+    }
+}
+__global__ void embed_scan_kernel(const int* __restrict__ counts, int* __restrict__ offsets, int V) {
+    // single block exclusive scan; V <= 1024 * items
+    __shared__ int sh[1024];
+    const int items = (V + 1023) / 1024;
+    const int base = threadIdx.x * items;
+    int local = 0;
+    for (int k = 0; k < items; k++)
+        if (base + k < V) local += counts[base + k];
+    sh[threadIdx.x] = local;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        int v = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = sh[threadIdx.x] - local;
+    for (int k = 0; k < items; k++)
+        if (base + k < V) {
+            offsets[base + k] = run;
+            run += counts[base + k];
+        }
+    if (threadIdx.x == 1023) offsets[V] = sh[1023];
+}
+__global__ void embed_fill_kernel(const long long* __restrict__ ids, int n, int V, const int* __restrict__ offsets,
+                                  int* __restrict__ cursor, int* __restrict__ sorted) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        long long id = ids[i];
+        if (id >= 0 && id < V) {
+            int pos = atomicAdd(&cursor[id], 1);
+            sorted[offsets[id] + pos] = i;
+        }
+    }
+}
+// grid (V, SLICES): block (v, y) sums entries y, y+SLICES, ... of segment v and adds the partial to acc32[v,:]
+__global__ void embed_segsum_kernel(const int* __restrict__ offsets, const int* __restrict__ sorted,
+                                    const bf16* __restrict__ dout, float* __restrict__ acc32, int H, int per_row,
+                                    int row_stride, int row_inner, int row_off, int pad_id) {
+    const int v = blockIdx.x;
+    if (v == pad_id) return;   // padding_idx row receives zero gradient (hf nn.Embedding(padding_idx))
+    const int beg = offsets[v], end = offsets[v + 1];
+    if (beg + (int)blockIdx.y >= end) return;
+    for (int c = threadIdx.x; c < H / 8; c += blockDim.x) {
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int j = beg + blockIdx.y; j < end; j += gridDim.y) {
+            const int i = sorted[j];
+            const size_t row = (size_t)(i / per_row) * row_stride + (size_t)(i % per_row) * row_inner + row_off;
+            float f[8];
+            unpack8(ld_nc16(dout + row * H + c * 8), f);
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[k] += f[k];
+        }
+        float* dst = acc32 + (size_t)v * H + c * 8;
+#pragma unroll
+        for (int k = 0; k < 8; k++) atomicAdd(dst + k, acc[k]);
+    }
+}
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n, int accumulate) {
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+    for (; i < n; i += stride) {
+        float4 a = *reinterpret_cast<const float4*>(src + i);
+        bf162* o = reinterpret_cast<bf162*>(dst + i);
+        if (accumulate) {
+            float2 o0 = __bfloat1622float2(o[0]), o1 = __bfloat1622float2(o[1]);
+            a.x = bf16_round(a.x) + o0.x; a.y = bf16_round(a.y) + o0.y;
+            a.z = bf16_round(a.z) + o1.x; a.w = bf16_round(a.w) + o1.y;
+        }
+        o[0] = __floats2bfloat162_rn(a.x, a.y);
+        o[1] = __floats2bfloat162_rn(a.z, a.w);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// RMSNorm
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    float t = 0.f;
+    const int nw = blockDim.x >> 5;
+    for (int i = 0; i < nw; i++) t += sh[i];
+    return t;
+}
+
+// y = w * bf16(x * rsqrt(mean(x^2) + eps))  -- two roundings (Appendix A.2)
+template <int VPT>
+__global__ void __launch_bounds__(ROW_THREADS)
+rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
+                   float* __restrict__ rstd_out, int M, int H, float eps) {
+    __shared__ float sh[8];
+    const int nv = H / 8;
+    for (int m = blockIdx.x; m < M; m += gridDim.x) {
+        float xv[VPT][8];
+        float ss = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPT; k++) {
+            const int v = threadIdx.x + k * ROW_THREADS;
+            if (v < nv) {
+                unpack8(ld_nc16(x + (size_t)m * H + v * 8), xv[k]);
+#pragma unroll
+                for (int j = 0; j < 8; j++) ss += xv[k][j] * xv[k][j];
+            }
+        }
+        ss = block_sum(ss, sh);
+        const float rstd = rsqrtf(ss / (float)H + eps);
+        if (threadIdx.x == 0 && rstd_out) rstd_out[m] = rstd;
+#pragma unroll
+        for (int k = 0; k < VPT; k++) {
+            const int v = threadIdx.x + k * ROW_THREADS;
+            if (v < nv) {
+                float wv[8], o[8];
+                unpack8(*reinterpret_cast<const uint4*>(w + v * 8), wv);
+#pragma unroll
+                for (int j = 0; j < 8; j++) o[j] = wv[j] * bf16_round(xv[k][j] * rstd);
+                *reinterpret_cast<uint4*>(y + (size_t)m * H + v * 8) = pack8(o);
+            }
+        }
+    }
+}
+
+// dx = dres + rstd * (dn - n * mean(dn . n)),  dn = dy*w, n = x*rstd ;  dw_partial[block,:] = sum_rows dy * n
+template <int VPT>
+__global__ void __launch_bounds__(ROW_THREADS)
+rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
+                   const float* __restrict__ rstd_in, const bf16* __restrict__ dres, bf16* __restrict__ dx,
+                   float* __restrict__ dw_partial, int M, int H) {
+    __shared__ float sh[8];
+    const int nv = H / 8;
+    float dwacc[VPT][8];
+#pragma unroll
+    for (int k = 0; k < VPT; k++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) dwacc[k][j] = 0.f;
+    for (int m = blockIdx.x; m < M; m += gridDim.x) {
+        const float rstd = rstd_in[m];
+        float nn[VPT][8], dn[VPT][8];
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPT; k++) {
+            const int v = threadIdx.x + k * ROW_THREADS;
+            if (v < nv) {
+                float xv[8], dyv[8], wv[8];
+                unpack8(ld_nc16(x + (size_t)m * H + v * 8), xv);
+                unpack8(ld_nc16(dy + (size_t)m * H + v * 8), dyv);
+                unpack8(*reinterpret_cast<const uint4*>(w + v * 8), wv);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    nn[k][j] = xv[j] * rstd;
+                    dn[k][j] = dyv[j] * wv[j];
+                    dot += dn[k][j] * nn[k][j];
+                    dwacc[k][j] += dyv[j] * nn[k][j];
+                }
+            }
+        }
+        dot = block_sum(dot, sh) / (float)H;
+#pragma unroll
+        for (int k = 0; k < VPT; k++) {
+            const int v = threadIdx.x + k * ROW_THREADS;
+            if (v < nv) {
+                float o[8];
+                if (dres) unpack8(ld_nc16(dres + (size_t)m * H + v * 8), o);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) o[j] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++) o[j] += rstd * (dn[k][j] - nn[k][j] * dot);
+                *reinterpret_cast<uint4*>(dx + (size_t)m * H + v * 8) = pack8(o);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < VPT; k++) {
+        const int v = threadIdx.x + k * ROW_THREADS;
+        if (v < nv) {
+            float* dst = dw_partial + (size_t)blockIdx.x * H + v * 8;
+#pragma unroll
+            for (int j = 0; j < 8; j++) dst[j] = dwacc[k][j];
+        }
+    }
+}
+__global__ void colsum_partial_kernel(const float* __restrict__ partial, int nparts, int H, bf16* __restrict__ out,
+                                      int accumulate) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= H) return;
+    float s = 0.f;
+    for (int p = 0; p < nparts; p++) s += partial[(size_t)p * H + c];
+    if (accumulate) s = bf16_round(s) + __bfloat162float(out[c]);
+    out[c] = __float2bfloat16_rn(s);
+}
+
+// ---------------------------------------------------------------------------
+// RoPE
+// ---------------------------------------------------------------------------
+// cos/sin tables exactly as hf :124-135: fp32 pos * fp32(inv_freq buffer), fp32 cos/sin, cast to bf16.
+__global__ void rope_table_kernel(const float* __restrict__ inv_freq, int half, int n_pos, int pos0, const int* pos0_dev,
+                                  bf16* __restrict__ cos_t, bf16* __restrict__ sin_t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pos * half) return;
+    const int s = i / half, j = i % half;
+    const int base = pos0_dev ? *pos0_dev : pos0;
+    const float f = (float)(base + s) * inv_freq[j];
+    cos_t[i] = __float2bfloat16_rn(cosf(f));
+    sin_t[i] = __float2bfloat16_rn(sinf(f));
+}
+
+// In place on the q and k thirds of packed qkv rows [rows, 3*H]; position of row r = r % S.
+// forward : o1 = bf16(bf16(x1*c) + bf16(-x2*s)), o2 = bf16(bf16(x2*c) + bf16(x1*s))   (three roundings, A.4)
+// backward: dx1 = do1*c + do2*s, dx2 = do2*c - do1*s  (one rounding)
+template <bool BWD>
+__global__ void rope_kernel(bf16* __restrict__ qkv, const bf16* __restrict__ cos_t, const bf16* __restrict__ sin_t,
+                            int rows, int S, int H, int D, int ld) {
+    const int r = blockIdx.x;
+    const int s = r % S;
+    const int half = D / 2;
+    const int vec_per_head = half / 8;
+    const int heads2 = 2 * (H / D);   // q heads then k heads (k third starts at column H)
+    const int total = heads2 * vec_per_head;
+    bf16* row = qkv + (size_t)r * ld;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int hh = i / vec_per_head, v = i % vec_per_head;
+        bf16* p1 = row + (size_t)hh * D + v * 8;   // q heads occupy [0,H), k heads [H,2H): contiguous in hh*D
+        bf16* p2 = p1 + half;
+        float x1[8], x2[8], c[8], sn[8], o1[8], o2[8];
+        unpack8(*reinterpret_cast<const uint4*>(p1), x1);
+        unpack8(*reinterpret_cast<const uint4*>(p2), x2);
+        unpack8(*reinterpret_cast<const uint4*>(cos_t + (size_t)s * half + v * 8), c);
+        unpack8(*reinterpret_cast<const uint4*>(sin_t + (size_t)s * half + v * 8), sn);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (!BWD) {
+                o1[j] = bf16_round(x1[j] * c[j]) + bf16_round(-x2[j] * sn[j]);
+                o2[j] = bf16_round(x2[j] * c[j]) + bf16_round(x1[j] * sn[j]);
+            } else {
+                o1[j] = x1[j] * c[j] + x2[j] * sn[j];
+                o2[j] = x2[j] * c[j] - x1[j] * sn[j];
+            }
+        }
+        *reinterpret_cast<uint4*>(p1) = pack8(o1);
+        *reinterpret_cast<uint4*>(p2) = pack8(o2);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// SwiGLU on packed [rows, 2*I] = [gate | up]
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// act = bf16( bf16(silu(g)) * u )   (two roundings, A.6)
+__global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ act, size_t rows, int I) {
+    const size_t nvec = rows * (size_t)(I / 8);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / (I / 8);
+        const int c = (int)(i % (I / 8)) * 8;
+        float g[8], u[8], o[8];
+        unpack8(ld_nc16(gu + r * 2 * I + c), g);
+        unpack8(ld_nc16(gu + r * 2 * I + I + c), u);
+#pragma unroll
+        for (int j = 0; j < 8; j++) o[j] = bf16_round(g[j] * sigmoidf_(g[j])) * u[j];
+        *reinterpret_cast<uint4*>(act + r * I + c) = pack8(o);
+    }
+}
+// dg = dact * u * silu'(g), du = dact * silu(g)
+__global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, const bf16* __restrict__ dact, bf16* __restrict__ dgu,
+                                  size_t rows, int I) {
+    const size_t nvec = rows * (size_t)(I / 8);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / (I / 8);
+        const int c = (int)(i % (I / 8)) * 8;
+        float g[8], u[8], d[8], dg[8], du[8];
+        unpack8(ld_nc16(gu + r * 2 * I + c), g);
+        unpack8(ld_nc16(gu + r * 2 * I + I + c), u);
+        unpack8(ld_nc16(dact + r * I + c), d);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float sg = sigmoidf_(g[j]);
+            const float silu = g[j] * sg;
+            dg[j] = d[j] * u[j] * (sg * (1.f + g[j] * (1.f - sg)));
+            du[j] = d[j] * silu;
+        }
+        *reinterpret_cast<uint4*>(dgu + r * 2 * I + c) = pack8(dg);
+        *reinterpret_cast<uint4*>(dgu + r * 2 * I + I + c) = pack8(du);
+    }
+}
+
+inline int grid_for(size_t n_items, int threads, int per_sm = 16) {
+    size_t b = (n_items + threads - 1) / threads;
+    size_t cap = (size_t)b200_num_sms() * per_sm;
+    return (int)(b < cap ? (b ? b : 1) : cap);
+}
+
+}   // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" int b200_embed_sum_fwd(const long long* ids, const void* table, void* out, int M, int T, int H, int V,
+                                  cudaStream_t stream) {
+    B200_CHECK_ARG(H % 8 == 0 && M >= 0, "embed_sum_fwd: H must be a multiple of 8");
+    if (M == 0) return B200_OK;
+    embed_sum_fwd_kernel<<<M, ROW_THREADS, 0, stream>>>(ids, (const bf16*)table, (bf16*)out, T, H, V);
+    B200_CHECK_LAUNCH("embed_sum_fwd");
+    return B200_OK;
+}
+
+extern "C" int b200_inner_input_fwd(const void* hidden, const long long* ids, const void* table, void* out, int n_events,
+                                    int n_ids, int H, int V, cudaStream_t stream) {
+    B200_CHECK_ARG(H % 8 == 0, "inner_input_fwd: H must be a multiple of 8");
+    const int has_hidden = hidden != nullptr;
+    const int Tin = n_ids + has_hidden;
+    if (n_events == 0 || Tin == 0) return B200_OK;
+    inner_input_fwd_kernel<<<n_events * Tin, ROW_THREADS, 0, stream>>>((const bf16*)hidden, ids, (const bf16*)table,
+                                                                       (bf16*)out, Tin, n_ids, has_hidden, H, V);
+    B200_CHECK_LAUNCH("inner_input_fwd");
+    return B200_OK;
+}
+
+extern "C" int b200_inner_input_bwd_hidden(const void* dx, void* dhidden, int n_events, int Tin, int H,
+                                           cudaStream_t stream) {
+    if (n_events == 0) return B200_OK;
+    inner_input_bwd_hidden_kernel<<<n_events, ROW_THREADS, 0, stream>>>((const bf16*)dx, (bf16*)dhidden, Tin, H);
+    B200_CHECK_LAUNCH("inner_input_bwd_hidden");
+    return B200_OK;
+}
+
+extern "C" size_t b200_embed_bwd_workspace_bytes(int n_ids, int V, int H) {
+    return (size_t)(3 * (V + 1) + n_ids) * sizeof(int) + 256 + (size_t)V * H * sizeof(float);
+}
+
+// dtable[v,:] (+)= sum over ids i == v of dout[row(i), :]; padding row gets zero (or is left untouched when accumulating)
+extern "C" int b200_embed_bwd(const long long* ids, int n_ids, const void* dout, void* dtable, int V, int H, int per_row,
+                              int row_stride, int row_inner, int row_off, int pad_id, int accumulate, void* workspace,
+                              size_t workspace_bytes, cudaStream_t stream) {
+    B200_CHECK_ARG(H % 8 == 0, "embed_bwd: H must be a multiple of 8");
+    B200_CHECK_ARG(workspace_bytes >= b200_embed_bwd_workspace_bytes(n_ids, V, H), "embed_bwd: workspace too small");
+    B200_CHECK_ARG(V <= 1024 * 64, "embed_bwd: vocabulary too large");
+    int* counts = (int*)workspace;
+    int* offsets = counts + (V + 1);
+    int* cursor = offsets + (V + 1);
+    int* sorted = cursor + (V + 1);
+    float* acc32 = (float*)(((uintptr_t)(sorted + n_ids) + 255) & ~(uintptr_t)255);
+    B200_CUDA(cudaMemsetAsync(counts, 0, sizeof(int) * 3 * (V + 1), stream), "embed_bwd memset");
+    B200_CUDA(cudaMemsetAsync(acc32, 0, sizeof(float) * (size_t)V * H, stream), "embed_bwd memset");
+    if (n_ids > 0) {
+        const int g = grid_for(n_ids, 256);
+        embed_hist_kernel<<<g, 256, 0, stream>>>(ids, n_ids, V, counts);
+        embed_scan_kernel<<<1, 1024, 0, stream>>>(counts, offsets, V);
+        embed_fill_kernel<<<g, 256, 0, stream>>>(ids, n_ids, V, offsets, cursor, sorted);
+        dim3 grid(V, 32);
+        embed_segsum_kernel<<<grid, ROW_THREADS, 0, stream>>>(offsets, sorted, (const bf16*)dout, acc32, H, per_row,
+                                                              row_stride, row_inner, row_off, pad_id);
+    }
+    const size_t n = (size_t)V * H;
+    f32_to_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(acc32, (bf16*)dtable, n, accumulate);
+    B200_CHECK_LAUNCH("embed_bwd");
+    return B200_OK;
+}
+
+extern "C" int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int M, int H, float eps,
+                                cudaStream_t stream) {
+    B200_CHECK_ARG(H % 8 == 0 && H <= ROW_THREADS * 8 * MAXV, "rmsnorm_fwd: unsupported hidden size %d", H);
+    if (M == 0) return B200_OK;
+    const int grid = M < b200_num_sms() * 16 ? M : b200_num_sms() * 16;
+    const int vpt = (H / 8 + ROW_THREADS - 1) / ROW_THREADS;
+#define B200_RMS_FWD(V) rmsnorm_fwd_kernel<V><<<grid, ROW_THREADS, 0, stream>>>((const bf16*)x, (const bf16*)w, (bf16*)y, rstd, M, H, eps)
+    if (vpt <= 1) B200_RMS_FWD(1); else if (vpt <= 2) B200_RMS_FWD(2); else if (vpt <= 4) B200_RMS_FWD(4); else B200_RMS_FWD(8);
+#undef B200_RMS_FWD
+    B200_CHECK_LAUNCH("rmsnorm_fwd");
+    return B200_OK;
+}
+
+extern "C" int b200_rmsnorm_bwd_parts(void) { return b200_num_sms() * 4; }
+
+// workspace: float[b200_rmsnorm_bwd_parts() * H]
+extern "C" int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres,
+                                void* dx, void* dw, int M, int H, int accumulate_dw, void* workspace,
+                                size_t workspace_bytes, cudaStream_t stream) {
+    B200_CHECK_ARG(H % 8 == 0 && H <= ROW_THREADS * 8 * MAXV, "rmsnorm_bwd: unsupported hidden size %d", H);
+    const int parts = b200_rmsnorm_bwd_parts();
+    B200_CHECK_ARG(workspace_bytes >= (size_t)parts * H * sizeof(float), "rmsnorm_bwd: workspace too small");
+    if (M == 0) return B200_OK;
+    const int vpt = (H / 8 + ROW_THREADS - 1) / ROW_THREADS;
+#define B200_RMS_BWD(V) rmsnorm_bwd_kernel<V><<<parts, ROW_THREADS, 0, stream>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, rstd, (const bf16*)dres, (bf16*)dx, (float*)workspace, M, H)
+    if (vpt <= 1) B200_RMS_BWD(1); else if (vpt <= 2) B200_RMS_BWD(2); else if (vpt <= 4) B200_RMS_BWD(4); else B200_RMS_BWD(8);
+#undef B200_RMS_BWD
+    B200_CHECK_LAUNCH("rmsnorm_bwd");
+    if (dw) {
+        colsum_partial_kernel<<<(H + 127) / 128, 128, 0, stream>>>((const float*)workspace, parts, H, (bf16*)dw,
+                                                                  accumulate_dw);
+        B200_CHECK_LAUNCH("rmsnorm_bwd_dw");
+    }
+    return B200_OK;
+}
+
+extern "C" int b200_rope_table(const float* inv_freq, int half, int n_pos, int pos0, const int* pos0_dev, void* cos_t,
+                               void* sin_t, cudaStream_t stream) {
+    if (n_pos <= 0) return B200_OK;
+    const int n = n_pos * half;
+    rope_table_kernel<<<(n + 255) / 256, 256, 0, stream>>>(inv_freq, half, n_pos, pos0, pos0_dev, (bf16*)cos_t,
+                                                          (bf16*)sin_t);
+    B200_CHECK_LAUNCH("rope_table");
+    return B200_OK;
+}
+
+extern "C" int b200_rope_qk(void* qkv, const void* cos_t, const void* sin_t, int rows, int S, int H, int D, int ld,
+                            int backward, cudaStream_t stream) {
+    B200_CHECK_ARG(D % 16 == 0 && H % D == 0 && ld % 8 == 0, "rope: head_dim must be a multiple of 16");
+    if (rows == 0) return B200_OK;
+    if (backward)
+        rope_kernel<true><<<rows, ROW_THREADS, 0, stream>>>((bf16*)qkv, (const bf16*)cos_t, (const bf16*)sin_t, rows, S, H, D, ld);
+    else
+        rope_kernel<false><<<rows, ROW_THREADS, 0, stream>>>((bf16*)qkv, (const bf16*)cos_t, (const bf16*)sin_t, rows, S, H, D, ld);
+    B200_CHECK_LAUNCH("rope");
+    return B200_OK;
+}
+
+extern "C" int b200_swiglu_fwd(const void* gu, void* act, long long rows, int I, cudaStream_t stream) {
+    B200_CHECK_ARG(I % 8 == 0, "swiglu: intermediate size must be a multiple of 8");
+    if (rows == 0) return B200_OK;
+    swiglu_fwd_kernel<<<grid_for((size_t)rows * (I / 8), 256), 256, 0, stream>>>((const bf16*)gu, (bf16*)act, rows, I);
+    B200_CHECK_LAUNCH("swiglu_fwd");
+    return B200_OK;
+}
+
+extern "C" int b200_swiglu_bwd(const void* gu, const void* dact, void* dgu, long long rows, int I, cudaStream_t stream) {
+    B200_CHECK_ARG(I % 8 == 0, "swiglu: intermediate size must be a multiple of 8");
+    if (rows == 0) return B200_OK;
+    swiglu_bwd_kernel<<<grid_for((size_t)rows * (I / 8), 256), 256, 0, stream>>>((const bf16*)gu, (const bf16*)dact,
+                                                                                 (bf16*)dgu, rows, I);
+    B200_CHECK_LAUNCH("swiglu_bwd");
+    return B200_OK;
+}

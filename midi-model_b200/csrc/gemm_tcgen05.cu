@@ -1,0 +1,497 @@
+// bf16 GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands
+// staged by TMA into 128B-swizzled shared memory), persistent, warp-specialised:
+//   warp 0     : TMA producer (one elected lane)
+//   warp 1     : TMEM allocator + MMA issuer (one elected lane)
+//   warps 2..5 : epilogue (TMEM -> registers -> fused epilogue -> global)
+// D[M,N] = A . B^T with fp32 accumulation.  Each operand is either "K-major"
+// (row-major [rows, K], what nn.Linear's forward needs: hf modeling_llama.py:177-184,
+// 238-264) or "MN-major" (stored [K, rows]); the latter serves dgrad (B = W as stored)
+// and wgrad (A = dY, B = X as stored) without any transposed copies.
+// Epilogues: bf16 store; bf16 store + residual (two roundings, like `x + o_proj(..)`
+// in hf :325/:331); fp32 split-K partials reduced by splitk_reduce_kernel.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARP0 = 2;
+
+enum { EPI_STORE = 0, EPI_RESIDUAL = 1, EPI_PARTIAL_F32 = 2 };
+
+struct GemmParams {
+    bf16* C;
+    const bf16* R;
+    float* ws;
+    int M, N, K;
+    int ldc, ldr;
+    int epilogue;
+    int splits, kb_per_split, num_kb;
+    int m_tiles, n_tiles;
+    uint32_t mn_lbo, mn_sbo;   // MN-major descriptor byte offsets (overridable for bring-up)
+};
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (error return on the host), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("b200 gemm: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+        "%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (sm_100 format): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
+// version=1 [46,48) | layout_type [61,64) (2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BLOCK_N>
+struct SmemLayout {
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
+    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;   // 16/32 KB
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+    static constexpr int BAR_BYTES = 1024;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024 for manual alignment
+};
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    using L = SmemLayout<BLOCK_N>;
+    constexpr int STAGES = L::STAGES;
+    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;   // double-buffered accumulator (256 or 512 columns)
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* bar_base = smem + STAGES * L::STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_items = p.m_tiles * p.n_tiles * p.splits;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+                const int split = item % p.splits;
+                const int t = item / p.splits;
+                const int n_blk = t % p.n_tiles, m_blk = t / p.n_tiles;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+                for (int kb = kb0; kb < kb1; kb++) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sA = smem + stage * L::STAGE_BYTES;
+                    uint8_t* sB = sA + L::A_BYTES;
+                    mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                    if (!A_MN) {
+                        tma_load_2d(sA, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < BLOCK_M / 64; c++)
+                            tma_load_2d(sA + c * (BLOCK_K * 128), &tmA, &full_bar[stage], m_blk * BLOCK_M + c * 64, kb * BLOCK_K);
+                    }
+                    if (!B_MN) {
+                        tma_load_2d(sB, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < BLOCK_N / 64; c++)
+                            tma_load_2d(sB + c * (BLOCK_K * 128), &tmB, &full_bar[stage], n_blk * BLOCK_N + c * 64, kb * BLOCK_K);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, A_MN, B_MN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+                const int split = item % p.splits;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                for (int kb = kb0; kb < kb1; kb++) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sA = smem_u32(smem + stage * L::STAGE_BYTES);
+                    const uint32_t sB = sA + L::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
+                        const uint64_t adesc = A_MN ? make_smem_desc(sA + k * (UMMA_K * 128), p.mn_lbo, p.mn_sbo)
+                                                    : make_smem_desc(sA + k * (UMMA_K * 2), 16, 1024);
+                        const uint64_t bdesc = B_MN ? make_smem_desc(sB + k * (UMMA_K * 128), p.mn_lbo, p.mn_sbo)
+                                                    : make_smem_desc(sB + k * (UMMA_K * 2), 16, 1024);
+                        umma_f16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);          // accumulator ready for the epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        const int quarter = warp & 3;               // TMEM lane quarter this warp may access
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+            const int split = item % p.splits;
+            const int t = item / p.splits;
+            const int n_blk = t % p.n_tiles, m_blk = t / p.n_tiles;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const int row = m_blk * BLOCK_M + quarter * 32 + lane;
+            const bool row_ok = row < p.M;
+            const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; c++) {
+                uint32_t r[32];
+                tmem_ld32(taddr + c * 32, r);
+                tmem_ld_wait();
+                const int col0 = n_blk * BLOCK_N + c * 32;
+                if (row_ok && col0 < p.N) {
+                    if (p.epilogue == EPI_PARTIAL_F32) {
+                        float* dst = p.ws + ((size_t)split * p.M + row) * p.N + col0;
+#pragma unroll
+                        for (int v = 0; v < 8; v++) {
+                            if (col0 + v * 4 < p.N) {
+                                uint4 u = make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+                                *reinterpret_cast<uint4*>(dst + v * 4) = u;
+                            }
+                        }
+                    } else {
+                        bf16* dst = p.C + (size_t)row * p.ldc + col0;
+                        const bf16* res = (p.epilogue == EPI_RESIDUAL) ? p.R + (size_t)row * p.ldr + col0 : nullptr;
+#pragma unroll
+                        for (int v = 0; v < 4; v++) {
+                            if (col0 + v * 8 < p.N) {
+                                float f[8];
+#pragma unroll
+                                for (int j = 0; j < 8; j++) f[j] = __uint_as_float(r[8 * v + j]);
+                                if (res != nullptr) {
+                                    float rr[8];
+                                    unpack8(*reinterpret_cast<const uint4*>(res + v * 8), rr);
+#pragma unroll
+                                    for (int j = 0; j < 8; j++) f[j] = bf16_round(f[j]) + rr[j];
+                                }
+                                *reinterpret_cast<uint4*>(dst + v * 8) = pack8(f);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, bf16* __restrict__ out, size_t n, int splits,
+                                     int accumulate) {
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+    for (; i < n; i += stride) {
+        float4 a = *reinterpret_cast<const float4*>(ws + i);
+        for (int s = 1; s < splits; s++) {
+            float4 b = *reinterpret_cast<const float4*>(ws + (size_t)s * n + i);
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        bf162* o = reinterpret_cast<bf162*>(out + i);
+        if (accumulate) {   // grad accumulation across micro-batches: bf16 += bf16(new), like autograd's AccumulateGrad
+            float2 o0 = __bfloat1622float2(o[0]), o1 = __bfloat1622float2(o[1]);
+            a.x = bf16_round(a.x) + o0.x; a.y = bf16_round(a.y) + o0.y;
+            a.z = bf16_round(a.z) + o1.x; a.w = bf16_round(a.w) + o1.y;
+        }
+        o[0] = __floats2bfloat162_rn(a.x, a.y);
+        o[1] = __floats2bfloat162_rn(a.z, a.w);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side: tensor maps through the driver entry point (no -lcuda link dependency)
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of pitch `ld` elements, 128B swizzle, zero OOB fill.
+int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+              uint32_t box_outer) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        b200_set_error("gemm: cuTensorMapEncodeTiled entry point unavailable");
+        return B200_ERR_CUDA;
+    }
+    cuuint64_t gdim[2] = {inner, outer};
+    cuuint64_t gstride[1] = {ld * 2};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        b200_set_error("gemm: cuTensorMapEncodeTiled failed (%d) ptr=%p inner=%llu outer=%llu ld=%llu", (int)r, ptr,
+                       (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);
+        return B200_ERR_CUDA;
+    }
+    return B200_OK;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+    using L = SmemLayout<BLOCK_N>;
+    auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN>;
+    static bool configured = false;
+    if (!configured) {
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL), "gemm smem attr");
+        configured = true;
+    }
+    const int items = p.m_tiles * p.n_tiles * p.splits;
+    const int grid = items < b200_num_sms() ? items : b200_num_sms();
+    kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, p);
+    B200_CHECK_LAUNCH("gemm_tcgen05");
+    return B200_OK;
+}
+
+}   // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI (declared in include/midi_b200.h)
+// ---------------------------------------------------------------------------
+extern "C" size_t b200_gemm_workspace_bytes(int M, int N, int splits) {
+    return splits > 1 ? (size_t)splits * M * N * sizeof(float) : 0;
+}
+
+// Suggest a split-K factor for an [M,N,K] problem so that at least ~one wave of CTAs is busy.
+extern "C" int b200_gemm_suggest_splits(int M, int N, int K, int block_n) {
+    const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + block_n - 1) / block_n);
+    const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+    int sms = b200_num_sms();
+    if (tiles >= sms) return 1;
+    int s = sms / tiles;
+    const int max_by_k = num_kb / 8 > 0 ? num_kb / 8 : 1;   // keep >= 8 k-blocks per split
+    if (s > max_by_k) s = max_by_k;
+    if (s > 16) s = 16;
+    return s < 1 ? 1 : s;
+}
+
+extern "C" int b200_gemm_bf16(const void* A, const void* B, void* C, const void* R, int M, int N, int K, int lda, int ldb,
+                              int ldc, int ldr, int a_mn_major, int b_mn_major, int accumulate, int block_n, int splits,
+                              void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    B200_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+    // N need not be a multiple of 8: B rows >= N are out of bounds for the tensor map (zero-filled), so the
+    // epilogue may store whole 16-byte vectors up to roundup8(N) (zeros) as long as the row pitch covers them.
+    const int N8 = (N + 7) / 8 * 8;
+    B200_CHECK_ARG(ldc % 8 == 0 && ldc >= N8, "gemm: ldc (%d) must be a multiple of 8 and >= roundup8(N=%d)", ldc, N);
+    B200_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 (16-byte TMA strides)");
+    B200_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0),
+                   "gemm: operands must be 16-byte aligned");
+    B200_CHECK_ARG(block_n == 128 || block_n == 256, "gemm: block_n must be 128 or 256");
+    B200_CHECK_ARG(R == nullptr || (ldr % 8 == 0 && (uintptr_t)R % 16 == 0 && N % 8 == 0),
+                   "gemm: residual must be 16-byte aligned and N a multiple of 8");
+    if (splits < 1) splits = 1;
+    GemmParams p;
+    p.C = (bf16*)C;
+    p.R = (const bf16*)R;
+    p.ws = (float*)workspace;
+    p.M = M; p.N = N8; p.K = K;
+    p.ldc = ldc; p.ldr = ldr;
+    p.num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+    if (splits > p.num_kb) splits = p.num_kb;
+    p.kb_per_split = (p.num_kb + splits - 1) / splits;
+    splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;   // no empty splits
+    p.splits = splits;
+    p.m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    p.n_tiles = (N + block_n - 1) / block_n;
+    p.mn_lbo = BLOCK_K * 128;
+    p.mn_sbo = 1024;
+    if (const char* e = getenv("B200_GEMM_MN_SWAP")) {
+        if (e[0] == '1') { p.mn_lbo = 1024; p.mn_sbo = BLOCK_K * 128; }
+    }
+    if (splits > 1 || accumulate) {
+        B200_CHECK_ARG(R == nullptr, "gemm: split-K/accumulate cannot be combined with a residual epilogue");
+        B200_CHECK_ARG(ldc == N && N % 8 == 0, "gemm: split-K/accumulate output must be contiguous (ldc == N, N %% 8 == 0)");
+        const size_t need = (size_t)splits * M * N * sizeof(float);
+        B200_CHECK_ARG(workspace != nullptr && workspace_bytes >= need, "gemm: workspace too small (%zu < %zu)",
+                       workspace_bytes, need);
+        p.epilogue = EPI_PARTIAL_F32;
+    } else {
+        p.epilogue = R ? EPI_RESIDUAL : EPI_STORE;
+    }
+
+    CUtensorMap tmA, tmB;
+    int rc;
+    if (!a_mn_major) rc = make_tmap(&tmA, A, K, M, lda, BLOCK_K, BLOCK_M);
+    else             rc = make_tmap(&tmA, A, M, K, lda, 64, BLOCK_K);
+    if (rc) return rc;
+    if (!b_mn_major) rc = make_tmap(&tmB, B, K, N, ldb, BLOCK_K, block_n);
+    else             rc = make_tmap(&tmB, B, N, K, ldb, 64, BLOCK_K);
+    if (rc) return rc;
+
+#define B200_DISPATCH(BN)                                                                   \
+    do {                                                                                    \
+        if (!a_mn_major && !b_mn_major) rc = launch<BN, false, false>(tmA, tmB, p, stream);  \
+        else if (!a_mn_major && b_mn_major) rc = launch<BN, false, true>(tmA, tmB, p, stream); \
+        else if (a_mn_major && b_mn_major) rc = launch<BN, true, true>(tmA, tmB, p, stream);  \
+        else rc = launch<BN, true, false>(tmA, tmB, p, stream);                              \
+    } while (0)
+    if (block_n == 256) B200_DISPATCH(256);
+    else B200_DISPATCH(128);
+#undef B200_DISPATCH
+    if (rc) return rc;
+
+    if (p.epilogue == EPI_PARTIAL_F32) {
+        const size_t n = (size_t)M * N;
+        int blocks = (int)((n / 4 + 255) / 256);
+        if (blocks > b200_num_sms() * 8) blocks = b200_num_sms() * 8;
+        splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(p.ws, p.C, n, splits, accumulate);
+        B200_CHECK_LAUNCH("splitk_reduce");
+    }
+    return B200_OK;
+}

@@ -1,0 +1,269 @@
+"""Layer-by-layer execution of the two Llama stacks of MIDIModel on the sm_100a kernels.
+
+`ParamStore` keeps every parameter (and gradient) of the model as a view into ONE flat bf16
+buffer, in `named_parameters()` order.  Because q/k/v and gate/up projections are adjacent in
+that order, the fused `[3H, H]` QKV and `[2I, H]` gate|up weights are *views* -- the reference's
+`state_dict` keys stay the source of truth (checkpoint row) and no packed
+copies exist.  One flat gradient buffer means one all-reduce and one AdamW launch per step.
+
+`StackEngine` runs forward (saving exactly what backward needs) and an explicit backward; there
+is no autograd graph inside -- `autograd.Function`s in midi_model.py wrap whole stacks.
+Math per layer: hf modeling_llama.py:303-332; rounding points: SURVEY.md Appendix A.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from . import lib, ops
+
+BF16 = torch.bfloat16
+ALIGN = 256   # elements; AdamW's no-decay flags are per 256-element block
+
+
+class ParamStore:
+    def __init__(self, module: torch.nn.Module):
+        named = list(module.named_parameters())
+        if not named:
+            raise lib.B200Error("model has no parameters")
+        dev = named[0][1].device
+        for n, p in named:
+            if p.device != dev or p.dtype != BF16 or not p.is_cuda:
+                raise lib.B200Error(f"parameter {n} is {p.dtype} on {p.device}: the B200 path needs the whole model in "
+                                    "bfloat16 on one CUDA device (model.to('cuda', dtype=torch.bfloat16)); no fallback")
+        self.device = dev
+        self.names = [n for n, _ in named]
+        self.offsets = {}
+        off = 0
+        for n, p in named:
+            self.offsets[n] = off
+            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=BF16, device=dev)
+        self.gflat = torch.zeros(off, dtype=BF16, device=dev)
+        self.views = {}
+        self.gviews = {}
+        with torch.no_grad():
+            for n, p in named:
+                o = self.offsets[n]
+                v = self.flat[o:o + p.numel()].view(p.shape)
+                v.copy_(p.data)
+                p.data = v
+                self.views[n] = v
+                self.gviews[n] = self.gflat[o:o + p.numel()].view(p.shape)
+        self._params = dict(named)
+        # no-decay flags (train.py:123-131: names containing 'bias' or 'norm')
+        flags = torch.zeros(off // ALIGN, dtype=torch.uint8)
+        for n, p in named:
+            if "bias" in n or "norm" in n:
+                o = self.offsets[n] // ALIGN
+                flags[o:o + (p.numel() + ALIGN - 1) // ALIGN] = 1
+        self.nodecay = flags.to(dev)
+
+    def valid(self) -> bool:
+        """False once somebody re-created the parameters (.to(dtype), .cuda(), ...)."""
+        for n in (self.names[0], self.names[-1]):
+            if self._params[n].data_ptr() != self.views[n].data_ptr():
+                return False
+        return True
+
+    def fused(self, names: List[str]) -> torch.Tensor:
+        """[sum(rows), cols] view over adjacent 2-D parameters (q|k|v or gate|up)."""
+        first = self.views[names[0]]
+        o = self.offsets[names[0]]
+        rows = 0
+        for n in names:
+            v = self.views[n]
+            if self.offsets[n] != o + rows * first.shape[1] or v.shape[1] != first.shape[1]:
+                raise lib.B200Error(f"parameters {names} are not adjacent in the flat buffer")
+            rows += v.shape[0]
+        return self.flat[o:o + rows * first.shape[1]].view(rows, first.shape[1])
+
+    def fused_grad(self, names: List[str]) -> torch.Tensor:
+        first = self.views[names[0]]
+        o = self.offsets[names[0]]
+        rows = sum(self.views[n].shape[0] for n in names)
+        return self.gflat[o:o + rows * first.shape[1]].view(rows, first.shape[1])
+
+    def publish_grads(self):
+        """Expose the flat gradient buffer as `.grad` of every parameter (for train.py / torch optimizers)."""
+        for n, p in self._params.items():
+            if p.requires_grad:
+                p.grad = self.gviews[n]
+
+    def zero_grad(self):
+        self.gflat.zero_()
+
+
+@dataclass
+class StackCfg:
+    prefix: str
+    n_layer: int
+    n_head: int
+    hidden: int
+    inner: int
+    eps: float
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden // self.n_head
+
+
+class LayerW:
+    __slots__ = ("qkv", "o", "gu", "down", "ln1", "ln2")
+
+
+class LayerG:
+    __slots__ = ("qkv", "o", "gu", "down", "ln1", "ln2")
+
+
+class StackGrads:
+    """Gradient views of one stack inside a flat buffer laid out like ParamStore.flat (offset by `base`)."""
+
+    def __init__(self, store: "ParamStore", cfg: "StackCfg", buf: torch.Tensor, base: int):
+        p = cfg.prefix
+        H = cfg.hidden
+
+        def view(name, rows=None):
+            v = store.views[name]
+            o = store.offsets[name] - base
+            if rows is None:
+                return buf[o:o + v.numel()].view(v.shape)
+            return buf[o:o + rows * v.shape[1]].view(rows, v.shape[1])
+
+        self.layers = []
+        for l in range(cfg.n_layer):
+            a = f"{p}.layers.{l}.self_attn."
+            m = f"{p}.layers.{l}.mlp."
+            g = LayerG()
+            g.qkv = view(a + "q_proj.weight", 3 * H)
+            g.o = view(a + "o_proj.weight")
+            g.gu = view(m + "gate_proj.weight", 2 * cfg.inner)
+            g.down = view(m + "down_proj.weight")
+            g.ln1 = view(f"{p}.layers.{l}.input_layernorm.weight")
+            g.ln2 = view(f"{p}.layers.{l}.post_attention_layernorm.weight")
+            self.layers.append(g)
+        self.norm = view(f"{p}.norm.weight")
+        self.embed = view(f"{p}.embed_tokens.weight")
+        self.buf, self.base = buf, base
+
+    def named(self, store: "ParamStore", names):
+        """name -> gradient view, for handing gradients back to autograd."""
+        out = []
+        for n in names:
+            v = store.views[n]
+            o = store.offsets[n] - self.base
+            out.append(self.buf[o:o + v.numel()].view(v.shape))
+        return out
+
+
+class StackEngine:
+    """One Llama stack (outer `net`: causal over events; inner `net_token`: causal over <= 8 tokens per event)."""
+
+    def __init__(self, store: ParamStore, cfg: StackCfg, tiny_attention: bool):
+        self.cfg = cfg
+        self.store = store
+        self.tiny = tiny_attention
+        p = cfg.prefix
+        self.layers: List[LayerW] = []
+        for l in range(cfg.n_layer):
+            a = f"{p}.layers.{l}.self_attn."
+            m = f"{p}.layers.{l}.mlp."
+            w = LayerW()
+            qkv_n = [a + "q_proj.weight", a + "k_proj.weight", a + "v_proj.weight"]
+            gu_n = [m + "gate_proj.weight", m + "up_proj.weight"]
+            w.qkv = store.fused(qkv_n)
+            w.gu = store.fused(gu_n)
+            w.o = store.views[a + "o_proj.weight"]
+            w.down = store.views[m + "down_proj.weight"]
+            w.ln1 = store.views[f"{p}.layers.{l}.input_layernorm.weight"]
+            w.ln2 = store.views[f"{p}.layers.{l}.post_attention_layernorm.weight"]
+            self.layers.append(w)
+        self.norm = store.views[f"{p}.norm.weight"]
+        self.embed = store.views[f"{p}.embed_tokens.weight"]
+        self.names = [n for n in store.names if n.startswith(p + ".")]
+        self.seg_start = store.offsets[self.names[0]]
+        last = self.names[-1]
+        self.seg_end = store.offsets[last] + (store.views[last].numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.main_grads = StackGrads(store, cfg, store.gflat, 0)
+        if tiny_attention and cfg.head_dim != 256:
+            raise lib.B200Error(f"inner stack head_dim {cfg.head_dim} unsupported (kernels are built for 256)")
+        if not tiny_attention and cfg.head_dim != 64:
+            raise lib.B200Error(f"outer stack head_dim {cfg.head_dim} unsupported (kernels are built for 64)")
+
+    def fresh_grads(self) -> StackGrads:
+        """A private gradient buffer for this stack (autograd mode hands these tensors to torch)."""
+        buf = torch.empty(self.seg_end - self.seg_start, dtype=BF16, device=self.store.device)
+        return StackGrads(self.store, self.cfg, buf, self.seg_start)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor, n_seq: int, S: int, inv_freq: torch.Tensor, save: bool):
+        """x: [n_seq * S, H] inputs_embeds (row-major, sequences contiguous) -> (final-normed hidden, saved)."""
+        c = self.cfg
+        H, D, nh = c.hidden, c.head_dim, c.n_head
+        cos, sin = ops.rope_table(inv_freq, S)
+        saved = [] if save else None
+        for w in self.layers:
+            n1, rstd1 = ops.rmsnorm(x, w.ln1, c.eps, want_rstd=True)
+            qkv = ops.linear(n1, w.qkv)
+            ops.rope_qk_(qkv, cos, sin, S, H, D)
+            if self.tiny:
+                attn, lse = ops.attn_tiny_fwd(qkv, n_seq, S, nh, D), None
+            else:
+                attn, lse = ops.attn_causal_fwd(qkv, n_seq, S, nh, D, want_lse=save)
+            h = ops.linear(attn, w.o, residual=x)
+            n2, rstd2 = ops.rmsnorm(h, w.ln2, c.eps, want_rstd=True)
+            gu = ops.linear(n2, w.gu)
+            act = ops.swiglu(gu)
+            x_next = ops.linear(act, w.down, residual=h)
+            if save:
+                saved.append((x, n1, rstd1, qkv, attn, lse, h, n2, rstd2, gu, act))
+            x = x_next
+        y, rstd_f = ops.rmsnorm(x, self.norm, c.eps, want_rstd=True)
+        sv = dict(layers=saved, x_last=x, rstd_f=rstd_f, n_seq=n_seq, S=S, cos=cos, sin=sin) if save else None
+        return y, sv
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, sv: dict, dy: torch.Tensor, grads: StackGrads, accumulate: bool = False) -> torch.Tensor:
+        """dy: grad of the final-normed output.  Writes (or accumulates) every weight gradient of the stack into
+        `grads` and returns the gradient w.r.t. the stack input (inputs_embeds)."""
+        c = self.cfg
+        H, D, nh = c.hidden, c.head_dim, c.n_head
+        if sv is None or sv["layers"] is None:
+            raise lib.B200Error("backward called without a saved forward")
+        n_seq, S, cos, sin = sv["n_seq"], sv["S"], sv["cos"], sv["sin"]
+        dx = ops.rmsnorm_bwd(dy, sv["x_last"], self.norm, sv["rstd_f"], None, grads.norm, accumulate)
+        for li in range(len(self.layers) - 1, -1, -1):
+            w = self.layers[li]
+            g = grads.layers[li]
+            x, n1, rstd1, qkv, attn, lse, h, n2, rstd2, gu, act = sv["layers"][li]
+            sv["layers"][li] = None   # free as we go
+            # ---- MLP block: x_out = h + down(act)
+            dact = ops.linear_dgrad(dx, w.down)
+            ops.linear_wgrad(dx, act, g.down, accumulate)
+            del act
+            dgu = ops.swiglu_bwd(gu, dact)
+            del dact, gu
+            dn2 = ops.linear_dgrad(dgu, w.gu)
+            ops.linear_wgrad(dgu, n2, g.gu, accumulate)
+            del dgu, n2
+            dh = ops.rmsnorm_bwd(dn2, h, w.ln2, rstd2, dx, g.ln2, accumulate)
+            del dn2, h, dx
+            # ---- attention block: h = x + o(attn)
+            dattn = ops.linear_dgrad(dh, w.o)
+            ops.linear_wgrad(dh, attn, g.o, accumulate)
+            if self.tiny:
+                dqkv = ops.attn_tiny_bwd(qkv, dattn, n_seq, S, nh, D)
+            else:
+                dqkv = ops.attn_causal_bwd(qkv, attn, dattn, lse, n_seq, S, nh, D)
+            del dattn, attn, qkv
+            ops.rope_qk_(dqkv, cos, sin, S, H, D, backward=True)
+            dn1 = ops.linear_dgrad(dqkv, w.qkv)
+            ops.linear_wgrad(dqkv, n1, g.qkv, accumulate)
+            del dqkv, n1
+            dx = ops.rmsnorm_bwd(dn1, x, w.ln1, rstd1, dh, g.ln1, accumulate)
+            del dn1, dh, x
+        sv["layers"] = None
+        return dx

@@ -1,0 +1,465 @@
+"""Drop-in `midi_model` module: B200-native MIDIModel.
+
+Place this directory ahead of the reference checkout on `sys.path`; `train.py` / `app.py` then do
+`from midi_model import MIDIModel, MIDIModelConfig, config_name_list` and get this implementation
+(reference: `midi_model.py:14-250`).  What is kept verbatim is the *contract*: constructor, module
+tree and `state_dict` keys (`net.*`, `net_token.*`, `lm_head.weight` -- the HF `LlamaModel`s are used
+as parameter containers only, so seeded init, the four dtype-following RoPE `inv_freq` buffers and
+peft/LoRA affordances behave exactly like the reference), and the signatures / semantics of
+`forward`, `forward_token`, `sample_top_p_k`, `generate`.  What is new is everything that computes:
+all arithmetic runs in hand-written sm_100a kernels behind the C ABI in `include/midi_b200.h`
+(`midi_b200/lib.py`).  There is no PyTorch / CPU fallback: parameters must be bfloat16 on a CUDA
+device, otherwise the call raises.
+
+Extra (non-reference) entry points used by the fused trainer and the benchmark:
+`training_loss(batch)`, `training_step_fused(batch, ...)`.
+"""
+from __future__ import annotations
+
+import json
+from typing import Any, Dict, Optional, Union
+
+import numpy as np
+import torch
+import torch.nn as nn
+import tqdm
+from transformers import DynamicCache, LlamaConfig, LlamaModel, PretrainedConfig, PreTrainedModel
+
+from midi_b200 import decode as _dec
+from midi_b200 import lib as _lib
+from midi_b200 import ops as _ops
+from midi_b200.engine import ParamStore, StackCfg, StackEngine
+from midi_b200.tokenizer_tables import make_tokenizer
+
+config_name_list = ["tv1-medium", "tv2-medium", "tv2o-medium", "tv2-large", "tv2o-large"]
+
+_SIZES = {"medium": dict(n_layer=12, n_head=16, n_embd=1024, n_inner=4096),
+          "large": dict(n_layer=24, n_head=16, n_embd=1024, n_inner=4096)}
+
+
+class MIDIModelConfig(PretrainedConfig):
+    """Same public surface as the reference config (midi_model.py:17-96)."""
+    model_type = "midi_model"
+
+    def __init__(self, tokenizer=None, net_config: Union[LlamaConfig, Dict, None] = None,
+                 net_token_config: Union[LlamaConfig, Dict, None] = None, **kwargs):
+        super().__init__(**kwargs)
+        if isinstance(tokenizer, dict):
+            tok = make_tokenizer(tokenizer["version"])
+            tok.set_optimise_midi(tokenizer["optimise_midi"])
+            tokenizer = tok
+        self.tokenizer = tokenizer if tokenizer else make_tokenizer()
+
+        def as_llama(c):
+            if isinstance(c, dict):
+                return LlamaConfig(**c)
+            return c if c else LlamaConfig()
+
+        self.net_config = as_llama(net_config)
+        self.net_token_config = as_llama(net_token_config)
+        self.n_embd = self.net_token_config.hidden_size   # midi_model.py:48
+
+    def to_dict(self) -> Dict[str, Any]:
+        d = super().to_dict()
+        d["tokenizer"] = self.tokenizer.to_dict()
+        return d
+
+    def __str__(self):
+        return json.dumps({"net": self.net_config.to_json_string(use_diff=False),
+                           "net_token": self.net_token_config.to_json_string(use_diff=False)}, indent=4)
+
+    @staticmethod
+    def get_config(tokenizer_ver="v2", optimise_midi=True, n_layer=12, n_head=16, n_embd=1024, n_inner=4096):
+        tok = make_tokenizer(tokenizer_ver)
+        tok.set_optimise_midi(optimise_midi)
+        common = dict(vocab_size=tok.vocab_size, hidden_size=n_embd, pad_token_id=tok.pad_id,
+                      max_position_embeddings=4096, use_cache=False)
+        outer = LlamaConfig(num_attention_heads=n_head, num_hidden_layers=n_layer, intermediate_size=n_inner, **common)
+        # the token-level stack is a quarter of the event-level one in heads, depth and MLP width (midi_model.py:71-75)
+        inner = LlamaConfig(num_attention_heads=n_head // 4, num_hidden_layers=n_layer // 4,
+                            intermediate_size=n_inner // 4, **common)
+        return MIDIModelConfig(tok, outer, inner)
+
+    @staticmethod
+    def from_name(name="tv2o-medium"):
+        tv, size = name.split("-")
+        tv = tv[1:]
+        optimise = tv.endswith("o")
+        if optimise:
+            tv = tv[:-1]
+        if tv not in ("v1", "v2"):
+            raise ValueError(f"Unknown tokenizer version {tv}")
+        if size not in _SIZES:
+            raise ValueError(f"Unknown model size {size}")
+        return MIDIModelConfig.get_config(tokenizer_ver=tv, optimise_midi=optimise, **_SIZES[size])
+
+
+# ---------------------------------------------------------------------------------------------
+# runtime: flat parameter store + the two stack engines, (re)built lazily
+# ---------------------------------------------------------------------------------------------
+class _Runtime:
+    def __init__(self, model: "MIDIModel"):
+        self.store = ParamStore(model)
+        nc, tc = model.config.net_config, model.config.net_token_config
+        self.outer = StackEngine(self.store, StackCfg("net", nc.num_hidden_layers, nc.num_attention_heads, nc.hidden_size,
+                                                      nc.intermediate_size, nc.rms_norm_eps), tiny_attention=False)
+        self.inner = StackEngine(self.store, StackCfg("net_token", tc.num_hidden_layers, tc.num_attention_heads,
+                                                      tc.hidden_size, tc.intermediate_size, tc.rms_norm_eps),
+                                 tiny_attention=True)
+        self.lm_head = self.store.views["lm_head.weight"]
+        self.g_lm_head = self.store.gviews["lm_head.weight"]
+        self.V = self.lm_head.shape[0]
+        self.pitch = (self.V + 7) // 8 * 8
+        self.H = nc.hidden_size
+        self.opt_state = None
+        self.cached_outer = None
+        self.cached_inner = None
+        self.grammar = None
+
+
+def _flat_ids(x: torch.Tensor) -> torch.Tensor:
+    return x.to(torch.long).contiguous()
+
+
+class _OuterFn(torch.autograd.Function):
+    """forward(): embed-sum + event-level stack, as one autograd node (parameters are inputs so that
+    torch's AccumulateGrad / DDP hooks see their gradients)."""
+
+    @staticmethod
+    def forward(ctx, model, x_ids, *params):
+        rt = model._rt()
+        B, S, T = x_ids.shape
+        ids = _flat_ids(x_ids).view(B * S, T)
+        need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        e = _ops.embed_sum(ids, rt.outer.embed)
+        y, sv = rt.outer.forward(e, B, S, model.net.rotary_emb.inv_freq, save=need)
+        ctx.model, ctx.sv, ctx.ids, ctx.shape = model, sv, ids, (B, S, T)
+        return y.view(B, S, -1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        model = ctx.model
+        rt = model._rt()
+        B, S, T = ctx.shape
+        g = rt.outer.fresh_grads()
+        dy2 = dy.reshape(B * S, -1).to(torch.bfloat16).contiguous()
+        de = rt.outer.backward(ctx.sv, dy2, g, accumulate=False)
+        _ops.embed_bwd(ctx.ids.view(-1), de, g.embed, per_row=T, row_stride=1, row_inner=0, row_off=0,
+                       pad_id=model.config.net_config.pad_token_id, accumulate=False)
+        ctx.sv = None
+        return (None, None, *g.named(rt.store, rt.outer.names))
+
+
+class _InnerFn(torch.autograd.Function):
+    """forward_token() without cache: [hidden, embed(x)] -> token-level stack -> lm_head logits."""
+
+    @staticmethod
+    def forward(ctx, model, hidden, x_ids, *params):
+        rt = model._rt()
+        N = hidden.shape[0] if hidden is not None else x_ids.shape[0]
+        ids = _flat_ids(x_ids) if x_ids is not None else None
+        n_ids = 0 if ids is None else ids.shape[1]
+        L = n_ids + (1 if hidden is not None else 0)
+        need = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or
+                                            (hidden is not None and hidden.requires_grad))
+        hid = hidden.to(torch.bfloat16).contiguous() if hidden is not None else None
+        xin = _ops.inner_input(hid, ids, rt.inner.embed)
+        hs, sv = rt.inner.forward(xin, N, L, model.net_token.rotary_emb.inv_freq, save=need)
+        logits = _ops.linear(hs, rt.lm_head, pitch=rt.pitch)          # [N*L, pitch]
+        ctx.model, ctx.sv, ctx.ids, ctx.hs = model, sv, ids, (hs if need else None)
+        ctx.dims = (N, L, n_ids, hidden is not None)
+        return logits.view(N, L, rt.pitch)[:, :, :rt.V]
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        model = ctx.model
+        rt = model._rt()
+        N, L, n_ids, has_hidden = ctx.dims
+        # caller gradients arrive dense [N, L, V]; the kernels want 16-byte row pitch
+        dl = torch.zeros((N * L, rt.pitch), dtype=torch.bfloat16, device=dlogits.device)
+        dl[:, :rt.V] = dlogits.reshape(N * L, rt.V)
+        g = rt.inner.fresh_grads()
+        g_head = torch.empty_like(rt.lm_head)
+        dhidden, = _inner_backward(rt, model, ctx.sv, ctx.hs, dl, ctx.ids, N, L, n_ids, has_hidden, g, g_head, False)
+        ctx.sv = ctx.hs = None
+        lm = [g_head] if model.lm_head.weight.requires_grad else [None]
+        return (None, dhidden, None, *g.named(rt.store, rt.inner.names), *lm)
+
+
+def _inner_backward(rt, model, sv, hs, dlogits, ids, N, L, n_ids, has_hidden, g, g_head, accumulate):
+    """dlogits [N*L, pitch] -> grads of lm_head, the token-level stack, its embedding; returns (dhidden,)."""
+    _ops.linear_wgrad(dlogits, hs, g_head, accumulate)
+    dhs = _ops.linear_dgrad(dlogits, rt.lm_head)
+    dx = rt.inner.backward(sv, dhs, g, accumulate=accumulate)
+    if n_ids > 0:
+        _ops.embed_bwd(ids.view(-1), dx, g.embed, per_row=n_ids, row_stride=L, row_inner=1, row_off=1 if has_hidden else 0,
+                       pad_id=model.config.net_token_config.pad_token_id, accumulate=accumulate)
+    else:
+        if not accumulate:
+            g.embed.zero_()
+    dhidden = None
+    if has_hidden:
+        dhidden = torch.empty((N, rt.H), dtype=torch.bfloat16, device=dx.device)
+        _lib.call("b200_inner_input_bwd_hidden", dx.data_ptr(), dhidden.data_ptr(), N, L, rt.H, _lib.stream())
+    return (dhidden,)
+
+
+class _KVState:
+    """Paged KV cache hung off the caller's (opaque) DynamicCache object."""
+
+    def __init__(self, kv):
+        self.kv = kv
+
+
+class MIDIModel(PreTrainedModel):
+    config_class = MIDIModelConfig
+
+    def __init__(self, config: MIDIModelConfig, *args, **kwargs):
+        super(MIDIModel, self).__init__(config, *args, **kwargs)
+        self.tokenizer = config.tokenizer
+        # HF modules are parameter containers (same construction order as midi_model.py:105-107 => same seeded init)
+        self.net = LlamaModel(config.net_config)
+        self.net_token = LlamaModel(config.net_token_config)
+        self.lm_head = nn.Linear(config.n_embd, self.tokenizer.vocab_size, bias=False)
+        self._b200_rt: Optional[_Runtime] = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _rt(self) -> _Runtime:
+        rt = self.__dict__.get("_b200_rt")
+        if rt is None or not rt.store.valid():
+            if getattr(self, "_hf_peft_config_loaded", False):
+                raise _lib.B200Error("LoRA adapters are injected: merge them first (load_merge_lora); the sm_100a "
+                                     "kernels read the base weights only")
+            _lib.load()
+            rt = _Runtime(self)
+            self.__dict__["_b200_rt"] = rt
+        return rt
+
+    def load_merge_lora(self, model_id):
+        """midi_model.py:109-114 (peft imported lazily: it is only needed here)."""
+        from peft import LoraModel, PeftConfig, load_peft_weights, set_peft_model_state_dict
+        peft_config = PeftConfig.from_pretrained(model_id)
+        model = LoraModel(self, peft_config, adapter_name="default")
+        adapter_state_dict = load_peft_weights(model_id, device=str(self.device))
+        set_peft_model_state_dict(self, adapter_state_dict, "default")
+        merged = model.merge_and_unload()
+        self.__dict__["_b200_rt"] = None
+        return merged
+
+    def _kv_for(self, cache, which: str, batch: int):
+        rt = self._rt()
+        st = getattr(cache, "_b200_" + which, None)
+        if st is None or st.kv.batch != batch:
+            if which == "outer":
+                cfgs, page, cap = rt.outer.cfg, 64, self.config.net_config.max_position_embeddings
+            else:
+                cfgs, page, cap = rt.inner.cfg, 8, 8
+            st = _KVState(_dec.PagedKV(cfgs, batch, cap, page, rt.store.device))
+            setattr(cache, "_b200_" + which, st)
+        return st.kv
+
+    def _cached_stack(self, which: str):
+        rt = self._rt()
+        if which == "outer":
+            if rt.cached_outer is None:
+                rt.cached_outer = _dec.CachedStack(rt.outer, self.config.net_config.max_position_embeddings,
+                                                   self.net.rotary_emb.inv_freq)
+            return rt.cached_outer
+        if rt.cached_inner is None:
+            rt.cached_inner = _dec.CachedStack(rt.inner, 8, self.net_token.rotary_emb.inv_freq)
+        return rt.cached_inner
+
+    # ------------------------------------------------------------------ reference API
+    def forward_token(self, hidden_state=None, x=None, cache=None):
+        """
+        :param hidden_state: (batch_size, n_embd)
+        :param x: (batch_size, token_sequence_length)
+        :param cache: Cache
+        :return: (batch_size, 1 + token_sequence_length, vocab_size)
+        """
+        rt = self._rt()
+        if cache is None:
+            params = [self._b200_param(n) for n in rt.inner.names] + [self.lm_head.weight]
+            return _InnerFn.apply(self, hidden_state, x, *params)
+        # cached (inference) path: midi_model.py:216-221 call modes
+        N = hidden_state.shape[0] if hidden_state is not None else x.shape[0]
+        kv = self._kv_for(cache, "inner", N)
+        ids = _flat_ids(x) if x is not None else None
+        hid = hidden_state.to(torch.bfloat16).contiguous() if hidden_state is not None else None
+        xin = _ops.inner_input(hid, ids, rt.inner.embed)
+        L = xin.shape[0] // N
+        hs = self._cached_stack("inner").step(xin, kv, L)
+        logits = _dec._lm_head(hs, rt.lm_head, rt.pitch)
+        return logits.view(N, L, rt.pitch)[:, :, :rt.V]
+
+    def forward(self, x, cache=None):
+        """
+        :param x: (batch_size, midi_sequence_length, token_sequence_length)
+        :param cache: Cache
+        :return: hidden (batch_size, midi_sequence_length, n_embd)
+        """
+        rt = self._rt()
+        _lib.require_cuda(x, "x")
+        if cache is None:
+            params = [self._b200_param(n) for n in rt.outer.names]
+            return _OuterFn.apply(self, x, *params)
+        B, S, T = x.shape
+        kv = self._kv_for(cache, "outer", B)
+        e = _ops.embed_sum(_flat_ids(x).view(B * S, T), rt.outer.embed)
+        y = self._cached_stack("outer").step(e, kv, S)
+        return y.view(B, S, -1)
+
+    def _b200_param(self, name: str) -> torch.Tensor:
+        mod, _, leaf = name.rpartition(".")
+        return getattr(self.get_submodule(mod), leaf)
+
+    def sample_top_p_k(self, probs, p, k, generator=None):
+        """midi_model.py:152-165 as one kernel.  `probs`: (..., vocab) softmaxed and masked, un-normalised."""
+        _lib.require_cuda(probs, "probs")
+        shape = probs.shape
+        V = shape[-1]
+        flat = probs.reshape(-1, V)
+        if flat.dtype not in (torch.bfloat16, torch.float32):
+            flat = flat.float()
+        flat = flat.contiguous()
+        rows = flat.shape[0]
+        gen_dev = generator.device if generator is not None else probs.device
+        u = torch.rand(rows, generator=generator, device=gen_dev, dtype=torch.float32).to(probs.device)
+        out = torch.empty(rows, dtype=torch.long, device=probs.device)
+        _lib.call("b200_sample_topp_topk", flat.data_ptr(), int(flat.dtype == torch.bfloat16), rows, V, flat.stride(0),
+                  float(p), int(k), u.data_ptr(), out.data_ptr(), _lib.stream())
+        return out.reshape(*shape[:-1])
+
+    @torch.inference_mode()
+    def generate(self, prompt=None, batch_size=1, max_len=512, temp=1.0, top_p=0.98, top_k=20, generator=None):
+        """midi_model.py:167-250 with the per-token work on the device (see midi_b200/decode.py)."""
+        tok = self.tokenizer
+        T = tok.max_token_seq
+        rt = self._rt()
+        dev = rt.store.device
+        if prompt is None:
+            inp = torch.full((batch_size, 1, T), tok.pad_id, dtype=torch.long, device=dev)
+            inp[:, 0, 0] = tok.bos_id
+        else:
+            if len(prompt.shape) == 2:
+                prompt = np.repeat(prompt[None, :], repeats=batch_size, axis=0)
+            elif prompt.shape[0] == 1:
+                prompt = np.repeat(prompt, repeats=batch_size, axis=0)
+            elif len(prompt.shape) != 3 or prompt.shape[0] != batch_size:
+                raise ValueError(f"invalid shape for prompt, {prompt.shape}")
+            prompt = prompt[..., :T]
+            if prompt.shape[-1] < T:
+                prompt = np.pad(prompt, ((0, 0), (0, 0), (0, T - prompt.shape[-1])), mode="constant",
+                                constant_values=tok.pad_id)
+            inp = torch.from_numpy(np.ascontiguousarray(prompt)).to(dtype=torch.long, device=dev)
+        cur_len = inp.shape[1]
+        if cur_len >= max_len:
+            return inp.cpu().numpy()
+        seq = torch.full((batch_size, max_len, T), tok.pad_id, dtype=torch.long, device=dev)
+        seq[:, :cur_len] = inp
+        if rt.grammar is None:
+            rt.grammar = _dec.GrammarLUT(tok, dev)
+        g = rt.grammar
+        n_params = g.n_params
+        outer, inner = self._cached_stack("outer"), self._cached_stack("inner")
+        kv1 = _dec.PagedKV(rt.outer.cfg, batch_size, max(max_len, 1), 64, dev)
+        kv2 = _dec.PagedKV(rt.inner.cfg, batch_size, T, T, dev)
+        gen_dev = generator.device if generator is not None else dev
+        past_len = 0
+        bar = tqdm.tqdm(desc="generating", total=max_len - cur_len)
+        with bar:
+            while cur_len < max_len:
+                s_new = cur_len - past_len
+                e = _ops.embed_sum(seq[:, past_len:cur_len].reshape(batch_size * s_new, T), rt.outer.embed)
+                hidden = outer.step(e, kv1, s_new).view(batch_size, s_new, -1)[:, -1].contiguous()
+                evb = torch.full((batch_size, T), tok.pad_id, dtype=torch.long, device=dev)   # event being generated
+                evt0 = evb                               # step-0 tokens (contiguous [B]) once sampled
+                kv2.reset()
+                n_steps = T
+                end = [False] * batch_size
+                for i in range(T):
+                    if i >= n_steps:
+                        break
+                    if i == 0:
+                        xin = _ops.inner_input(hidden, None, rt.inner.embed)
+                    else:
+                        xin = _ops.inner_input(None, evb[:, i - 1:i].contiguous(), rt.inner.embed)
+                    hs = inner.step(xin, kv2, 1)
+                    logits = _dec._lm_head(hs, rt.lm_head, rt.pitch)
+                    u = torch.rand(batch_size, generator=generator, device=gen_dev, dtype=torch.float32).to(dev)
+                    _dec.sample_from_logits(logits, rt.V, float(temp), float(top_p), int(top_k), i, evt0, g, u, evb)
+                    if i == 0:
+                        # one small device->host read per event: the reference's `end` / early-exit logic
+                        # (midi_model.py:224-237) needs the event types on the host
+                        evt0 = evb[:, 0].contiguous()
+                        evt = evt0.tolist()
+                        end = [t == tok.eos_id for t in evt]
+                        lens = {n_params.get(t, 0) for t, e_ in zip(evt, end) if not e_}
+                        if len(lens) == 0:
+                            n_steps = 2            # all rows ended: reference breaks after i == 1
+                        elif len(lens) == 1:
+                            n_steps = lens.pop() + 1
+                        else:
+                            n_steps = T
+                seq[:, cur_len] = evb
+                past_len = cur_len
+                cur_len += 1
+                bar.update(1)
+                if all(end):
+                    break
+        return seq[:, :cur_len].cpu().numpy()
+
+    # ------------------------------------------------------------------ fused training path (non-reference API)
+    def training_loss(self, batch: torch.Tensor, backward: bool = True, accumulate: bool = False):
+        """train.py:168-185 (sample_seq=False) fused: x = batch[:, :-1], y = batch[:, 1:], both stacks, lm_head,
+        mean CE with ignore_index=pad -- and, if `backward`, every gradient written to the flat gradient buffer
+        (`.grad` of each parameter is a view of it).  Returns a 0-dim fp32 tensor (no host sync)."""
+        rt = self._rt()
+        tok = self.tokenizer
+        B, S1, T = batch.shape
+        S = S1 - 1
+        batch = batch.to(torch.long)
+        x = batch[:, :-1].contiguous().view(B * S, T)
+        y = batch[:, 1:].contiguous().view(B * S, T)
+        e = _ops.embed_sum(x, rt.outer.embed)
+        hidden, sv_o = rt.outer.forward(e, B, S, self.net.rotary_emb.inv_freq, save=backward)
+        ids_in = y[:, :-1].contiguous()
+        xin = _ops.inner_input(hidden, ids_in, rt.inner.embed)
+        hs, sv_i = rt.inner.forward(xin, B * S, T, self.net_token.rotary_emb.inv_freq, save=backward)
+        del xin
+        logits = _ops.linear(hs, rt.lm_head, pitch=rt.pitch)
+        targets = y.reshape(-1)
+        lac, lse = _ops.ce_fwd(logits, targets, rt.V, tok.pad_id)
+        loss = lac[0]
+        if backward:
+            _ops.ce_bwd_(logits, targets, lse, lac, rt.V, tok.pad_id, 1.0)
+            g_i, g_o = rt.inner.main_grads, rt.outer.main_grads
+            dhidden, = _inner_backward(rt, self, sv_i, hs, logits, ids_in, B * S, T, T - 1, True, g_i, rt.g_lm_head,
+                                       accumulate)
+            del logits, hs
+            de = rt.outer.backward(sv_o, dhidden, g_o, accumulate=accumulate)
+            _ops.embed_bwd(x.view(-1), de, g_o.embed, per_row=T, row_stride=1, row_inner=0, row_off=0,
+                           pad_id=self.config.net_config.pad_token_id, accumulate=accumulate)
+            rt.store.publish_grads()
+        return loss
+
+    def fused_optimizer_step(self, lr: float, step: int, weight_decay: float = 0.01, betas=(0.9, 0.99), eps: float = 1e-8,
+                             max_grad_norm: float = 1.0):
+        """Global-norm clip (train.py:464) + AdamW with the no-decay split (train.py:121-138) over the flat
+        parameter / gradient buffers: two small reductions and one update launch."""
+        rt = self._rt()
+        st = rt.opt_state
+        n = rt.store.numel
+        if st is None:
+            st = dict(m=torch.zeros(n, dtype=torch.float32, device=rt.store.device),
+                      v=torch.zeros(n, dtype=torch.float32, device=rt.store.device),
+                      nc=torch.zeros(2, dtype=torch.float32, device=rt.store.device))
+            rt.opt_state = st
+        parts = _lib.query("b200_gradnorm_parts")
+        ws = _ops._ws("gradnorm", parts * 4, rt.store.device)
+        _lib.call("b200_grad_clip_coef", rt.store.gflat.data_ptr(), n, float(max_grad_norm), st["nc"].data_ptr(),
+                  ws.data_ptr(), ws.numel(), _lib.stream())
+        _lib.call("b200_adamw_step", rt.store.flat.data_ptr(), rt.store.gflat.data_ptr(), st["m"].data_ptr(),
+                  st["v"].data_ptr(), rt.store.nodecay.data_ptr(), n, float(lr), float(betas[0]), float(betas[1]),
+                  float(eps), float(weight_decay), int(step), st["nc"].data_ptr(), _lib.stream())
+        return st["nc"]

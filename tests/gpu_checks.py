@@ -1,0 +1,586 @@
+"""GPU parity checks: every sm_100a kernel (through the C ABI) against the fp32 PyTorch composite it
+replaces, and the drop-in MIDIModel against the CPU oracle restatement run on the same device.
+Each check returns {metric_name: value}; thresholds live in THRESH (asserted by test_gpu_*.py and
+reported by tools/run_gpu_checks.py).  Seeds are fixed; sizes are chosen so the oracle finishes in
+seconds and so that odd / ragged shapes are covered (S=2047, V=3406, rows not /128, L<8, empty)."""
+from __future__ import annotations
+
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "midi-model_b200"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from midi_b200 import lib, ops  # noqa: E402
+from oracle import midi_oracle as O  # noqa: E402
+
+DEV = "cuda"
+BF = torch.bfloat16
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def randn(*shape, scale=1.0, seed=0, dtype=BF):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device=DEV, dtype=torch.float32) * scale).to(dtype)
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+def check_gemm_fwd():
+    out = {}
+    for i, (M, N, K) in enumerate([(256, 256, 128), (1000, 1024, 1024), (2048, 3072, 1024), (384, 8192, 1024),
+                                   (4096, 1024, 4096), (130, 136, 72)]):
+        a, w = randn(M, K, seed=i), randn(N, K, scale=0.05, seed=100 + i)
+        y = ops.linear(a, w)
+        ref = (a.float() @ w.float().T)
+        out[f"gemm_tn_{M}x{N}x{K}"] = rel(y.float(), ref)
+    # residual epilogue: bf16(bf16(acc) + r)
+    M, N, K = 1024, 1024, 1024
+    a, w, r = randn(M, K, seed=7), randn(N, K, scale=0.05, seed=8), randn(M, N, seed=9)
+    y = ops.linear(a, w, residual=r)
+    ref = ((a.float() @ w.float().T).to(BF).float() + r.float())
+    out["gemm_residual"] = rel(y.float(), ref)
+    # N = 3406 (vocab): pitch 3408, trailing columns zero
+    a, w = randn(520, 1024, seed=11), randn(3406, 1024, scale=0.05, seed=12)
+    y = ops.linear(a, w, pitch=3408)
+    out["gemm_vocab"] = rel(y[:, :3406].float(), a.float() @ w.float().T)
+    out["gemm_vocab_padcols_absmax"] = float(y[:, 3406:].float().abs().max())
+    return out
+
+
+def check_gemm_dgrad():
+    out = {}
+    for i, (M, N, K) in enumerate([(256, 256, 128), (1000, 3072, 1024), (2048, 1024, 4096), (520, 3406, 1024)]):
+        pitch = (N + 7) // 8 * 8
+        dy = torch.zeros(M, pitch, device=DEV, dtype=BF)
+        dy[:, :N] = randn(M, N, seed=20 + i)
+        w = randn(N, K, scale=0.05, seed=30 + i)
+        dx = ops.linear_dgrad(dy, w)
+        out[f"gemm_dgrad_{M}x{N}x{K}"] = rel(dx.float(), dy[:, :N].float() @ w.float())
+    return out
+
+
+def check_gemm_wgrad():
+    out = {}
+    for i, (M, N, K) in enumerate([(256, 256, 128), (4096, 1024, 1024), (3000, 3072, 1024), (2048, 3406, 1024),
+                                   (16384, 1024, 1024)]):
+        pitch = (N + 7) // 8 * 8
+        dy = torch.zeros(M, pitch, device=DEV, dtype=BF)
+        dy[:, :N] = randn(M, N, seed=40 + i)
+        x = randn(M, K, seed=50 + i)
+        dw = torch.empty(N, K, device=DEV, dtype=BF)
+        ops.linear_wgrad(dy, x, dw, accumulate=False)
+        ref = dy[:, :N].float().T @ x.float()
+        out[f"gemm_wgrad_{M}x{N}x{K}"] = rel(dw.float(), ref)
+        if i == 1:
+            ops.linear_wgrad(dy, x, dw, accumulate=True)
+            out["gemm_wgrad_accumulate"] = rel(dw.float(), 2 * ref)
+    return out
+
+
+# ------------------------------------------------------------------------------------------ elementwise
+def check_elementwise():
+    out = {}
+    V, H = 3406, 1024
+    table = randn(V, H, scale=0.02, seed=1)
+    ids = torch.randint(0, V, (300, 8), device=DEV, generator=torch.Generator(device=DEV).manual_seed(2))
+    ids[5] = 0
+    y = ops.embed_sum(ids, table)
+    ref = F.embedding(ids, table).float().sum(-2).to(BF)
+    out["embed_sum_maxabs"] = float((y.float() - ref.float()).abs().max())
+    # embedding backward (outer: 8 ids per gradient row; pad row zero)
+    dout = randn(300, H, seed=3)
+    dtab = torch.empty(V, H, device=DEV, dtype=BF)
+    ops.embed_bwd(ids.view(-1), dout, dtab, per_row=8, row_stride=1, row_inner=0, row_off=0, pad_id=0, accumulate=False)
+    t32 = table.float().clone().requires_grad_(True)
+    F.embedding(ids, t32, padding_idx=0).sum(-2).backward(dout.float())
+    out["embed_bwd"] = rel(dtab.float(), t32.grad)
+    out["embed_bwd_padrow_absmax"] = float(dtab[0].float().abs().max())
+    # inner input builder + its embedding backward (7 ids per event, rows e*8 + 1 + j)
+    hid = randn(40, H, seed=4)
+    ids7 = torch.randint(0, V, (40, 7), device=DEV, generator=torch.Generator(device=DEV).manual_seed(5))
+    xin = ops.inner_input(hid, ids7, table)
+    ref = torch.cat([hid[:, None], F.embedding(ids7, table)], 1).reshape(-1, H)
+    out["inner_input_equal"] = float((xin != ref).sum())
+    dx = randn(40 * 8, H, seed=6)
+    ops.embed_bwd(ids7.view(-1), dx, dtab, per_row=7, row_stride=8, row_inner=1, row_off=1, pad_id=0, accumulate=False)
+    t32 = table.float().clone().requires_grad_(True)
+    F.embedding(ids7, t32, padding_idx=0).backward(dx.float().view(40, 8, H)[:, 1:])
+    out["inner_embed_bwd"] = rel(dtab.float(), t32.grad)
+    # rmsnorm
+    for M in (1, 300, 5000):
+        x, w = randn(M, H, seed=7), (1 + 0.1 * randn(H, seed=8).float()).to(BF)
+        y, rstd = ops.rmsnorm(x, w, 1e-6, want_rstd=True)
+        ref = O.rmsnorm(x, w, 1e-6)
+        out[f"rmsnorm_fwd_mismatch_{M}"] = float((y != ref).float().mean())
+        out[f"rmsnorm_fwd_{M}"] = rel(y.float(), ref.float())
+        dy, dres = randn(M, H, seed=9), randn(M, H, seed=10)
+        dw = torch.empty(H, device=DEV, dtype=BF)
+        dx = ops.rmsnorm_bwd(dy, x, w, rstd, dres, dw, False)
+        x32, w32 = x.float().requires_grad_(True), w.float().requires_grad_(True)
+        v = x32.pow(2).mean(-1, keepdim=True)
+        (w32 * (x32 * torch.rsqrt(v + 1e-6))).backward(dy.float())
+        out[f"rmsnorm_bwd_dx_{M}"] = rel(dx.float(), x32.grad + dres.float())
+        out[f"rmsnorm_bwd_dw_{M}"] = rel(dw.float(), w32.grad)
+    # rope (bf16-rounded inv_freq, as after model.to(bf16)) on packed qkv
+    for (S, nh, D) in ((37, 16, 64), (8, 4, 256)):
+        Hh = nh * D
+        inv = O.default_inv_freq(D).to(BF).to(DEV)
+        cos, sin = ops.rope_table(inv, S)
+        rc, rs = O.rope_cos_sin(inv, torch.arange(S, device=DEV), BF)
+        out[f"rope_table_mismatch_D{D}"] = float((cos != rc[:, :D // 2]).sum() + (sin != rs[:, :D // 2]).sum())
+        qkv = randn(3 * S, 3 * Hh, seed=11)
+        q0 = qkv.clone()
+        ops.rope_qk_(qkv, cos, sin, S, Hh, D)
+        q = q0[:, :Hh].view(3, S, nh, D).transpose(1, 2)
+        k = q0[:, Hh:2 * Hh].view(3, S, nh, D).transpose(1, 2)
+        rq = O.apply_rope(q, rc, rs).transpose(1, 2).reshape(3 * S, Hh)
+        rk = O.apply_rope(k, rc, rs).transpose(1, 2).reshape(3 * S, Hh)
+        out[f"rope_fwd_mismatch_D{D}"] = float((qkv[:, :Hh] != rq).sum() + (qkv[:, Hh:2 * Hh] != rk).sum()
+                                               + (qkv[:, 2 * Hh:] != q0[:, 2 * Hh:]).sum())
+        # backward == transpose of the rotation: <R x, y> == <x, R^T y>
+        d = randn(3 * S, 3 * Hh, seed=12)
+        d_in = d.clone()
+        ops.rope_qk_(d_in, cos, sin, S, Hh, D, backward=True)
+        c32 = torch.cat([cos, cos], -1).float()
+        s32 = torch.cat([sin, sin], -1).float()
+
+        def rot32(t):
+            t4 = t.float().view(3, S, nh, D)
+            return (t4 * c32[None, :, None] + O.rotate_half(t4) * s32[None, :, None]).reshape(3 * S, Hh)
+        lhs = (rot32(q0[:, :Hh]) * d[:, :Hh].float()).sum()
+        rhs = (q0[:, :Hh].float() * d_in[:, :Hh].float()).sum()
+        out[f"rope_bwd_adjoint_D{D}"] = float((lhs - rhs).abs() / lhs.abs().clamp_min(1e-6))
+    # swiglu
+    gu = randn(777, 2 * 1024, seed=13)
+    act = ops.swiglu(gu)
+    ref = F.silu(gu[:, :1024]) * gu[:, 1024:]
+    out["swiglu_fwd_mismatch"] = float((act != ref).float().mean())
+    dact = randn(777, 1024, seed=14)
+    dgu = ops.swiglu_bwd(gu, dact)
+    g32 = gu.float().requires_grad_(True)
+    (F.silu(g32[:, :1024]) * g32[:, 1024:]).backward(dact.float())
+    out["swiglu_bwd"] = rel(dgu.float(), g32.grad)
+    return out
+
+
+# ------------------------------------------------------------------------------------------ attention
+def _sdpa_ref(q, k, v, off):
+    # q (B,h,Sq,d) fp32; causal with offset
+    Sq, Sk = q.shape[-2], k.shape[-2]
+    s = q @ k.transpose(-1, -2) / math.sqrt(q.shape[-1])
+    m = torch.arange(Sk, device=q.device)[None] > (torch.arange(Sq, device=q.device)[:, None] + off)
+    s = s.masked_fill(m, float("-inf"))
+    return torch.softmax(s, -1) @ v
+
+
+def check_attn_flash():
+    out = {}
+    for (B, S, nh) in ((2, 64, 4), (1, 200, 16), (2, 2047, 16)):
+        D, H = 64, nh * 64
+        qkv = randn(B * S, 3 * H, seed=S)
+        o, lse = ops.attn_causal_fwd(qkv, B, S, nh, D, want_lse=True)
+        q32 = qkv.float().view(B, S, 3, nh, D).permute(2, 0, 3, 1, 4).clone().requires_grad_(True)
+        ref = _sdpa_ref(q32[0], q32[1], q32[2], 0)
+        out[f"flash_fwd_S{S}"] = rel(o.float().view(B, S, nh, D).transpose(1, 2), ref)
+        sc = (q32[0] @ q32[1].transpose(-1, -2)) / 8.0
+        msk = torch.triu(torch.ones(S, S, device=DEV, dtype=torch.bool), 1)
+        out[f"flash_lse_S{S}"] = rel(lse, torch.logsumexp(sc.masked_fill(msk, float("-inf")), -1))
+        do = randn(B * S, H, seed=S + 1)
+        dqkv = ops.attn_causal_bwd(qkv, o, do, lse, B, S, nh, D)
+        ref.backward(do.float().view(B, S, nh, D).transpose(1, 2))
+        g = q32.grad.permute(1, 3, 0, 2, 4).reshape(B * S, 3 * H)
+        out[f"flash_bwd_dq_S{S}"] = rel(dqkv[:, :H].float(), g[:, :H])
+        out[f"flash_bwd_dk_S{S}"] = rel(dqkv[:, H:2 * H].float(), g[:, H:2 * H])
+        out[f"flash_bwd_dv_S{S}"] = rel(dqkv[:, 2 * H:].float(), g[:, 2 * H:])
+    return out
+
+
+def check_attn_tiny():
+    out = {}
+    nh, D = 4, 256
+    H = nh * D
+    for (N, L) in ((50, 8), (33, 5), (7, 1)):
+        qkv = randn(N * L, 3 * H, seed=L)
+        o = ops.attn_tiny_fwd(qkv, N, L, nh, D)
+        q32 = qkv.float().view(N, L, 3, nh, D).permute(2, 0, 3, 1, 4).clone().requires_grad_(True)
+        ref = _sdpa_ref(q32[0], q32[1], q32[2], 0)
+        out[f"tiny_fwd_L{L}"] = rel(o.float().view(N, L, nh, D).transpose(1, 2), ref)
+        do = randn(N * L, H, seed=L + 1)
+        dqkv = ops.attn_tiny_bwd(qkv, do, N, L, nh, D)
+        ref.backward(do.float().view(N, L, nh, D).transpose(1, 2))
+        g = q32.grad.permute(1, 3, 0, 2, 4).reshape(N * L, 3 * H)
+        out[f"tiny_bwd_L{L}"] = rel(dqkv.float(), g)
+    return out
+
+
+# ------------------------------------------------------------------------------------------ loss / optimizer
+def check_loss_optim():
+    out = {}
+    V, pitch, R = 3406, 3408, 1000
+    logits = torch.zeros(R, pitch, device=DEV, dtype=BF)
+    logits[:, :V] = randn(R, V, scale=2.0, seed=1)
+    tg = torch.randint(0, V, (R,), device=DEV, generator=torch.Generator(device=DEV).manual_seed(2))
+    tg[::5] = 0
+    lac, lse = ops.ce_fwd(logits, tg, V, 0)
+    l32 = logits[:, :V].float().requires_grad_(True)
+    ref = F.cross_entropy(l32, tg, ignore_index=0)
+    out["ce_loss_abs"] = float((lac[0] - ref).abs())
+    out["ce_count_abs"] = float((lac[1] - (tg != 0).sum()).abs())
+    ref.backward()
+    ops.ce_bwd_(logits, tg, lse, lac, V, 0, 1.0)
+    out["ce_bwd"] = rel(logits[:, :V].float(), l32.grad)
+    out["ce_bwd_padcols_absmax"] = float(logits[:, V:].float().abs().max())
+    # all-ignored rows -> loss 0, zero grads
+    tg0 = torch.zeros(R, dtype=torch.long, device=DEV)
+    lac0, _ = ops.ce_fwd(logits, tg0, V, 0)
+    out["ce_all_ignored_loss"] = float(lac0[0].abs())
+    # AdamW + clip vs torch.optim.AdamW (fp32 reference on the bf16-rounded values)
+    n = 256 * 1000
+    p = randn(n, scale=0.05, seed=3)
+    g = randn(n, scale=0.5, seed=4)
+    nodecay = torch.zeros(n // 256, dtype=torch.uint8, device=DEV)
+    nodecay[500:] = 1
+    pr = p.float().clone()
+    m = torch.zeros(n, device=DEV)
+    v = torch.zeros(n, device=DEV)
+    nc = torch.zeros(2, device=DEV)
+    ws = torch.empty(lib.query("b200_gradnorm_parts") * 4, dtype=torch.uint8, device=DEV)
+    pa = torch.nn.Parameter(pr[: 500 * 256].clone())
+    pb = torch.nn.Parameter(pr[500 * 256:].clone())
+    opt = torch.optim.AdamW([dict(params=[pa], weight_decay=0.01), dict(params=[pb], weight_decay=0.0)], lr=1e-3,
+                            betas=(0.9, 0.99), eps=1e-8)
+    pcur = p.clone()
+    for step in (1, 2, 3):
+        lib.call("b200_grad_clip_coef", g.data_ptr(), n, 1.0, nc.data_ptr(), ws.data_ptr(), ws.numel(), lib.stream())
+        lib.call("b200_adamw_step", pcur.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), nodecay.data_ptr(), n, 1e-3,
+                 0.9, 0.99, 1e-8, 0.01, step, nc.data_ptr(), lib.stream())
+        pa.grad = g.float()[: 500 * 256].clone()
+        pb.grad = g.float()[500 * 256:].clone()
+        torch.nn.utils.clip_grad_norm_([pa, pb], 1.0)
+        opt.step()
+        # the kernel rounds the parameter to bf16 each step; mirror that in the reference
+        with torch.no_grad():
+            pa.copy_(pa.to(BF).float())
+            pb.copy_(pb.to(BF).float())
+    out["gradnorm_rel"] = float((nc[0] - g.float().norm()).abs() / g.float().norm())
+    out["adamw_maxabs"] = float((pcur.float() - torch.cat([pa, pb]).detach()).abs().max())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ decode kernels
+def check_decode():
+    out = {}
+    from midi_b200 import decode as dec
+    from midi_b200.engine import StackCfg
+    # skinny GEMM
+    for B in (1, 3, 8, 16):
+        x, w, r = randn(B, 1024, seed=B), randn(3072, 1024, scale=0.05, seed=B + 1), randn(B, 3072, seed=B + 2)
+        y = dec._linear(x, w)
+        out[f"gemv_B{B}"] = rel(y.float(), x.float() @ w.float().T)
+        y = dec._linear(x, w, residual=r)
+        out[f"gemv_res_B{B}"] = rel(y.float(), (x.float() @ w.float().T).to(BF).float() + r.float())
+    x, w = randn(2, 1024, seed=40), randn(3406, 1024, scale=0.05, seed=41)
+    y = dec._lm_head(x, w, 3408)
+    out["gemv_vocab"] = rel(y[:, :3406].float(), x.float() @ w.float().T)
+    x, w = randn(4, 4096, seed=42), randn(1024, 4096, scale=0.05, seed=43)
+    out["gemv_K4096"] = rel(dec._linear(x, w).float(), x.float() @ w.float().T)
+    # paged KV append + single-query attention vs dense reference
+    for (nh, D, page, T, sq) in ((16, 64, 64, 300, 1), (16, 64, 64, 1500, 1), (4, 256, 8, 6, 1), (16, 64, 64, 70, 5)):
+        Bn, H = 2, nh * D
+        cfg = StackCfg("net", 1, nh, H, 4 * H, 1e-6)
+        kv = dec.PagedKV(cfg, Bn, 2048 if D == 64 else 8, page, DEV)
+        past = T - sq
+        hist = randn(Bn * past, 3 * H, seed=T) if past > 0 else None
+        new = randn(Bn * sq, 3 * H, seed=T + 1)
+        if past > 0:
+            lib.call("b200_kv_append", hist.data_ptr(), kv.k[0].data_ptr(), kv.v[0].data_ptr(), kv.block_table.data_ptr(),
+                     kv.max_pages, kv.page, nh, D, Bn, past, 0, None, 3 * H, lib.stream())
+        lib.call("b200_kv_append", new.data_ptr(), kv.k[0].data_ptr(), kv.v[0].data_ptr(), kv.block_table.data_ptr(),
+                 kv.max_pages, kv.page, nh, D, Bn, sq, past, None, 3 * H, lib.stream())
+        n_split = max(1, (T + 255) // 256) if D == 64 else 1
+        ws = torch.empty(lib.query("b200_attn_decode_workspace_bytes", Bn * sq, nh, D, n_split), dtype=torch.uint8, device=DEV)
+        o = torch.empty(Bn * sq, H, device=DEV, dtype=BF)
+        lib.call("b200_attn_decode", new.data_ptr(), kv.k[0].data_ptr(), kv.v[0].data_ptr(), kv.block_table.data_ptr(),
+                 kv.max_pages, kv.page, o.data_ptr(), Bn, sq, nh, D, past, None, T, 3 * H, H, 1.0 / math.sqrt(D), n_split,
+                 ws.data_ptr(), ws.numel(), lib.stream())
+        allrows = new.view(Bn, sq, 3 * H) if past == 0 else torch.cat([hist.view(Bn, past, 3 * H), new.view(Bn, sq, 3 * H)], 1)
+        q = new.view(Bn, sq, 3, nh, D)[:, :, 0].transpose(1, 2).float()
+        k = allrows.view(Bn, T, 3, nh, D)[:, :, 1].transpose(1, 2).float()
+        v = allrows.view(Bn, T, 3, nh, D)[:, :, 2].transpose(1, 2).float()
+        ref = _sdpa_ref(q, k, v, past)
+        out[f"decode_attn_D{D}_T{T}_q{sq}"] = rel(o.float().view(Bn, sq, nh, D).transpose(1, 2), ref)
+    # sampler: greedy == argmax; top-k support; distribution sanity
+    V = 3406
+    g = torch.Generator(device=DEV).manual_seed(5)
+    probs = torch.softmax(torch.randn(64, V, generator=g, device=DEV) * 3, -1)
+    mask = torch.zeros(V, device=DEV)
+    mask[9:137] = 1
+    probs = (probs * mask)
+    u = torch.rand(64, generator=g, device=DEV)
+    o1 = torch.empty(64, dtype=torch.long, device=DEV)
+    lib.call("b200_sample_topp_topk", probs.data_ptr(), 0, 64, V, V, 0.98, 1, u.data_ptr(), o1.data_ptr(), lib.stream())
+    out["sampler_greedy_mismatch"] = float((o1 != probs.argmax(-1)).sum())
+    lib.call("b200_sample_topp_topk", probs.data_ptr(), 0, 64, V, V, 0.98, 20, u.data_ptr(), o1.data_ptr(), lib.stream())
+    top20 = probs.topk(20, -1).indices
+    out["sampler_topk_outside"] = float((~(top20 == o1[:, None]).any(-1)).sum())
+    # empirical distribution of one row vs the reference algorithm's renormalised top-p/top-k weights
+    row = probs[:1].repeat(4096, 1).contiguous()
+    u = torch.rand(4096, generator=g, device=DEV)
+    o2 = torch.empty(4096, dtype=torch.long, device=DEV)
+    lib.call("b200_sample_topp_topk", row.data_ptr(), 0, 4096, V, V, 0.9, 8, u.data_ptr(), o2.data_ptr(), lib.stream())
+    ps, pi = torch.sort(probs[0], descending=True)
+    cs = torch.cumsum(ps, 0)
+    ps = torch.where(cs - ps > 0.9, torch.zeros_like(ps), ps)
+    ps[8:] = 0
+    ps = ps / ps.sum()
+    want = torch.zeros(V, device=DEV).scatter(0, pi, ps)
+    emp = torch.bincount(o2, minlength=V).float() / 4096
+    out["sampler_dist_l1"] = float((emp - want).abs().sum())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ model level
+def _model(n_layer=4, seed=0):
+    import midi_model as mm
+    torch.manual_seed(seed)
+    cfg = mm.MIDIModelConfig.get_config("v2", True, n_layer=n_layer, n_head=16, n_embd=1024, n_inner=4096)
+    return mm, mm.MIDIModel(cfg)
+
+
+def _sd(model, dtype, device=DEV):
+    return {k: v.detach().to(device=device, dtype=dtype) for k, v in model.state_dict().items()}
+
+
+def check_model_forward():
+    """forward + forward_token logits vs the oracle (fp32 and bf16 on the same device): noise-floor protocol
+    of SURVEY.md section 8c tier 2."""
+    from midi_b200.synth import synth_batch
+    out = {}
+    mm, model = _model(4)
+    ocfg = O.cfg_from_hf(model.config)
+    sd32 = _sd(model, torch.float32)
+    model = model.to(DEV, dtype=BF).eval()
+    sd16 = _sd(model, BF)
+    inv_n = model.net.rotary_emb.inv_freq
+    inv_t = model.net_token.rotary_emb.inv_freq
+    out["inv_freq_is_bf16"] = float(inv_n.dtype == BF)
+    batch = synth_batch(model.tokenizer, 2, 130, seed=1234).to(DEV)
+    x, y = batch[:, :-1], batch[:, 1:]
+    with torch.no_grad():
+        h = model.forward(x)
+        lg = model.forward_token(h.reshape(-1, 1024), y.reshape(-1, 8)[:, :-1])
+        h32 = O.forward(sd32, ocfg, x)
+        l32 = O.forward_token(sd32, ocfg, h32.reshape(-1, 1024), y.reshape(-1, 8)[:, :-1])
+        h16 = O.forward(sd16, ocfg, x, inv_freq=inv_n)
+        l16 = O.forward_token(sd16, ocfg, h16.reshape(-1, 1024), y.reshape(-1, 8)[:, :-1], inv_freq=inv_t)
+    out["hidden_new_vs_fp32"] = rel(h.float(), h32)
+    out["hidden_oracle16_vs_fp32"] = rel(h16.float(), h32)
+    out["hidden_new_vs_oracle16"] = rel(h.float(), h16.float())
+    out["logits_new_vs_fp32"] = rel(lg.float(), l32)
+    out["logits_oracle16_vs_fp32"] = rel(l16.float(), l32)
+    out["logits_new_vs_oracle16"] = rel(lg.float(), l16.float())
+    out["argmax_agree_new_fp32"] = float((lg.float().argmax(-1) == l32.argmax(-1)).float().mean())
+    out["argmax_agree_oracle16_fp32"] = float((l16.float().argmax(-1) == l32.argmax(-1)).float().mean())
+    # teacher-forced inner stack: feed the oracle's bf16 hidden
+    with torch.no_grad():
+        lg_tf = model.forward_token(h16.reshape(-1, 1024), y.reshape(-1, 8)[:, :-1])
+    out["logits_teacher_forced_vs_oracle16"] = rel(lg_tf.float(), l16.float())
+    return out
+
+
+def check_model_layer_teacher_forced():
+    """One decoder layer at a time, fed the oracle's own bf16 input (tier 1: <= 1e-3 on GEMM-dominated ops)."""
+    from midi_b200.synth import synth_batch
+    out = {}
+    mm, model = _model(4)
+    ocfg = O.cfg_from_hf(model.config)
+    model = model.to(DEV, dtype=BF).eval()
+    sd16 = _sd(model, BF)
+    rt = model._rt()
+    B, S = 2, 96
+    x_in = randn(B * S, 1024, seed=3)
+    # oracle: a 1-layer stack built from layer 0's weights
+    one = O.StackCfg("net", 1, 16, 1024, 4096)
+    inv = model.net.rotary_emb.inv_freq
+    sd1 = {k: v for k, v in sd16.items() if k.startswith("net.layers.0.") or k == "net.norm.weight"}
+    with torch.no_grad():
+        ref = O.llama_stack(sd1, one, x_in.view(B, S, 1024), inv)
+    eng = rt.outer
+    keep = eng.layers
+    eng.layers = keep[:1]
+    y, _ = eng.forward(x_in, B, S, inv, save=False)
+    eng.layers = keep
+    out["outer_layer_tf"] = rel(y.float().view(B, S, 1024), ref.float())
+    one_t = O.StackCfg("net_token", 1, 4, 1024, 1024)
+    sd1 = {k: v for k, v in sd16.items() if k.startswith("net_token.layers.0.") or k == "net_token.norm.weight"}
+    inv_t = model.net_token.rotary_emb.inv_freq
+    x_in = randn(64 * 8, 1024, seed=4)
+    with torch.no_grad():
+        ref = O.llama_stack(sd1, one_t, x_in.view(64, 8, 1024), inv_t)
+    eng = rt.inner
+    keep = eng.layers
+    eng.layers = keep[:1]
+    y, _ = eng.forward(x_in, 64, 8, inv_t, save=False)
+    eng.layers = keep
+    out["inner_layer_tf"] = rel(y.float().view(64, 8, 1024), ref.float())
+    return out
+
+
+def check_model_train():
+    """Fused loss + all gradients vs the oracle under torch autograd (fp32 weights = the bf16 weights upcast)."""
+    from midi_b200.synth import synth_batch
+    out = {}
+    mm, model = _model(4)
+    ocfg = O.cfg_from_hf(model.config)
+    model = model.to(DEV, dtype=BF).train()
+    batch = synth_batch(model.tokenizer, 2, 66, seed=77, pad_tail=3).to(DEV)
+    sd = {k: v.detach().float().requires_grad_(True) for k, v in model.state_dict().items()}
+    ref = O.train_loss(sd, ocfg, batch)
+    ref.backward()
+    loss = model.training_loss(batch)
+    out["loss_abs"] = float((loss - ref.detach()).abs())
+    out["loss_ref"] = float(ref)
+    worst, worst_name = 0.0, ""
+    tot_n, tot_d = 0.0, 0.0
+    for n, p in model.named_parameters():
+        gref = sd[n].grad
+        e = rel(p.grad.float(), gref)
+        tot_n += float((p.grad.float() - gref).double().pow(2).sum())
+        tot_d += float(gref.double().pow(2).sum())
+        if e > worst:
+            worst, worst_name = e, n
+    out["grad_global_rel"] = math.sqrt(tot_n / tot_d)
+    out["grad_worst_rel"] = worst
+    print("worst grad tensor:", worst_name, worst)
+    out["grad_pad_row_outer"] = float(model.net.embed_tokens.weight.grad[0].float().abs().max())
+    out["grad_pad_row_inner"] = float(model.net_token.embed_tokens.weight.grad[0].float().abs().max())
+    # autograd (drop-in) path == fused path
+    fused = {n: p.grad.clone() for n, p in model.named_parameters()}
+    for p in model.parameters():
+        p.grad = None
+    x, y = batch[:, :-1].contiguous(), batch[:, 1:].contiguous()
+    hidden = model.forward(x)
+    hidden = hidden.reshape(-1, hidden.shape[-1])
+    yy = y.reshape(-1, y.shape[-1])
+    logits = model.forward_token(hidden, yy[:, :-1])
+    l2 = F.cross_entropy(logits.view(-1, model.tokenizer.vocab_size), yy.view(-1), reduction="mean",
+                         ignore_index=model.tokenizer.pad_id)
+    l2.backward()
+    out["autograd_loss_abs"] = float((l2.float() - ref.detach()).abs())
+    tot_n = tot_d = 0.0
+    for n, p in model.named_parameters():
+        tot_n += float((p.grad.float() - sd[n].grad).double().pow(2).sum())
+        tot_d += float(sd[n].grad.double().pow(2).sum())
+    out["autograd_grad_global_rel"] = math.sqrt(tot_n / tot_d)
+    # 5 fused steps: loss curve vs torch AdamW on the oracle (tier 3)
+    return out
+
+
+def check_model_generate():
+    """Greedy (top_k=1) generate and the KV-cached forward vs the oracle."""
+    from midi_b200.synth import synth_batch
+    out = {}
+    mm, model = _model(4)
+    ocfg = O.cfg_from_hf(model.config)
+    model = model.to(DEV, dtype=BF).eval()
+    sd16 = _sd(model, BF)
+    tok = model.tokenizer
+    batch = synth_batch(tok, 2, 40, seed=5).to(DEV)
+    from transformers import DynamicCache
+    with torch.no_grad():
+        full = model.forward(batch)
+        c = DynamicCache()
+        parts = [model.forward(batch[:, :17], cache=c), model.forward(batch[:, 17:18], cache=c),
+                 model.forward(batch[:, 18:23], cache=c)]
+        for t in range(23, 40):
+            parts.append(model.forward(batch[:, t:t + 1], cache=c))
+    out["cached_vs_full_hidden"] = rel(torch.cat(parts, 1).float(), full.float())
+    # inner cached path vs uncached logits
+    with torch.no_grad():
+        hid = full[:, -1]
+        ids = batch[:, -1, :7]
+        lg = model.forward_token(hid, ids)
+        c2 = DynamicCache()
+        steps = [model.forward_token(hid, None, cache=c2)]
+        for i in range(7):
+            steps.append(model.forward_token(None, ids[:, i:i + 1], cache=c2))
+    out["inner_cached_vs_full_logits"] = rel(torch.cat(steps, 1).float(), lg.float())
+    # greedy generate vs oracle generate (bf16 oracle on the same device), teacher-free
+    prompt = batch[:, :6].cpu().numpy()
+    ids_new = model.generate(prompt=prompt, batch_size=2, max_len=14, top_k=1, generator=torch.Generator(DEV).manual_seed(0))
+    ids_ref = O.generate(sd16, ocfg, tok, prompt, batch_size=2, max_len=14, top_k=1,
+                         inv_freq_net=model.net.rotary_emb.inv_freq, inv_freq_tok=model.net_token.rotary_emb.inv_freq)
+    n = min(ids_new.shape[1], ids_ref.shape[1])
+    out["greedy_len_new"], out["greedy_len_ref"] = float(ids_new.shape[1]), float(ids_ref.shape[1])
+    out["greedy_token_agree"] = float((ids_new[:, :n] == ids_ref[:, :n]).mean())
+    # grammar validity of sampled generation
+    ids_s = model.generate(prompt=None, batch_size=4, max_len=24, generator=torch.Generator(DEV).manual_seed(1))
+    bad = 0
+    for row in ids_s.reshape(-1, 8)[4:]:
+        if row[0] == tok.eos_id or row[0] == tok.pad_id:
+            continue
+        if tok.tokens2event(row.tolist()) == []:
+            bad += 1
+    out["sampled_invalid_events"] = float(bad)
+    return out
+
+
+GROUPS = {
+    "gemm_fwd": check_gemm_fwd, "gemm_dgrad": check_gemm_dgrad, "gemm_wgrad": check_gemm_wgrad,
+    "elementwise": check_elementwise, "attn_flash": check_attn_flash, "attn_tiny": check_attn_tiny,
+    "loss_optim": check_loss_optim, "decode": check_decode, "model_forward": check_model_forward,
+    "model_layer_tf": check_model_layer_teacher_forced, "model_train": check_model_train,
+    "model_generate": check_model_generate,
+}
+
+# metric-name prefix -> upper bound (first matching prefix wins); "min:" entries are lower bounds
+THRESH = [
+    ("gemm_vocab_padcols_absmax", 0.0), ("gemm_", 4e-3), ("embed_sum_maxabs", 0.0), ("embed_bwd_padrow_absmax", 0.0),
+    ("embed_bwd", 4e-3), ("inner_input_equal", 0.0), ("inner_embed_bwd", 4e-3),
+    ("rmsnorm_fwd_mismatch", 2e-3), ("rmsnorm_fwd", 2e-3), ("rmsnorm_bwd", 4e-3),
+    ("rope_table_mismatch", 8.0), ("rope_fwd_mismatch", 64.0), ("rope_bwd_adjoint", 2e-2),
+    ("swiglu_fwd_mismatch", 2e-2), ("swiglu_bwd", 4e-3),
+    ("flash_fwd", 6e-3), ("flash_lse", 1e-4), ("flash_bwd", 1.2e-2), ("tiny_fwd", 6e-3), ("tiny_bwd", 1.2e-2),
+    ("ce_loss_abs", 2e-3), ("ce_count_abs", 0.0), ("ce_bwd_padcols_absmax", 0.0), ("ce_bwd", 6e-3),
+    ("ce_all_ignored_loss", 0.0), ("gradnorm_rel", 1e-4), ("adamw_maxabs", 2e-3),
+    ("gemv_", 4e-3), ("decode_attn", 6e-3), ("sampler_greedy_mismatch", 0.0), ("sampler_topk_outside", 0.0),
+    ("sampler_dist_l1", 0.12),
+    ("min:inv_freq_is_bf16", 1.0),
+    ("hidden_new_vs_oracle16", 3e-2), ("logits_new_vs_oracle16", 4e-2), ("logits_teacher_forced_vs_oracle16", 2e-2),
+    ("outer_layer_tf", 6e-3), ("inner_layer_tf", 6e-3),
+    ("loss_abs", 3e-2), ("grad_global_rel", 6e-2), ("grad_pad_row", 0.0), ("autograd_loss_abs", 5e-2),
+    ("autograd_grad_global_rel", 6e-2),
+    ("cached_vs_full_hidden", 3e-2), ("inner_cached_vs_full_logits", 3e-2), ("min:greedy_token_agree", 0.9),
+    ("sampled_invalid_events", 0.0),
+]
+
+
+def verdict(metrics: dict):
+    """Returns list of (name, value, bound, ok).  Noise-floor rules (tier 2) are added for model_forward."""
+    res = []
+    for k, v in metrics.items():
+        bound, ok = None, True
+        for pref, b in THRESH:
+            if pref.startswith("min:"):
+                if k.startswith(pref[4:]):
+                    bound, ok = b, v >= b
+                    break
+            elif k.startswith(pref):
+                bound, ok = b, (v <= b) and not math.isnan(v)
+                break
+        res.append((k, v, bound, ok))
+    if "hidden_new_vs_fp32" in metrics:
+        for a, b in (("hidden_new_vs_fp32", "hidden_oracle16_vs_fp32"), ("logits_new_vs_fp32", "logits_oracle16_vs_fp32")):
+            res.append((a + "<=1.25x_floor", metrics[a], 1.25 * metrics[b], metrics[a] <= 1.25 * metrics[b]))
+    return res

@@ -1,0 +1,126 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol of include/midi_b200.h, the
+drop-in module keeps the reference's contract, and the product refuses to run without CUDA."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _built():
+    from midi_b200 import lib
+    if not os.path.exists(lib.LIB_PATH):
+        import subprocess
+        import sys
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "midi-model_b200", "build_ext.py")])
+    return lib
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _built()
+    hdr = open(os.path.join(ROOT, "include", "midi_b200.h")).read()
+    declared = set(re.findall(r"\b(b200_\w+)\s*\(", hdr))
+    assert len(declared) >= 30
+    dll = ctypes.CDLL(lib.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(dll, s)]
+    assert not missing, missing
+    # the ctypes table mirrors the header one to one
+    assert declared == set(lib.SIGNATURES), declared ^ set(lib.SIGNATURES)
+    lib.load()
+    assert lib.query("b200_abi_version") == 1
+
+
+def test_dropin_contract_and_seeded_init(golden_tiny):
+    import midi_model as mm
+    assert mm.config_name_list == ["tv1-medium", "tv2-medium", "tv2o-medium", "tv2-large", "tv2o-large"]
+    torch.manual_seed(0)
+    cfg = mm.MIDIModelConfig.get_config("v2", True, n_layer=4, n_head=4, n_embd=32, n_inner=64)
+    m = mm.MIDIModel(cfg)
+    sd = m.state_dict()
+    for k, v in sd.items():      # same RNG consumption as the reference constructor => bit-identical weights
+        np.testing.assert_array_equal(v.numpy(), golden_tiny["sd/" + k], err_msg=k)
+    assert [n for n, _ in m.named_buffers()] == ["net.rotary_emb.inv_freq", "net.rotary_emb.original_inv_freq",
+                                                "net_token.rotary_emb.inv_freq", "net_token.rotary_emb.original_inv_freq"]
+    m16 = m.to(torch.bfloat16)
+    np.testing.assert_array_equal(m16.net.rotary_emb.inv_freq.float().numpy(), golden_tiny["bf16/inv_freq_net"])
+
+
+def test_medium_config_matches_reference_fixture(golden_medium):
+    import midi_model as mm
+    cfg = mm.MIDIModelConfig.from_name("tv2o-medium")
+    assert cfg.tokenizer.vocab_size == 3406 and cfg.n_embd == 1024
+    assert (cfg.net_config.num_hidden_layers, cfg.net_config.num_attention_heads, cfg.net_config.intermediate_size) == (12, 16, 4096)
+    assert (cfg.net_token_config.num_hidden_layers, cfg.net_token_config.num_attention_heads,
+            cfg.net_token_config.intermediate_size) == (3, 4, 1024)
+    large = mm.MIDIModelConfig.from_name("tv2o-large")
+    assert large.net_config.num_hidden_layers == 24 and large.net_token_config.num_hidden_layers == 6
+    assert large.net_config.hidden_size == 1024       # reference: 2x layers only
+    with pytest.raises(ValueError):
+        mm.MIDIModelConfig.from_name("tv3-medium")
+    d = cfg.to_dict()
+    cfg2 = mm.MIDIModelConfig(**{k: d[k] for k in ("tokenizer", "net_config", "net_token_config")})
+    assert cfg2.net_config.hidden_size == 1024 and cfg2.tokenizer.vocab_size == 3406
+
+
+def test_medium_seeded_init_and_oracle_golden(golden_medium):
+    """The drop-in class regenerates the reference's seed-0 tv2o-medium weights; the oracle on them reproduces
+    the reference's fp32 hidden / logits / loss fixture."""
+    import midi_model as mm
+    from oracle import midi_oracle as O
+    g = golden_medium
+    torch.manual_seed(0)
+    m = mm.MIDIModel(mm.MIDIModelConfig.from_name("tv2o-medium"))
+    sd = m.state_dict()
+    assert len(sd) == int(g["n_tensors"]) == 140 and sum(v.numel() for v in sd.values()) == int(g["n_params"]) == 233842688
+    for k in [k[5:] for k in g if k.startswith("init/")]:
+        v = sd[k].double()
+        got = np.array([v.sum().item(), v.abs().sum().item(), v.flatten()[12345 % v.numel()].item()])
+        np.testing.assert_allclose(got, g["init/" + k], rtol=1e-12)
+    ocfg = O.cfg_from_hf(m.config)
+    batch = torch.from_numpy(g["batch"])
+    sd = {k: v.detach() for k, v in sd.items()}
+    with torch.no_grad():
+        h = O.forward(sd, ocfg, batch[:, :-1])
+        lg = O.forward_token(sd, ocfg, h.reshape(-1, 1024), batch[:, 1:].reshape(-1, 8)[:, :-1])
+        loss = O.train_loss(sd, ocfg, batch)
+    np.testing.assert_allclose(h.reshape(-1, 1024).numpy()[:, :64], g["fp32/hidden"], rtol=2e-3, atol=2e-4)
+    np.testing.assert_allclose(lg.numpy()[:, :, :128], g["fp32/logits"], rtol=2e-3, atol=2e-4)
+    assert abs(h.double().norm().item() - float(g["fp32/hidden_norm"])) < 1e-3 * float(g["fp32/hidden_norm"])
+    assert abs(loss.item() - float(g["fp32/loss"])) < 1e-4
+
+
+def test_no_cpu_fallback():
+    import midi_model as mm
+    from midi_b200.lib import B200Error
+    cfg = mm.MIDIModelConfig.get_config("v2", True, n_layer=4, n_head=4, n_embd=32, n_inner=64)
+    m = mm.MIDIModel(cfg)
+    with pytest.raises(B200Error):
+        m.forward(torch.zeros(1, 2, 8, dtype=torch.long))
+    with pytest.raises(B200Error):
+        m.sample_top_p_k(torch.ones(1, 1, 3406) / 3406, 0.98, 20)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "midi-model_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), os.path.join(dp, f)
+
+
+def test_synth_batch_is_grammar_valid():
+    from midi_b200.synth import synth_batch
+    from midi_b200.tokenizer_tables import TokenizerTables
+    tok = TokenizerTables("v2")
+    b = synth_batch(tok, 3, 50, seed=1, pad_tail=4)
+    assert b.shape == (3, 50, 8) and b.dtype == torch.int64
+    assert (b[:, 0, 0] == tok.bos_id).all() and (b[:, 0, 1:] == 0).all()
+    assert (b[:, -4:] == 0).all()
+    for row in b[:, 1:-4].reshape(-1, 8).tolist():
+        assert tok.tokens2event(row) != []
+    assert torch.equal(b, synth_batch(tok, 3, 50, seed=1, pad_tail=4))
