@@ -36,6 +36,7 @@ typedef struct CUstream_st* cudaStream_t;
 /* ---- runtime ------------------------------------------------------------------------------ */
 const char* b200_last_error(void);
 int b200_abi_version(void);
+long long b200_launch_count(void);   /* kernels launched by this library so far (all threads) */
 int b200_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* ---- embeddings (midi_model.py:145-146 `embed_tokens(x).sum(-2)`; :126-131 cat([hidden, embed(x)])) */

@@ -30,8 +30,13 @@ void b200_set_error(const char* fmt, ...);
         }                                        \
     } while (0)
 
+// every kernel launch of this library is counted (bench.py reports `gpu_launches` from it)
+void b200_count_launches(int n);
+#define B200_COUNT_EXTRA(n) b200_count_launches(n)
+
 #define B200_CHECK_LAUNCH(name)                                                       \
     do {                                                                              \
+        b200_count_launches(1);                                                       \
         cudaError_t e__ = cudaGetLastError();                                         \
         if (e__ != cudaSuccess) {                                                     \
             b200_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));   \

@@ -477,6 +477,7 @@ extern "C" int b200_attn_decode(const void* q, const void* k_pool, const void* v
         decode_attn_kernel<256><<<grid, 128, 0, stream>>>((const bf16*)q, L, (float*)workspace, s_q, past, past_dev, ldq, scale, n_split);
         decode_attn_combine_kernel<256><<<rows * n_heads, 128, 0, stream>>>((const float*)workspace, (bf16*)out, n_heads, n_split, ldo);
     }
+    B200_COUNT_EXTRA(1);
     B200_CHECK_LAUNCH("attn_decode");
     return B200_OK;
 }

@@ -421,6 +421,7 @@ extern "C" int b200_embed_bwd(const long long* ids, int n_ids, const void* dout,
         dim3 grid(V, 32);
         embed_segsum_kernel<<<grid, ROW_THREADS, 0, stream>>>(offsets, sorted, (const bf16*)dout, acc32, H, per_row,
                                                               row_stride, row_inner, row_off, pad_id);
+        B200_COUNT_EXTRA(4);
     }
     const size_t n = (size_t)V * H;
     f32_to_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(acc32, (bf16*)dtable, n, accumulate);

@@ -14,6 +14,11 @@ void b200_set_error(const char* fmt, ...) {
 
 extern "C" const char* b200_last_error(void) { return g_err; }
 
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+void b200_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" long long b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
 int b200_num_sms() {
     static int sms = 0;
     if (sms == 0) {

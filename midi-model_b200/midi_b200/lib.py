@@ -21,6 +21,7 @@ vp, i32, i64, f32, sz, u64 = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_s
 SIGNATURES = {
     "b200_last_error": (C.c_char_p, []),
     "b200_abi_version": (i32, []),
+    "b200_launch_count": (i64, []),
     "b200_device_info": (i32, [vp, vp, vp]),
     "b200_embed_sum_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
     "b200_inner_input_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),

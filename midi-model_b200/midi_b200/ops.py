@@ -14,6 +14,7 @@ from . import lib
 
 BF16 = torch.bfloat16
 _ws_cache: dict = {}
+GEMM_PROFILE = None   # bench.py sets this to a list: (start_event, end_event, flops) per tensor-core GEMM launch
 
 
 def _ws(key, nbytes: int, device) -> torch.Tensor:
@@ -139,8 +140,15 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, lda: int, 
         ws = _ws("gemm", nbytes, A.device)
         ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
     ldr = residual.stride(0) if residual is not None else 0
+    prof = GEMM_PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     lib.call("b200_gemm_bf16", A.data_ptr(), B.data_ptr(), out.data_ptr(), lib.ptr(residual), M, N, K, lda, ldb, ldc, ldr,
              int(a_mn), int(b_mn), int(accumulate), block_n, splits, ws_ptr, ws_bytes, lib.stream())
+    if prof is not None:
+        e1.record()
+        prof.append((e0, e1, 2.0 * M * N * K))
     return out
 
 

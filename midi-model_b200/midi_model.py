@@ -130,7 +130,7 @@ class _OuterFn(torch.autograd.Function):
         rt = model._rt()
         B, S, T = x_ids.shape
         ids = _flat_ids(x_ids).view(B * S, T)
-        need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        need = any(ctx.needs_input_grad)   # (grad mode is off inside Function.forward; this is the reliable signal)
         e = _ops.embed_sum(ids, rt.outer.embed)
         y, sv = rt.outer.forward(e, B, S, model.net.rotary_emb.inv_freq, save=need)
         ctx.model, ctx.sv, ctx.ids, ctx.shape = model, sv, ids, (B, S, T)
@@ -160,8 +160,7 @@ class _InnerFn(torch.autograd.Function):
         ids = _flat_ids(x_ids) if x_ids is not None else None
         n_ids = 0 if ids is None else ids.shape[1]
         L = n_ids + (1 if hidden is not None else 0)
-        need = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or
-                                            (hidden is not None and hidden.requires_grad))
+        need = any(ctx.needs_input_grad)
         hid = hidden.to(torch.bfloat16).contiguous() if hidden is not None else None
         xin = _ops.inner_input(hid, ids, rt.inner.embed)
         hs, sv = rt.inner.forward(xin, N, L, model.net_token.rotary_emb.inv_freq, save=need)
