@@ -62,8 +62,9 @@ int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* 
 /* ---- RoPE (hf modeling_llama.py:124-168), applied in place to the q,k thirds of packed qkv -------- */
 int b200_rope_table(const float* inv_freq, int half, int n_pos, int pos0, const int* pos0_dev /*may be NULL*/,
                     void* cos_t, void* sin_t, cudaStream_t s);
+/* row r sits at absolute position pos0 (+ *pos0_dev) + r % S; tables are indexed by absolute position */
 int b200_rope_qk(void* qkv, const void* cos_t, const void* sin_t, int rows, int S, int H, int D, int ld, int backward,
-                 cudaStream_t s);
+                 int pos0, const int* pos0_dev /*may be NULL*/, cudaStream_t s);
 
 /* ---- SwiGLU (hf modeling_llama.py:183) on packed [rows, 2I] = [gate | up] ------------------------- */
 int b200_swiglu_fwd(const void* gu, void* act, long long rows, int I, cudaStream_t s);
@@ -131,6 +132,9 @@ int b200_sample_from_logits(const void* logits, int rows, int V, int ld, float t
                             int out_stride, cudaStream_t s);
 int b200_uniform_fill(float* u, int n, unsigned long long seed, unsigned long long* counter_dev, cudaStream_t s);
 int b200_add_int(int* p, int v, cudaStream_t s);
+/* graph-captured generate loop: commit the event sampled into ev_t [T][B] to seq[:, *pos+1] and ev_next; (*pos)++ */
+int b200_event_commit(const long long* ev_t, long long* seq, long long* ev_next, int* pos_dev, int B, int T, int max_len,
+                      cudaStream_t s);
 
 #ifdef __cplusplus
 }

@@ -393,6 +393,21 @@ __global__ void philox_uniform_kernel(float* __restrict__ u, int n, unsigned lon
 
 __global__ void add_int_kernel(int* p, int v) { *p += v; }
 
+// End of one generated event (graph-captured loop): ev_t [T][B] (token-major scratch written by the sampler)
+// -> seq[b, *pos + 1, :] and ev_next[b, :] (input of the next outer step); then (*pos)++.
+__global__ void event_commit_kernel(const long long* __restrict__ ev_t, long long* __restrict__ seq,
+                                    long long* __restrict__ ev_next, int* __restrict__ pos, int B, int T, int max_len) {
+    const int p = *pos;
+    for (int i = threadIdx.x; i < B * T; i += blockDim.x) {
+        const int b = i / T, t = i % T;
+        const long long v = ev_t[(size_t)t * B + b];
+        if (p + 1 < max_len) seq[((size_t)b * max_len + p + 1) * T + t] = v;
+        ev_next[(size_t)b * T + t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *pos = p + 1;
+}
+
 }   // namespace
 
 // =============================================================================================
@@ -515,6 +530,13 @@ extern "C" int b200_uniform_fill(float* u, int n, unsigned long long seed, unsig
     B200_CHECK_ARG(n >= 1 && n <= 1024, "uniform_fill: n outside 1..1024");
     philox_uniform_kernel<<<1, 1024, 0, stream>>>(u, n, seed, counter_dev);
     B200_CHECK_LAUNCH("uniform_fill");
+    return B200_OK;
+}
+
+extern "C" int b200_event_commit(const long long* ev_t, long long* seq, long long* ev_next, int* pos_dev, int B, int T,
+                                 int max_len, cudaStream_t stream) {
+    event_commit_kernel<<<1, 256, 0, stream>>>(ev_t, seq, ev_next, pos_dev, B, T, max_len);
+    B200_CHECK_LAUNCH("event_commit");
     return B200_OK;
 }
 

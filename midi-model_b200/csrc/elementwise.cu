@@ -276,14 +276,15 @@ __global__ void rope_table_kernel(const float* __restrict__ inv_freq, int half, 
     sin_t[i] = __float2bfloat16_rn(sinf(f));
 }
 
-// In place on the q and k thirds of packed qkv rows [rows, 3*H]; position of row r = r % S.
+// In place on the q and k thirds of packed qkv rows [rows, 3*H]; position of row r = pos0 (+ *pos0_dev) + r % S
+// (the tables cover absolute positions).
 // forward : o1 = bf16(bf16(x1*c) + bf16(-x2*s)), o2 = bf16(bf16(x2*c) + bf16(x1*s))   (three roundings, A.4)
 // backward: dx1 = do1*c + do2*s, dx2 = do2*c - do1*s  (one rounding)
 template <bool BWD>
 __global__ void rope_kernel(bf16* __restrict__ qkv, const bf16* __restrict__ cos_t, const bf16* __restrict__ sin_t,
-                            int rows, int S, int H, int D, int ld) {
+                            int rows, int S, int H, int D, int ld, int pos0, const int* __restrict__ pos0_dev) {
     const int r = blockIdx.x;
-    const int s = r % S;
+    const int s = pos0 + (pos0_dev ? *pos0_dev : 0) + r % S;
     const int half = D / 2;
     const int vec_per_head = half / 8;
     const int heads2 = 2 * (H / D);   // q heads then k heads (k third starts at column H)
@@ -476,13 +477,13 @@ extern "C" int b200_rope_table(const float* inv_freq, int half, int n_pos, int p
 }
 
 extern "C" int b200_rope_qk(void* qkv, const void* cos_t, const void* sin_t, int rows, int S, int H, int D, int ld,
-                            int backward, cudaStream_t stream) {
+                            int backward, int pos0, const int* pos0_dev, cudaStream_t stream) {
     B200_CHECK_ARG(D % 16 == 0 && H % D == 0 && ld % 8 == 0, "rope: head_dim must be a multiple of 16");
     if (rows == 0) return B200_OK;
     if (backward)
-        rope_kernel<true><<<rows, ROW_THREADS, 0, stream>>>((bf16*)qkv, (const bf16*)cos_t, (const bf16*)sin_t, rows, S, H, D, ld);
+        rope_kernel<true><<<rows, ROW_THREADS, 0, stream>>>((bf16*)qkv, (const bf16*)cos_t, (const bf16*)sin_t, rows, S, H, D, ld, pos0, pos0_dev);
     else
-        rope_kernel<false><<<rows, ROW_THREADS, 0, stream>>>((bf16*)qkv, (const bf16*)cos_t, (const bf16*)sin_t, rows, S, H, D, ld);
+        rope_kernel<false><<<rows, ROW_THREADS, 0, stream>>>((bf16*)qkv, (const bf16*)cos_t, (const bf16*)sin_t, rows, S, H, D, ld, pos0, pos0_dev);
     B200_CHECK_LAUNCH("rope");
     return B200_OK;
 }

@@ -81,14 +81,13 @@ class CachedStack:
         T = past + s_new
         if T > kv.capacity or T > self.max_pos:
             raise lib.B200Error(f"KV cache overflow: {T} positions > capacity {min(kv.capacity, self.max_pos)}")
-        cos, sin = self.cos[past:past + s_new], self.sin[past:past + s_new]
         scale = 1.0 / math.sqrt(D)
         n_split = max(1, min(32, (T + 255) // 256)) if D == 64 else 1
         ws_bytes = lib.query("b200_attn_decode_workspace_bytes", B * s_new, nh, D, n_split)
         for li, w in enumerate(self.eng.layers):
             n1 = ops.rmsnorm(x, w.ln1, c.eps)
             qkv = _linear(n1, w.qkv)
-            ops.rope_qk_(qkv, cos, sin, s_new, H, D)
+            ops.rope_qk_(qkv, self.cos, self.sin, s_new, H, D, pos0=past)
             lib.call("b200_kv_append", qkv.data_ptr(), kv.k[li].data_ptr(), kv.v[li].data_ptr(), kv.block_table.data_ptr(),
                      kv.max_pages, kv.page, nh, D, B, s_new, past, None, qkv.stride(0), lib.stream())
             if past == 0 and s_new > 1 and D == 64:

@@ -32,7 +32,7 @@ SIGNATURES = {
     "b200_rmsnorm_bwd_parts": (i32, []),
     "b200_rmsnorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]),
     "b200_rope_table": (i32, [vp, i32, i32, i32, vp, vp, vp, vp]),
-    "b200_rope_qk": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "b200_rope_qk": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
     "b200_swiglu_fwd": (i32, [vp, vp, i64, i32, vp]),
     "b200_swiglu_bwd": (i32, [vp, vp, vp, i64, i32, vp]),
     "b200_gemm_workspace_bytes": (sz, [i32, i32, i32]),
@@ -55,6 +55,7 @@ SIGNATURES = {
     "b200_sample_from_logits": (i32, [vp, i32, i32, i32, f32, f32, i32, i32, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp]),
     "b200_uniform_fill": (i32, [vp, i32, u64, vp, vp]),
     "b200_add_int": (i32, [vp, i32, vp]),
+    "b200_event_commit": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
 }
 
 

@@ -93,9 +93,12 @@ def rope_table(inv_freq: torch.Tensor, n_pos: int, pos0: int = 0):
     return cos, sin
 
 
-def rope_qk_(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, S: int, H: int, D: int, backward: bool = False):
+def rope_qk_(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, S: int, H: int, D: int, backward: bool = False,
+             pos0: int = 0, pos0_dev: Optional[torch.Tensor] = None):
+    """cos/sin are indexed by absolute position; row r sits at pos0 (+ *pos0_dev) + r % S."""
     rows, ld = qkv.shape
-    lib.call("b200_rope_qk", qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), rows, S, H, D, ld, int(backward), lib.stream())
+    lib.call("b200_rope_qk", qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), rows, S, H, D, ld, int(backward), pos0,
+             lib.ptr(pos0_dev), lib.stream())
 
 
 def swiglu(gu: torch.Tensor) -> torch.Tensor:
