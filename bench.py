@@ -232,8 +232,20 @@ def run_native(args):
     prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
     clocks = sampler.stop(t0, t1)
     torch.cuda.synchronize()
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
-    gemm_flops = sum(f for _, _, f in prof)
+    gemm_ms = sum(p[0].elapsed_time(p[1]) for p in prof)
+    gemm_flops = sum(p[2] for p in prof)
+    shapes = {}
+    for e0, e1, fl, key in prof:
+        ent = shapes.setdefault(key, [0, 0.0, 0.0])
+        ent[0] += 1
+        ent[1] += e0.elapsed_time(e1)
+        ent[2] += fl
+    per_shape = sorted(([*k, c, round(ms / K, 4), round(fl / (ms / 1e3) / 1e12, 1)] for k, (c, ms, fl) in shapes.items()),
+                       key=lambda r: -r[-2])
+    if rank == 0 and os.environ.get("B200_BENCH_VERBOSE"):
+        print("M N K a_mn b_mn block_n splits count ms/step TF/s", file=sys.stderr)
+        for r in per_shape:
+            print(*r, file=sys.stderr)
 
     losses = []
 
@@ -268,8 +280,11 @@ def run_native(args):
                      "frac": ach_tf / peak_tf if peak_tf else None, "traffic": None,
                      "kernel": "gemm_tcgen05_kernel (all launches of the timed steps)", "peak_kind": f"{pk_kind} sustained cuBLAS bf16",
                      "gemm_ms_per_step": gemm_ms / K, "gemm_share_of_step": gemm_ms / ms_total if ms_total else None,
-                     "whole_step_model_tflops": step_tf, "whole_step_frac": step_tf / peak_tf if peak_tf else None},
+                     "whole_step_model_tflops": step_tf, "whole_step_frac": step_tf / peak_tf if peak_tf else None,
+                     "per_shape": {"columns": "M,N,K,a_mn,b_mn,block_n,splits,launches,ms_per_step,TFLOP/s", "rows": per_shape}},
     }
+    if not args.no_generate:
+        line["generate"] = generate_leg(model, dev, world, rank)
     if world == 1 and not args.no_cpu_baseline:
         v, ms, cores, sample = cpu_train_step_tokens_per_s(3, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_step": ms}
@@ -281,6 +296,40 @@ def run_native(args):
     return 0
 
 
+def generate_leg(model, dev, world, rank):
+    """BASELINE.json's second metric: events/s of the KV-cached generate loop (midi_model.py:167-250) with the
+    reference's default sampling (temp 1.0, top-p 0.98, top-k 20), from one BOS event; replicas only across GPUs
+    (each rank generates its own rows, no collective).  EOS stopping is disabled so the event count is fixed
+    (seeded-init weights emit EOS at random)."""
+    import torch.distributed as dist
+    from midi_b200 import decode as dec
+    rt = model._rt()
+    tok = model.tokenizer
+    res = {"unit": "events/s", "sampling": "temp=1.0 top_p=0.98 top_k=20", "note": "one CUDA-graph replay per event; wall clock incl. launches"}
+    for B, n_new in ((1, 512), (8, 512)):
+        gg = dec.GraphGenerator(model._cached_stack("outer"), model._cached_stack("inner"), rt.lm_head, rt.pitch, rt.V, tok,
+                                dec.GrammarLUT(tok, dev), B, n_new + 1, 1.0, 0.98, 20, 1234 + rank)
+        prompt = torch.full((B, 1, tok.max_token_seq), tok.pad_id, dtype=torch.long, device=dev)
+        prompt[:, 0, 0] = tok.bos_id
+        gg.run(prompt, check_every=1 << 30, stop_on_eos=False)      # captures the graph + warm-up
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        out = gg.run(prompt, check_every=1 << 30, stop_on_eos=False)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        assert out.shape[1] == n_new + 1
+        res[f"batch{B}"] = {"events_per_s": world * B * n_new / dt, "ms_per_event_step": 1e3 * dt / n_new, "rows": world * B,
+                            "new_events_per_row": n_new}
+        del gg
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -288,6 +337,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-generate", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -77,6 +77,8 @@ int b200_swiglu_bwd(const void* gu, const void* dact, void* dgu, long long rows,
  *      splits > 1 or accumulate: fp32 split-K partials in `workspace`, reduced (and added to C). */
 size_t b200_gemm_workspace_bytes(int M, int N, int splits);
 int b200_gemm_suggest_splits(int M, int N, int K, int block_n);
+/* cheapest (block_n in {128,256}, split-K factor) for an [M,N,K] problem on this device */
+int b200_gemm_plan(int M, int N, int K, int allow_split, int* block_n_out, int* splits_out);
 int b200_gemm_bf16(const void* A, const void* B, void* C, const void* R, int M, int N, int K, int lda, int ldb, int ldc,
                    int ldr, int a_mn_major, int b_mn_major, int accumulate, int block_n, int splits, void* workspace,
                    size_t workspace_bytes, cudaStream_t s);
@@ -130,7 +132,8 @@ int b200_sample_from_logits(const void* logits, int rows, int V, int ld, float t
                             const long long* event_tok, const int* lut, int n_event_types, int eos_id, int pad_id,
                             const unsigned char* dense_mask /*may be NULL*/, const float* uniforms, long long* out,
                             int out_stride, cudaStream_t s);
-int b200_uniform_fill(float* u, int n, unsigned long long seed, unsigned long long* counter_dev, cudaStream_t s);
+/* state_dev = {call counter (incremented), device-side seed}: u[i] = hash(seed ^ state[1], state[0], i) */
+int b200_uniform_fill(float* u, int n, unsigned long long seed, unsigned long long* state_dev, cudaStream_t s);
 int b200_add_int(int* p, int v, cudaStream_t s);
 /* graph-captured generate loop: commit the event sampled into ev_t [T][B] to seq[:, *pos+1] and ev_next; (*pos)++ */
 int b200_event_commit(const long long* ev_t, long long* seq, long long* ev_next, int* pos_dev, int B, int T, int max_len,

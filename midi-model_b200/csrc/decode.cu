@@ -376,10 +376,12 @@ sample_logits_kernel(const bf16* __restrict__ logits, int V, int ld, float temp,
     if (threadIdx.x == 0) out[(size_t)r * out_stride] = id;
 }
 
-// counter-based uniform generator for graph-captured loops: u[r] = hash(seed, counter, r) in [0,1)
+// counter-based uniform generator for graph-captured loops: u[r] = hash(seed ^ state[1], state[0], r) in [0,1);
+// state = {call counter, device-side seed} so that a captured graph can be re-seeded without re-capture
 __global__ void philox_uniform_kernel(float* __restrict__ u, int n, unsigned long long seed, unsigned long long* counter) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long c = *counter;
+    unsigned long long c = counter[0];
+    seed ^= counter[1];
     if (i < n) {
         unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (c * 4096ULL + (unsigned long long)i + 1ULL);
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;

@@ -251,14 +251,121 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, cons
         }
     }
 }
+// ---- warp-per-row variants (hidden = 256 * VPT): no block barrier, reductions are 5 shuffles; each lane owns
+// VPT 16-byte vectors of the row (coalesced 512 B per warp access).  These are the ones used at hidden = 1024.
+constexpr int WR_WARPS = 8;        // forward
+constexpr int WRB_WARPS = 4;       // backward (155 regs/thread at hidden=1024 -> 3 CTAs of 4 warps per SM)
+
+template <int VPT>
+__global__ void __launch_bounds__(WR_WARPS * 32)
+rmsnorm_fwd_warp_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
+                        float* __restrict__ rstd_out, int M, float eps) {
+    constexpr int H = 256 * VPT;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float wv[VPT][8];
+#pragma unroll
+    for (int k = 0; k < VPT; k++) unpack8(*reinterpret_cast<const uint4*>(w + (lane + k * 32) * 8), wv[k]);
+    for (int m = blockIdx.x * WR_WARPS + warp; m < M; m += gridDim.x * WR_WARPS) {
+        float xv[VPT][8];
+        float ss = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPT; k++) {
+            unpack8(ld_nc16(x + (size_t)m * H + (lane + k * 32) * 8), xv[k]);
+#pragma unroll
+            for (int j = 0; j < 8; j++) ss = fmaf(xv[k][j], xv[k][j], ss);
+        }
+        ss = warp_sum(ss);
+        const float rstd = rsqrtf(ss / (float)H + eps);
+        if (lane == 0 && rstd_out) rstd_out[m] = rstd;
+#pragma unroll
+        for (int k = 0; k < VPT; k++) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) o[j] = wv[k][j] * bf16_round(xv[k][j] * rstd);
+            *reinterpret_cast<uint4*>(y + (size_t)m * H + (lane + k * 32) * 8) = pack8(o);
+        }
+    }
+}
+
+template <int VPT>
+__global__ void __launch_bounds__(WRB_WARPS * 32)
+rmsnorm_bwd_warp_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
+                        const float* __restrict__ rstd_in, const bf16* __restrict__ dres, bf16* __restrict__ dx,
+                        float* __restrict__ dw_partial, int M) {
+    constexpr int H = 256 * VPT;
+    extern __shared__ float wr_smem[];   // [WRB_WARPS][H]
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float wv[VPT][8], dwacc[VPT][8];
+#pragma unroll
+    for (int k = 0; k < VPT; k++) {
+        unpack8(*reinterpret_cast<const uint4*>(w + (lane + k * 32) * 8), wv[k]);
+#pragma unroll
+        for (int j = 0; j < 8; j++) dwacc[k][j] = 0.f;
+    }
+    for (int m = blockIdx.x * WRB_WARPS + warp; m < M; m += gridDim.x * WRB_WARPS) {
+        const float rstd = rstd_in[m];
+        float nn[VPT][8], dn[VPT][8];
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPT; k++) {
+            float xv[8], dyv[8];
+            unpack8(ld_nc16(x + (size_t)m * H + (lane + k * 32) * 8), xv);
+            unpack8(ld_nc16(dy + (size_t)m * H + (lane + k * 32) * 8), dyv);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                nn[k][j] = xv[j] * rstd;
+                dn[k][j] = dyv[j] * wv[k][j];
+                dot = fmaf(dn[k][j], nn[k][j], dot);
+                dwacc[k][j] = fmaf(dyv[j], nn[k][j], dwacc[k][j]);
+            }
+        }
+        dot = warp_sum(dot) / (float)H;
+#pragma unroll
+        for (int k = 0; k < VPT; k++) {
+            float o[8];
+            if (dres) unpack8(ld_nc16(dres + (size_t)m * H + (lane + k * 32) * 8), o);
+            else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) o[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) o[j] += rstd * (dn[k][j] - nn[k][j] * dot);
+            *reinterpret_cast<uint4*>(dx + (size_t)m * H + (lane + k * 32) * 8) = pack8(o);
+        }
+    }
+    // block-level reduction of the per-warp dw partials, one partial row per CTA
+#pragma unroll
+    for (int k = 0; k < VPT; k++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) wr_smem[warp * H + (lane + k * 32) * 8 + j] = dwacc[k][j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < H; c += blockDim.x) {
+        float t = 0.f;
+#pragma unroll
+        for (int wi = 0; wi < WRB_WARPS; wi++) t += wr_smem[wi * H + c];
+        dw_partial[(size_t)blockIdx.x * H + c] = t;
+    }
+}
+
 __global__ void colsum_partial_kernel(const float* __restrict__ partial, int nparts, int H, bf16* __restrict__ out,
                                       int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= H) return;
+    // block (32, 8): x = column inside a 32-column tile, y = slice of the partial rows
+    __shared__ float sh[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
     float s = 0.f;
-    for (int p = 0; p < nparts; p++) s += partial[(size_t)p * H + c];
-    if (accumulate) s = bf16_round(s) + __bfloat162float(out[c]);
-    out[c] = __float2bfloat16_rn(s);
+    if (c < H)
+        for (int p = threadIdx.y; p < nparts; p += 8) s += partial[(size_t)p * H + c];
+    sh[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < H) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) t += sh[i][threadIdx.x];
+        if (accumulate) t = bf16_round(t) + __bfloat162float(out[c]);
+        out[c] = __float2bfloat16_rn(t);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -434,6 +541,16 @@ extern "C" int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rs
                                 cudaStream_t stream) {
     B200_CHECK_ARG(H % 8 == 0 && H <= ROW_THREADS * 8 * MAXV, "rmsnorm_fwd: unsupported hidden size %d", H);
     if (M == 0) return B200_OK;
+    if (H == 256 || H == 512 || H == 1024 || H == 2048) {
+        int g = (M + WR_WARPS - 1) / WR_WARPS;
+        const int cap = b200_num_sms() * 8;
+        if (g > cap) g = cap;
+#define B200_RMS_FWDW(V) rmsnorm_fwd_warp_kernel<V><<<g, WR_WARPS * 32, 0, stream>>>((const bf16*)x, (const bf16*)w, (bf16*)y, rstd, M, eps)
+        if (H == 256) B200_RMS_FWDW(1); else if (H == 512) B200_RMS_FWDW(2); else if (H == 1024) B200_RMS_FWDW(4); else B200_RMS_FWDW(8);
+#undef B200_RMS_FWDW
+        B200_CHECK_LAUNCH("rmsnorm_fwd");
+        return B200_OK;
+    }
     const int grid = M < b200_num_sms() * 16 ? M : b200_num_sms() * 16;
     const int vpt = (H / 8 + ROW_THREADS - 1) / ROW_THREADS;
 #define B200_RMS_FWD(V) rmsnorm_fwd_kernel<V><<<grid, ROW_THREADS, 0, stream>>>((const bf16*)x, (const bf16*)w, (bf16*)y, rstd, M, H, eps)
@@ -443,7 +560,7 @@ extern "C" int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rs
     return B200_OK;
 }
 
-extern "C" int b200_rmsnorm_bwd_parts(void) { return b200_num_sms() * 4; }
+extern "C" int b200_rmsnorm_bwd_parts(void) { return b200_num_sms() * 3; }
 
 // workspace: float[b200_rmsnorm_bwd_parts() * H]
 extern "C" int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres,
@@ -453,14 +570,40 @@ extern "C" int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, co
     const int parts = b200_rmsnorm_bwd_parts();
     B200_CHECK_ARG(workspace_bytes >= (size_t)parts * H * sizeof(float), "rmsnorm_bwd: workspace too small");
     if (M == 0) return B200_OK;
+    if (H == 256 || H == 512 || H == 1024) {
+        int g = (M + WRB_WARPS - 1) / WRB_WARPS;
+        if (g > parts) g = parts;
+        const size_t smem = (size_t)WRB_WARPS * H * sizeof(float);
+#define B200_RMS_BWDW(V)                                                                                              \
+    do {                                                                                                              \
+        static bool cfg = false;                                                                                      \
+        if (!cfg) {                                                                                                   \
+            B200_CUDA(cudaFuncSetAttribute(rmsnorm_bwd_warp_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                           (int)smem), "rmsnorm_bwd smem");                                           \
+            cfg = true;                                                                                               \
+        }                                                                                                             \
+        rmsnorm_bwd_warp_kernel<V><<<g, WRB_WARPS * 32, smem, stream>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, \
+                                                                       rstd, (const bf16*)dres, (bf16*)dx,            \
+                                                                       (float*)workspace, M);                         \
+    } while (0)
+        if (H == 256) B200_RMS_BWDW(1); else if (H == 512) B200_RMS_BWDW(2); else B200_RMS_BWDW(4);
+#undef B200_RMS_BWDW
+        B200_CHECK_LAUNCH("rmsnorm_bwd");
+        if (dw) {
+            colsum_partial_kernel<<<(H + 31) / 32, dim3(32, 8), 0, stream>>>((const float*)workspace, g, H, (bf16*)dw,
+                                                                            accumulate_dw);
+            B200_CHECK_LAUNCH("rmsnorm_bwd_dw");
+        }
+        return B200_OK;
+    }
     const int vpt = (H / 8 + ROW_THREADS - 1) / ROW_THREADS;
 #define B200_RMS_BWD(V) rmsnorm_bwd_kernel<V><<<parts, ROW_THREADS, 0, stream>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, rstd, (const bf16*)dres, (bf16*)dx, (float*)workspace, M, H)
     if (vpt <= 1) B200_RMS_BWD(1); else if (vpt <= 2) B200_RMS_BWD(2); else if (vpt <= 4) B200_RMS_BWD(4); else B200_RMS_BWD(8);
 #undef B200_RMS_BWD
     B200_CHECK_LAUNCH("rmsnorm_bwd");
     if (dw) {
-        colsum_partial_kernel<<<(H + 127) / 128, 128, 0, stream>>>((const float*)workspace, parts, H, (bf16*)dw,
-                                                                  accumulate_dw);
+        colsum_partial_kernel<<<(H + 31) / 32, dim3(32, 8), 0, stream>>>((const float*)workspace, parts, H, (bf16*)dw,
+                                                                        accumulate_dw);
         B200_CHECK_LAUNCH("rmsnorm_bwd_dw");
     }
     return B200_OK;

@@ -9,6 +9,8 @@
 // and wgrad (A = dY, B = X as stored) without any transposed copies.
 // Epilogues: bf16 store; bf16 store + residual (two roundings, like `x + o_proj(..)`
 // in hf :325/:331); fp32 split-K partials reduced by splitk_reduce_kernel.
+#include <math.h>
+
 #include "common.cuh"
 
 namespace {
@@ -408,17 +410,55 @@ extern "C" size_t b200_gemm_workspace_bytes(int M, int N, int splits) {
     return splits > 1 ? (size_t)splits * M * N * sizeof(float) : 0;
 }
 
-// Suggest a split-K factor for an [M,N,K] problem so that at least ~one wave of CTAs is busy.
-extern "C" int b200_gemm_suggest_splits(int M, int N, int K, int block_n) {
-    const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + block_n - 1) / block_n);
+// Tile / split-K planner.  Work items = tiles(block_n) x splits run persistently on `sms` CTAs, so the cost is
+// (waves of items) x (k-blocks per item) in MMA clocks, plus pipeline fill, the exposed last epilogue and, for
+// splits > 1, the fp32 partial round trip.  Picks the cheapest (block_n, splits): this is what removes the
+// wave-quantisation loss of the small-output wgrad problems (e.g. 192 tiles on 148 SMs -> 3 splits, 3.9 waves).
+static double plan_cost(int M, int N, int K, int block_n, int s, int sms) {
+    const double tiles = (double)((M + BLOCK_M - 1) / BLOCK_M) * ((N + block_n - 1) / block_n);
     const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
-    int sms = b200_num_sms();
-    if (tiles >= sms) return 1;
-    int s = sms / tiles;
-    const int max_by_k = num_kb / 8 > 0 ? num_kb / 8 : 1;   // keep >= 8 k-blocks per split
-    if (s > max_by_k) s = max_by_k;
-    if (s > 16) s = 16;
-    return s < 1 ? 1 : s;
+    const int kb_per = (num_kb + s - 1) / s;
+    const int s_eff = (num_kb + kb_per - 1) / kb_per;
+    const double items = tiles * s_eff;
+    const double waves = ceil(items / sms);
+    // 4 UMMAs of 128 x block_n x 16 per k-block; 128-wide tiles pull 33% more operand bytes per FLOP (small penalty)
+    const double kb_clk = 2.0 * block_n * (block_n == 128 ? 1.08 : 1.0);
+    const double tile_ovh = 150.0 + (s_eff > 1 ? 1.0 : 0.5) * block_n * 6.0;   // accumulator hand-over + epilogue pressure
+    double c = waves * (kb_per * kb_clk + tile_ovh) + 2500.0;   // + fill and exposed tail epilogue
+    if (s_eff > 1) c += ((double)s_eff * M * N * 8.0 + (double)M * N * 2.0) / 5000.0 + 4000.0;   // bytes / (B/clk, mostly L2) + launch
+    return c;
+}
+
+extern "C" int b200_gemm_plan(int M, int N, int K, int allow_split, int* block_n_out, int* splits_out) {
+    const int sms = b200_num_sms();
+    double best = 1e300;
+    int bb = 128, bs = 1;
+    for (int bn = 128; bn <= 256; bn += 128) {
+        if (bn == 256 && N < 256) continue;
+        const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+        const int smax = allow_split ? (num_kb / 8 > 16 ? 16 : (num_kb / 8 > 0 ? num_kb / 8 : 1)) : 1;
+        for (int s = 1; s <= smax; s++) {
+            const double c = plan_cost(M, N, K, bn, s, sms);
+            if (c < best) { best = c; bb = bn; bs = s; }
+        }
+    }
+    *block_n_out = bb;
+    *splits_out = bs;
+    return B200_OK;
+}
+
+// legacy helper (kept for ABI stability): split factor for a fixed block_n
+extern "C" int b200_gemm_suggest_splits(int M, int N, int K, int block_n) {
+    const int sms = b200_num_sms();
+    const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+    const int smax = num_kb / 8 > 16 ? 16 : (num_kb / 8 > 0 ? num_kb / 8 : 1);
+    double best = 1e300;
+    int bs = 1;
+    for (int s = 1; s <= smax; s++) {
+        const double c = plan_cost(M, N, K, block_n, s, sms);
+        if (c < best) { best = c; bs = s; }
+    }
+    return bs;
 }
 
 extern "C" int b200_gemm_bf16(const void* A, const void* B, void* C, const void* R, int M, int N, int K, int lda, int ldb,

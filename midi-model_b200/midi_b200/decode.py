@@ -72,25 +72,36 @@ class CachedStack:
         self.cos, self.sin = ops.rope_table(inv_freq, max_pos)
         self.max_pos = max_pos
 
-    def step(self, x: torch.Tensor, kv: PagedKV, s_new: int) -> torch.Tensor:
-        """x: [batch * s_new, H] new inputs_embeds; appends to kv; returns final-normed hidden for the new rows."""
+    def step(self, x: torch.Tensor, kv: PagedKV, s_new: int, pos_dev: Optional[torch.Tensor] = None,
+             max_T: Optional[int] = None) -> torch.Tensor:
+        """x: [batch * s_new, H] new inputs_embeds; appends to kv; returns final-normed hidden for the new rows.
+        With `pos_dev` (int32[1] on the device) the number of cached positions is read by the kernels themselves
+        (CUDA-graph replay); `max_T` then bounds the context for the split-T decode attention."""
         c = self.eng.cfg
         H, D, nh = c.hidden, c.head_dim, c.n_head
         B = kv.batch
-        past = kv.length
-        T = past + s_new
+        dev_pos = pos_dev is not None
+        past = 0 if dev_pos else kv.length
+        T = max_T if dev_pos else past + s_new
         if T > kv.capacity or T > self.max_pos:
             raise lib.B200Error(f"KV cache overflow: {T} positions > capacity {min(kv.capacity, self.max_pos)}")
         scale = 1.0 / math.sqrt(D)
         n_split = max(1, min(32, (T + 255) // 256)) if D == 64 else 1
+        pd = lib.ptr(pos_dev)
         ws_bytes = lib.query("b200_attn_decode_workspace_bytes", B * s_new, nh, D, n_split)
         for li, w in enumerate(self.eng.layers):
             n1 = ops.rmsnorm(x, w.ln1, c.eps)
             qkv = _linear(n1, w.qkv)
-            ops.rope_qk_(qkv, self.cos, self.sin, s_new, H, D, pos0=past)
+            ops.rope_qk_(qkv, self.cos, self.sin, s_new, H, D, pos0=past, pos0_dev=pos_dev)
             lib.call("b200_kv_append", qkv.data_ptr(), kv.k[li].data_ptr(), kv.v[li].data_ptr(), kv.block_table.data_ptr(),
-                     kv.max_pages, kv.page, nh, D, B, s_new, past, None, qkv.stride(0), lib.stream())
-            if past == 0 and s_new > 1 and D == 64:
+                     kv.max_pages, kv.page, nh, D, B, s_new, past, pd, qkv.stride(0), lib.stream())
+            if dev_pos:
+                attn = torch.empty((B * s_new, H), dtype=BF16, device=x.device)
+                ws = ops._ws("attn_decode", ws_bytes, x.device)
+                lib.call("b200_attn_decode", qkv.data_ptr(), kv.k[li].data_ptr(), kv.v[li].data_ptr(),
+                         kv.block_table.data_ptr(), kv.max_pages, kv.page, attn.data_ptr(), B, s_new, nh, D, 0, pd, T,
+                         qkv.stride(0), H, scale, n_split, ws.data_ptr(), ws.numel(), lib.stream())
+            elif past == 0 and s_new > 1 and D == 64:
                 attn, _ = ops.attn_causal_fwd(qkv, B, s_new, nh, D, want_lse=False)
             elif past == 0 and s_new > 1 and D == 256 and s_new <= 8:
                 attn = ops.attn_tiny_fwd(qkv, B, s_new, nh, D)
@@ -105,7 +116,8 @@ class CachedStack:
             gu = _linear(n2, w.gu)
             act = ops.swiglu(gu)
             x = _linear(act, w.down, residual=h)
-        kv.length = T
+        if not dev_pos:
+            kv.length = T
         return ops.rmsnorm(x, self.eng.norm, c.eps)
 
 
@@ -139,3 +151,108 @@ def sample_from_logits(logits: torch.Tensor, V: int, temp: float, top_p: float, 
     lib.call("b200_sample_from_logits", logits.data_ptr(), B, V, logits.stride(0), temp, top_p, top_k, step,
              event_tok.data_ptr(), g.lut.data_ptr(), g.n_event_types, g.eos, g.pad, lib.ptr(dense_mask), uniforms.data_ptr(),
              out.data_ptr() + 8 * step, out.stride(0), lib.stream())
+
+
+class GraphGenerator:
+    """Device-resident generate loop: ONE CUDA graph = one generated event (the event-level decode step, the 8
+    token-level decode steps with their sampler launches, and the bookkeeping), replayed once per event.
+
+    State lives on the device: `pos` (events already in the KV cache), `ev_in` (the event fed to the event-level
+    stack next), `seq` (the output), the RNG counter.  Every inner step always runs (tokens past an event's last
+    parameter are forced to pad by the grammar, exactly what the reference pads with, midi_model.py:239-241), so
+    no host decision is needed inside an event; the reference's stop rule -- all rows emitted EOS in the same
+    event (midi_model.py:248) -- is applied on the host every `check_every` events and the output truncated there.
+    """
+
+    def __init__(self, outer: CachedStack, inner: CachedStack, lm_head: torch.Tensor, pitch: int, V: int, tok,
+                 grammar: GrammarLUT, batch: int, max_len: int, temp: float, top_p: float, top_k: int, seed: int):
+        dev = lm_head.device
+        self.outer, self.inner, self.lm_head, self.pitch, self.V = outer, inner, lm_head, pitch, V
+        self.tok, self.g, self.B, self.max_len = tok, grammar, batch, max_len
+        self.T = tok.max_token_seq
+        self.temp, self.top_p, self.top_k, self.seed = float(temp), float(top_p), int(top_k), int(seed) & ((1 << 63) - 1)
+        self.kv1 = PagedKV(outer.eng.cfg, batch, max_len, 64, dev)
+        self.kv2 = PagedKV(inner.eng.cfg, batch, self.T, self.T, dev)
+        self.pos = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.ev_in = torch.zeros((batch, self.T), dtype=torch.long, device=dev)
+        self.ev_t = torch.zeros((self.T, batch), dtype=torch.long, device=dev)
+        self.seq = torch.full((batch, max_len, self.T), tok.pad_id, dtype=torch.long, device=dev)
+        self.u = torch.zeros(batch, dtype=torch.float32, device=dev)
+        self.counter = torch.zeros(2, dtype=torch.int64, device=dev)   # {call counter, seed} read by the RNG kernel
+        self.graph = None
+        self.stream = torch.cuda.Stream(device=dev)
+
+    def _event(self):
+        B, T = self.B, self.T
+        emb_o, emb_i = self.outer.eng.embed, self.inner.eng.embed
+        e = ops.embed_sum(self.ev_in, emb_o)
+        hidden = self.outer.step(e, self.kv1, 1, pos_dev=self.pos, max_T=self.max_len)
+        self.kv2.reset()
+        for i in range(T):
+            if i == 0:
+                xin = ops.inner_input(hidden, None, emb_i)
+            else:
+                xin = ops.inner_input(None, self.ev_t[i - 1].view(B, 1), emb_i)
+            hs = self.inner.step(xin, self.kv2, 1)
+            logits = _lm_head(hs, self.lm_head, self.pitch)
+            lib.call("b200_uniform_fill", self.u.data_ptr(), B, 0, self.counter.data_ptr(), lib.stream())
+            lib.call("b200_sample_from_logits", logits.data_ptr(), B, self.V, logits.stride(0), self.temp, self.top_p,
+                     self.top_k, i, self.ev_t.data_ptr(), self.g.lut.data_ptr(), self.g.n_event_types, self.g.eos, self.g.pad,
+                     None, self.u.data_ptr(), self.ev_t.data_ptr() + 8 * B * i, 1, lib.stream())
+        lib.call("b200_event_commit", self.ev_t.data_ptr(), self.seq.data_ptr(), self.ev_in.data_ptr(), self.pos.data_ptr(),
+                 B, T, self.max_len, lib.stream())
+
+    def _set_state(self, prompt: torch.Tensor):
+        """prompt [B, P, T]: events 0..P-2 are prefilled into the KV cache; event P-1 is fed by the first replay."""
+        P = prompt.shape[1]
+        self.seq.fill_(self.tok.pad_id)
+        self.seq[:, :P] = prompt
+        self.kv1.reset()
+        if P > 1:
+            e = ops.embed_sum(prompt[:, :P - 1].reshape(self.B * (P - 1), self.T).contiguous(), self.outer.eng.embed)
+            self.outer.step(e, self.kv1, P - 1)
+        self.pos.fill_(P - 1)
+        self.ev_in.copy_(prompt[:, P - 1])
+        self.counter.copy_(torch.tensor([0, self.seed], dtype=torch.int64))
+
+    def run(self, prompt: torch.Tensor, use_graph: bool = True, check_every: int = 32, progress=None,
+            stop_on_eos: bool = True) -> torch.Tensor:
+        P = prompt.shape[1]
+        n_new = self.max_len - P
+        if n_new <= 0:
+            return prompt
+        cur = torch.cuda.current_stream()
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            self._set_state(prompt)
+            if use_graph and self.graph is None:
+                self._event()                       # warm-up (allocations, function attributes) outside capture
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.stream):
+                    self._event()
+                self.graph = g
+                self._set_state(prompt)             # undo the warm-up's state changes
+            done = 0
+            stop_at = None
+            while done < n_new:
+                n = min(check_every, n_new - done)
+                for _ in range(n):
+                    if use_graph:
+                        self.graph.replay()
+                    else:
+                        self._event()
+                done += n
+                if progress is not None:
+                    progress(n)
+                if not stop_on_eos:
+                    continue
+                first = self.seq[:, P:P + done, 0]                       # event-type token of every generated event
+                all_eos = (first == self.tok.eos_id).all(dim=0)          # one small D2H sync per `check_every` events
+                hit = torch.nonzero(all_eos)
+                if hit.numel() > 0:
+                    stop_at = P + int(hit[0].item()) + 1                 # the all-EOS event itself is kept
+                    break
+            out = self.seq[:, :(stop_at if stop_at is not None else P + done)].clone()
+        cur.wait_stream(self.stream)
+        return out

@@ -116,11 +116,20 @@ def swiglu_bwd(gu: torch.Tensor, dact: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------ GEMM
-def _pick_block_n(M: int, N: int) -> int:
-    sms = 148
-    if N % 256 == 0 and ((M + 127) // 128) * (N // 256) >= sms:
-        return 256
-    return 128
+_plan_cache: dict = {}
+
+
+def _plan(M: int, N: int, K: int, allow_split: bool):
+    """(block_n, splits) from the library's cost model (cached per shape)."""
+    key = (M, N, K, allow_split)
+    p = _plan_cache.get(key)
+    if p is None:
+        import ctypes
+        bn, sp = ctypes.c_int(0), ctypes.c_int(0)
+        lib.load().b200_gemm_plan(M, N, K, int(allow_split), ctypes.byref(bn), ctypes.byref(sp))
+        p = (bn.value, sp.value)
+        _plan_cache[key] = p
+    return p
 
 
 def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, lda: int, ldb: int, a_mn: bool = False,
@@ -131,10 +140,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, lda: int, 
         out = torch.empty((M, N), dtype=BF16, device=A.device)
     if ldc is None:
         ldc = out.stride(0)
-    block_n = _pick_block_n(M, N)
-    splits = 1
-    if allow_split and residual is None and ldc == N:
-        splits = lib.query("b200_gemm_suggest_splits", M, N, K, block_n)
+    block_n, splits = _plan(M, N, K, bool(allow_split and residual is None and ldc == N and N % 8 == 0))
     ws_ptr, ws_bytes = None, 0
     if splits > 1 or accumulate:
         nbytes = lib.query("b200_gemm_workspace_bytes", M, N, max(splits, 1))
@@ -151,7 +157,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, lda: int, 
              int(a_mn), int(b_mn), int(accumulate), block_n, splits, ws_ptr, ws_bytes, lib.stream())
     if prof is not None:
         e1.record()
-        prof.append((e0, e1, 2.0 * M * N * K))
+        prof.append((e0, e1, 2.0 * M * N * K, (M, N, K, int(a_mn), int(b_mn), block_n, splits)))
     return out
 
 

@@ -532,6 +532,14 @@ def check_model_generate():
     n = min(ids_new.shape[1], ids_ref.shape[1])
     out["greedy_len_new"], out["greedy_len_ref"] = float(ids_new.shape[1]), float(ids_ref.shape[1])
     out["greedy_token_agree"] = float((ids_new[:, :n] == ids_ref[:, :n]).mean())
+    # the CUDA-graph loop and the host-driven loop run the same kernels: identical greedy ids
+    os.environ["B200_GENERATE"] = "eager"
+    ids_eager = model.generate(prompt=prompt, batch_size=2, max_len=14, top_k=1, generator=torch.Generator(DEV).manual_seed(0))
+    os.environ["B200_GENERATE"] = "nograph"
+    ids_ng = model.generate(prompt=prompt, batch_size=2, max_len=14, top_k=1, generator=torch.Generator(DEV).manual_seed(0))
+    os.environ["B200_GENERATE"] = "graph"
+    out["greedy_graph_vs_eager_mismatch"] = float((ids_new != ids_eager).sum()) if ids_new.shape == ids_eager.shape else 1e9
+    out["greedy_nograph_vs_eager_mismatch"] = float((ids_ng != ids_eager).sum()) if ids_ng.shape == ids_eager.shape else 1e9
     # grammar validity of sampled generation
     ids_s = model.generate(prompt=None, batch_size=4, max_len=24, generator=torch.Generator(DEV).manual_seed(1))
     bad = 0
@@ -544,13 +552,15 @@ def check_model_generate():
     return out
 
 
-def _song_batch(tok, B, n_events, seed):
+def _song_batch(tok, B, n_events, seed, fixed_step=3):
     """Deterministic grammar-valid 'songs' (SURVEY.md 8c peaked-checkpoint recipe): bos, one patch_change, then
     notes walking up a scale.  Learnable in a few hundred steps => large top-1 margins, no EOS."""
     rng = np.random.default_rng(seed)
     out = np.zeros((B, n_events, 8), dtype=np.int64)
     for b in range(B):
         ch, step, pitch = int(rng.integers(0, 4)), int(rng.integers(1, 6)), int(rng.integers(40, 80))
+        if fixed_step:
+            step = fixed_step      # continuation is then a deterministic function of the previous event
         rows = [[tok.bos_id] + [0] * 7, tok.event2tokens(["patch_change", 0, 0, 1, ch, int(rng.integers(0, 128))])]
         k = 0
         while len(rows) < n_events:
@@ -587,7 +597,25 @@ def check_model_peaked_greedy():
                          inv_freq_net=model.net.rotary_emb.inv_freq, inv_freq_tok=model.net_token.rotary_emb.inv_freq)
     out["peaked_len_new"], out["peaked_len_ref"] = float(ids_new.shape[1]), float(ids_ref.shape[1])
     n = min(ids_new.shape[1], ids_ref.shape[1])
-    out["peaked_greedy_mismatch"] = float((ids_new[:, :n] != ids_ref[:, :n]).sum()) + abs(ids_new.shape[1] - ids_ref.shape[1])
+    neq = ids_new[:, :n] != ids_ref[:, :n]
+    out["peaked_greedy_mismatch"] = float(neq.sum()) + abs(ids_new.shape[1] - ids_ref.shape[1])
+    # tie / margin audit: if the runs diverge, the first differing token must be one where
+    # the fp32 oracle's margin between the two candidates is within the bf16 noise
+    sd32a = {k: v.float() for k, v in sd16.items()}
+    ref_t = torch.from_numpy(ids_ref).to(DEV)
+    with torch.no_grad():
+        h32a = O.forward(sd32a, ocfg, ref_t[:, :-1])
+        l32a = O.forward_token(sd32a, ocfg, h32a.reshape(-1, 1024), ref_t[:, 1:].reshape(-1, 8)[:, :-1]).view(4, n - 1, 8, -1)
+    if neq.any():
+        first_e = int(np.argwhere(neq.any(-1).any(0))[0][0])
+        bs, ts = np.nonzero(neq[:, first_e])
+        b0, t0 = int(bs[0]), int(ts[0])
+        row = l32a[b0, first_e - 1, t0]
+        out["peaked_first_divergence_event"] = float(first_e)
+        out["peaked_first_divergence_margin"] = float((row[ids_ref[b0, first_e, t0]] - row[ids_new[b0, first_e, t0]]).abs())
+        print("first divergence at event", first_e, "row", b0, "token", t0, "ref", ids_ref[b0, first_e], "new", ids_new[b0, first_e])
+    top2 = l32a[:, 8:].topk(2, -1).values
+    out["peaked_min_top1_margin_fp32"] = float((top2[..., 0] - top2[..., 1])[ref_t[:, 9:] != 0].min())
     # the generated continuation is itself grammar-valid
     bad = sum(1 for row in ids_new[:, 1:].reshape(-1, 8) if row[0] not in (tok.eos_id, tok.pad_id) and tok.tokens2event(row.tolist()) == [])
     out["peaked_invalid_events"] = float(bad)
@@ -634,7 +662,7 @@ THRESH = [
     ("cached_vs_full_hidden", 3e-2), ("inner_cached_vs_full_logits", 3e-2), ("min:greedy_token_agree", 0.6),
     ("peaked_greedy_mismatch", 0.0), ("peaked_invalid_events", 0.0), ("peaked_loss_last", 1.5),
     ("peaked_argmax_mismatch_vs_fp32", 0.0), ("peaked_logits_vs_fp32", 3e-2),
-    ("sampled_invalid_events", 0.0),
+    ("sampled_invalid_events", 0.0), ("greedy_graph_vs_eager_mismatch", 0.0), ("greedy_nograph_vs_eager_mismatch", 0.0),
 ]
 
 
