@@ -105,7 +105,9 @@ def cpu_train_step_tokens_per_s(steps: int, warmup: int, batch: int = 1, n_event
     import midi_model as mm
     from midi_b200.synth import synth_batch
     from oracle import midi_oracle as O
-    cores = os.cpu_count() or 1
+    # eager PyTorch at B=1 does not scale past a few dozen threads (128 threads on the GPU box were 7x SLOWER than
+    # 16 in round-1 measurements): use up to 16 and report that count
+    cores = min(os.cpu_count() or 1, 16)
     torch.set_num_threads(cores)
     torch.manual_seed(0)
     cfg = mm.MIDIModelConfig.from_name(MODEL)

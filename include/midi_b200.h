@@ -53,6 +53,9 @@ int b200_embed_bwd(const long long* ids, int n_ids, const void* dout, void* dtab
 /* ---- RMSNorm (hf modeling_llama.py:62-67) --------------------------------------------------- */
 int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd /*may be NULL*/, int M, int H, float eps,
                      cudaStream_t s);
+/* fused residual add + norm: h_out = bf16(x + res) (hf :325 / :331), y = RMSNorm(h_out) * w */
+int b200_add_rmsnorm_fwd(const void* x, const void* res, const void* w, void* h_out, void* y, float* rstd /*may be NULL*/,
+                         int M, int H, float eps, cudaStream_t s);
 int b200_rmsnorm_bwd_parts(void);
 /* dx = dres + d(norm)/dx ; dw (+)= column sums.  workspace: float[b200_rmsnorm_bwd_parts() * H] */
 int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres /*may be NULL*/,
@@ -83,6 +86,11 @@ int b200_gemm_bf16(const void* A, const void* B, void* C, const void* R, int M, 
                    int ldr, int a_mn_major, int b_mn_major, int accumulate, int block_n, int splits, void* workspace,
                    size_t workspace_bytes, cudaStream_t s);
 
+/*      QKV projection with RoPE fused into the epilogue (hf modeling_llama.py:262-268): rows sit at positions
+ *      r % S, columns [0, rope_cols) are rotated per head of width head_dim, the rest (v) is stored unrotated. */
+int b200_gemm_bf16_rope(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                        const void* rope_cos, const void* rope_sin, int S, int head_dim, int rope_cols, cudaStream_t s);
+
 /* ---- attention (hf integrations/sdpa_attention.py:41-104 via modeling_llama.py:251-289) ----------
  *      outer stack: causal flash attention, head_dim 64; strides are element strides {batch,row,head}. */
 int b200_attn_causal_fwd(const void* q, const void* k, const void* v, void* o, float* lse /*may be NULL*/,
@@ -91,12 +99,14 @@ int b200_attn_causal_fwd(const void* q, const void* k, const void* v, void* o, f
 int b200_attn_causal_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                          float* delta /*float[batch*n_heads*Sq]*/, void* dq, void* dk, void* dv,
                          const long long* strides /*8x3: q,k,v,o,do,dq,dk,dv*/, int batch, int n_heads, int Sq, int Sk,
-                         int head_dim, float scale, cudaStream_t s);
+                         int head_dim, float scale, const void* rope_cos /*may be NULL: fuse RoPE backward into dq, dk*/,
+                         const void* rope_sin, cudaStream_t s);
 /*      inner stack: L <= 8 positions per event, head_dim 256, packed qkv rows [n_events*L, ld_qkv]. */
 int b200_attn_tiny_fwd(const void* qkv, void* out, int n_events, int L, int n_heads, int head_dim, int ld_qkv, int ld_out,
                        float scale, cudaStream_t s);
 int b200_attn_tiny_bwd(const void* qkv, const void* d_out, void* dqkv, int n_events, int L, int n_heads, int head_dim,
-                       int ld_qkv, int ld_out, float scale, cudaStream_t s);
+                       int ld_qkv, int ld_out, float scale, const void* rope_cos /*may be NULL*/, const void* rope_sin,
+                       cudaStream_t s);
 
 /* ---- loss (train.py:180-185: mean CE, ignore_index = pad) ----------------------------------------- */
 int b200_ce_fwd(const void* logits, const long long* targets, float* lse, float* row_loss,

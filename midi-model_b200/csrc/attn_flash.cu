@@ -261,6 +261,23 @@ flash_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const b
 // ============================================================================================
 // backward
 // ============================================================================================
+// Optional fused RoPE backward: the gradient w.r.t. the *pre-rotation* q / k is R^T applied to the accumulators
+// (dx1 = d1*c + d2*s, dx2 = d2*c - d1*s on the (d, d+32) pairs = accumulator blocks (nb, nb+4) of the same thread).
+__device__ __forceinline__ void rope_bwd_acc(float acc[8][4], int r, const bf16* __restrict__ cos_t,
+                                             const bf16* __restrict__ sin_t, int pos, int t) {
+#pragma unroll
+    for (int nb = 0; nb < 4; nb++) {
+        const float2 c = __bfloat1622float2(*reinterpret_cast<const bf162*>(cos_t + (size_t)pos * 32 + nb * 8 + 2 * t));
+        const float2 sn = __bfloat1622float2(*reinterpret_cast<const bf162*>(sin_t + (size_t)pos * 32 + nb * 8 + 2 * t));
+        const float a0 = acc[nb][2 * r], a1 = acc[nb][2 * r + 1];
+        const float b0 = acc[nb + 4][2 * r], b1 = acc[nb + 4][2 * r + 1];
+        acc[nb][2 * r] = a0 * c.x + b0 * sn.x;
+        acc[nb][2 * r + 1] = a1 * c.y + b1 * sn.y;
+        acc[nb + 4][2 * r] = b0 * c.x - a0 * sn.x;
+        acc[nb + 4][2 * r + 1] = b1 * c.y - a1 * sn.y;
+    }
+}
+
 // delta[b,h,q] = sum_d dO[q,d] * O[q,d]; one 128-thread CTA per (b, q) row of n_heads*64 columns
 __global__ void flash_bwd_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, float* __restrict__ delta,
                                        Strides so, Strides sdo, int n_heads, int Sq) {
@@ -281,11 +298,12 @@ __global__ void flash_bwd_delta_kernel(const bf16* __restrict__ o, const bf16* _
 }
 
 // dK, dV for one tile of 64 keys: S^T = K Q^T (rows = keys), loops over query tiles
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 3)
 flash_bwd_dkv_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
                      const bf16* __restrict__ d_o, const float* __restrict__ lse, const float* __restrict__ delta,
                      bf16* __restrict__ dk, bf16* __restrict__ dv, Strides sq, Strides sk, Strides sv, Strides sdo,
-                     Strides sdk, Strides sdv, int n_heads, int Sq, int Sk, float scale) {
+                     Strides sdk, Strides sdv, int n_heads, int Sq, int Sk, float scale, const bf16* __restrict__ rope_cos,
+                     const bf16* __restrict__ rope_sin) {
     extern __shared__ __align__(128) uint8_t smem[];    // K | V | Q0 | dO0 | Q1 | dO1 | lse[2][64] | delta[2][64]
     float (*s_lse)[BM] = reinterpret_cast<float (*)[BM]>(smem + 8192 * 6);
     float (*s_delta)[BM] = reinterpret_cast<float (*)[BM]>(smem + 8192 * 6 + 2 * BM * 4);
@@ -397,6 +415,7 @@ flash_bwd_dkv_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, con
     for (int r = 0; r < 2; r++) {
         const int key = k0 + warp * 16 + g + r * 8;
         if (key < Sk) {
+            if (rope_cos) rope_bwd_acc(dkacc, r, rope_cos, rope_sin, key, t);   // linear: commutes with the scale below
 #pragma unroll
             for (int nb = 0; nb < 8; nb++) {
                 *reinterpret_cast<uint32_t*>(dkg + (long long)key * sdk.r + nb * 8 + 2 * t) =
@@ -409,11 +428,11 @@ flash_bwd_dkv_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, con
 }
 
 // dQ for one tile of 64 query rows, loops over key tiles
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 3)
 flash_bwd_dq_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v,
                     const bf16* __restrict__ d_o, const float* __restrict__ lse, const float* __restrict__ delta,
                     bf16* __restrict__ dq, Strides sq, Strides sk, Strides sv, Strides sdo, Strides sdq, int n_heads,
-                    int Sq, int Sk, float scale) {
+                    int Sq, int Sk, float scale, const bf16* __restrict__ rope_cos, const bf16* __restrict__ rope_sin) {
     extern __shared__ __align__(128) uint8_t smem[];    // Q | dO | K0 | V0 | K1 | V1
     const int qt = gridDim.x - 1 - blockIdx.x;
     const int bh = blockIdx.y;
@@ -509,6 +528,7 @@ flash_bwd_dq_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, cons
     for (int r = 0; r < 2; r++) {
         const int row = q0 + warp * 16 + g + r * 8;
         if (row < Sq) {
+            if (rope_cos) rope_bwd_acc(dqacc, r, rope_cos, rope_sin, row + off, t);
 #pragma unroll
             for (int nb = 0; nb < 8; nb++)
                 *reinterpret_cast<uint32_t*>(dqg + (long long)row * sdq.r + nb * 8 + 2 * t) =
@@ -530,6 +550,12 @@ extern "C" int b200_attn_causal_fwd(const void* q, const void* k, const void* v,
     if (batch == 0 || Sq == 0) return B200_OK;
     Strides s[4];
     for (int i = 0; i < 4; i++) { s[i].b = strides[3 * i]; s[i].r = strides[3 * i + 1]; s[i].h = strides[3 * i + 2]; }
+    static bool configured = false;
+    if (!configured) {   // let 4+ CTAs (40 KB static smem each) share an SM
+        B200_CUDA(cudaFuncSetAttribute(flash_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared), "attn carveout");
+        configured = true;
+    }
     dim3 grid((Sq + BM - 1) / BM, batch * n_heads);
     flash_fwd_kernel<<<grid, NT, 0, stream>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)o, lse, s[0], s[1],
                                              s[2], s[3], n_heads, Sq, Sk, scale);
@@ -541,7 +567,8 @@ extern "C" int b200_attn_causal_fwd(const void* q, const void* k, const void* v,
 extern "C" int b200_attn_causal_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
                                     const float* lse, float* delta, void* dq, void* dk, void* dv,
                                     const long long* strides /* 8 x {b,r,h}: q,k,v,o,do,dq,dk,dv */, int batch,
-                                    int n_heads, int Sq, int Sk, int head_dim, float scale, cudaStream_t stream) {
+                                    int n_heads, int Sq, int Sk, int head_dim, float scale, const void* rope_cos,
+                                    const void* rope_sin, cudaStream_t stream) {
     B200_CHECK_ARG(head_dim == D, "attn_causal_bwd: head_dim %d unsupported (64 only)", head_dim);
     B200_CHECK_ARG(Sk >= Sq, "attn_causal_bwd: Sk must be >= Sq");
     if (batch == 0 || Sq == 0) return B200_OK;
@@ -555,16 +582,21 @@ extern "C" int b200_attn_causal_bwd(const void* q, const void* k, const void* v,
     if (!configured) {
         B200_CUDA(cudaFuncSetAttribute(flash_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD), "attn smem");
         B200_CUDA(cudaFuncSetAttribute(flash_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD), "attn smem");
+        B200_CUDA(cudaFuncSetAttribute(flash_bwd_dkv_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared), "attn carveout");
+        B200_CUDA(cudaFuncSetAttribute(flash_bwd_dq_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared), "attn carveout");
         configured = true;
     }
     dim3 gkv((Sk + BN - 1) / BN, batch * n_heads);
     flash_bwd_dkv_kernel<<<gkv, NT, SMEM_BWD, stream>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (const bf16*)d_o, lse, delta,
                                                  (bf16*)dk, (bf16*)dv, s[0], s[1], s[2], s[4], s[6], s[7], n_heads, Sq, Sk,
-                                                 scale);
+                                                 scale, (const bf16*)rope_cos, (const bf16*)rope_sin);
     B200_CHECK_LAUNCH("attn_causal_bwd_dkv");
     dim3 gq((Sq + BM - 1) / BM, batch * n_heads);
     flash_bwd_dq_kernel<<<gq, NT, SMEM_BWD, stream>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (const bf16*)d_o, lse, delta,
-                                               (bf16*)dq, s[0], s[1], s[2], s[4], s[5], n_heads, Sq, Sk, scale);
+                                               (bf16*)dq, s[0], s[1], s[2], s[4], s[5], n_heads, Sq, Sk, scale,
+                                               (const bf16*)rope_cos, (const bf16*)rope_sin);
     B200_CHECK_LAUNCH("attn_causal_bwd_dq");
     return B200_OK;
 }

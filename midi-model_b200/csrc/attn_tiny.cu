@@ -33,6 +33,21 @@ __device__ __forceinline__ void axpy8(float* acc, float a, const uint4& x) {
     }
 }
 
+// Fused RoPE backward (d = 256): lane l holds d = 8l..8l+7; the rotation pairs (d, d+128) live in lanes l and l^16.
+// dx1 = d1*c + d2*s (first half), dx2 = d2*c - d1*s (second half); tables are [pos][128].
+__device__ __forceinline__ void rope_bwd_lane(float* acc, const bf16* __restrict__ cos_t, const bf16* __restrict__ sin_t,
+                                              int pos, int lane) {
+    float c[8], sn[8];
+    unpack8(*reinterpret_cast<const uint4*>(cos_t + (size_t)pos * (TD / 2) + (lane & 15) * 8), c);
+    unpack8(*reinterpret_cast<const uint4*>(sin_t + (size_t)pos * (TD / 2) + (lane & 15) * 8), sn);
+    const bool first = lane < 16;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const float other = __shfl_xor_sync(0xffffffffu, acc[j], 16);
+        acc[j] = first ? acc[j] * c[j] + other * sn[j] : acc[j] * c[j] - other * sn[j];
+    }
+}
+
 // causal softmax over s[i][0..i] (scaled scores); returns fp32 probabilities in place
 template <int L>
 __device__ __forceinline__ void softmax_rows(float s[L][L]) {
@@ -90,7 +105,8 @@ tiny_attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int n
 template <int L>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 tiny_attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_out, bf16* __restrict__ dqkv, int n_events,
-                     int n_heads, int ld_qkv, int ld_out, float scale) {
+                     int n_heads, int ld_qkv, int ld_out, float scale, const bf16* __restrict__ rope_cos,
+                     const bf16* __restrict__ rope_sin) {
     const int wid = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
     if (wid >= n_events * n_heads) return;
     const int lane = threadIdx.x & 31;
@@ -154,6 +170,7 @@ tiny_attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_ou
             float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
             for (int j = 0; j <= i; j++) axpy8(acc, ds[i][j], k[j]);
+            if (rope_cos) rope_bwd_lane(acc, rope_cos, rope_sin, i, lane);
             *reinterpret_cast<uint4*>(dbase + (size_t)i * ld_qkv) = pack8(acc);
         }
     }
@@ -166,6 +183,7 @@ tiny_attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_ou
             float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
             for (int i = j; i < L; i++) axpy8(acc, ds[i][j], q[i]);
+            if (rope_cos) rope_bwd_lane(acc, rope_cos, rope_sin, j, lane);
             *reinterpret_cast<uint4*>(dbase + (size_t)j * ld_qkv + H) = pack8(acc);
         }
     }
@@ -199,14 +217,15 @@ extern "C" int b200_attn_tiny_fwd(const void* qkv, void* out, int n_events, int 
 }
 
 extern "C" int b200_attn_tiny_bwd(const void* qkv, const void* d_out, void* dqkv, int n_events, int L, int n_heads,
-                                  int head_dim, int ld_qkv, int ld_out, float scale, cudaStream_t stream) {
+                                  int head_dim, int ld_qkv, int ld_out, float scale, const void* rope_cos,
+                                  const void* rope_sin, cudaStream_t stream) {
     B200_CHECK_ARG(head_dim == TD, "attn_tiny_bwd: head_dim %d unsupported (256 only)", head_dim);
     B200_CHECK_ARG(L >= 1 && L <= 8, "attn_tiny_bwd: L=%d outside 1..8", L);
     B200_CHECK_ARG(ld_qkv % 8 == 0 && ld_out % 8 == 0, "attn_tiny_bwd: leading dims must be multiples of 8");
     if (n_events == 0) return B200_OK;
     const int grid = (n_events * n_heads + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     B200_TINY_DISPATCH(tiny_attn_bwd_kernel, (const bf16*)qkv, (const bf16*)d_out, (bf16*)dqkv, n_events, n_heads, ld_qkv,
-                       ld_out, scale);
+                       ld_out, scale, (const bf16*)rope_cos, (const bf16*)rope_sin);
     B200_CHECK_LAUNCH("attn_tiny_bwd");
     return B200_OK;
 }

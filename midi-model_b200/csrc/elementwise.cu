@@ -258,8 +258,8 @@ constexpr int WRB_WARPS = 4;       // backward (155 regs/thread at hidden=1024 -
 
 template <int VPT>
 __global__ void __launch_bounds__(WR_WARPS * 32)
-rmsnorm_fwd_warp_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
-                        float* __restrict__ rstd_out, int M, float eps) {
+rmsnorm_fwd_warp_kernel(const bf16* __restrict__ x, const bf16* __restrict__ res, const bf16* __restrict__ w,
+                        bf16* __restrict__ h_out, bf16* __restrict__ y, float* __restrict__ rstd_out, int M, float eps) {
     constexpr int H = 256 * VPT;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -272,6 +272,13 @@ rmsnorm_fwd_warp_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, 
 #pragma unroll
         for (int k = 0; k < VPT; k++) {
             unpack8(ld_nc16(x + (size_t)m * H + (lane + k * 32) * 8), xv[k]);
+            if (res) {   // fused residual add: h = bf16(x + res) is the new residual stream (hf :325 / :331)
+                float rv[8];
+                unpack8(ld_nc16(res + (size_t)m * H + (lane + k * 32) * 8), rv);
+#pragma unroll
+                for (int j = 0; j < 8; j++) xv[k][j] = bf16_round(xv[k][j] + rv[j]);
+                *reinterpret_cast<uint4*>(h_out + (size_t)m * H + (lane + k * 32) * 8) = pack8(xv[k]);
+            }
 #pragma unroll
             for (int j = 0; j < 8; j++) ss = fmaf(xv[k][j], xv[k][j], ss);
         }
@@ -537,15 +544,31 @@ extern "C" int b200_embed_bwd(const long long* ids, int n_ids, const void* dout,
     return B200_OK;
 }
 
+static int rmsnorm_fwd_impl(const void* x, const void* res, const void* w, void* h_out, void* y, float* rstd, int M, int H,
+                            float eps, cudaStream_t stream);
+
 extern "C" int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd, int M, int H, float eps,
                                 cudaStream_t stream) {
+    return rmsnorm_fwd_impl(x, nullptr, w, nullptr, y, rstd, M, H, eps, stream);
+}
+
+// h = bf16(x + res) (the residual add of hf modeling_llama.py:325 / :331, written to h_out) ; y = RMSNorm(h) * w
+extern "C" int b200_add_rmsnorm_fwd(const void* x, const void* res, const void* w, void* h_out, void* y, float* rstd, int M,
+                                    int H, float eps, cudaStream_t stream) {
+    B200_CHECK_ARG(H == 256 || H == 512 || H == 1024 || H == 2048, "add_rmsnorm_fwd: hidden size %d unsupported", H);
+    B200_CHECK_ARG(res != nullptr && h_out != nullptr, "add_rmsnorm_fwd: res and h_out are required");
+    return rmsnorm_fwd_impl(x, res, w, h_out, y, rstd, M, H, eps, stream);
+}
+
+static int rmsnorm_fwd_impl(const void* x, const void* res, const void* w, void* h_out, void* y, float* rstd, int M, int H,
+                            float eps, cudaStream_t stream) {
     B200_CHECK_ARG(H % 8 == 0 && H <= ROW_THREADS * 8 * MAXV, "rmsnorm_fwd: unsupported hidden size %d", H);
     if (M == 0) return B200_OK;
     if (H == 256 || H == 512 || H == 1024 || H == 2048) {
         int g = (M + WR_WARPS - 1) / WR_WARPS;
         const int cap = b200_num_sms() * 8;
         if (g > cap) g = cap;
-#define B200_RMS_FWDW(V) rmsnorm_fwd_warp_kernel<V><<<g, WR_WARPS * 32, 0, stream>>>((const bf16*)x, (const bf16*)w, (bf16*)y, rstd, M, eps)
+#define B200_RMS_FWDW(V) rmsnorm_fwd_warp_kernel<V><<<g, WR_WARPS * 32, 0, stream>>>((const bf16*)x, (const bf16*)res, (const bf16*)w, (bf16*)h_out, (bf16*)y, rstd, M, eps)
         if (H == 256) B200_RMS_FWDW(1); else if (H == 512) B200_RMS_FWDW(2); else if (H == 1024) B200_RMS_FWDW(4); else B200_RMS_FWDW(8);
 #undef B200_RMS_FWDW
         B200_CHECK_LAUNCH("rmsnorm_fwd");

@@ -21,7 +21,7 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
 constexpr int EPI_WARP0 = 2;
 
-enum { EPI_STORE = 0, EPI_RESIDUAL = 1, EPI_PARTIAL_F32 = 2 };
+enum { EPI_STORE = 0, EPI_RESIDUAL = 1, EPI_PARTIAL_F32 = 2, EPI_ROPE = 3 };
 
 struct GemmParams {
     bf16* C;
@@ -33,6 +33,10 @@ struct GemmParams {
     int splits, kb_per_split, num_kb;
     int m_tiles, n_tiles;
     uint32_t mn_lbo, mn_sbo;   // MN-major descriptor byte offsets (overridable for bring-up)
+    // EPI_ROPE: rotary embedding applied to columns [0, rope_cols) (the q and k thirds of a packed QKV row)
+    const bf16* rope_cos;
+    const bf16* rope_sin;
+    int rope_S, rope_D, rope_cols;
 };
 
 // ---------------------------------------------------------------------------
@@ -270,6 +274,56 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int row = m_blk * BLOCK_M + quarter * 32 + lane;
             const bool row_ok = row < p.M;
             const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(quarter * 32) << 16);
+            if (p.epilogue == EPI_ROPE) {
+                // QKV projection with RoPE fused (hf modeling_llama.py:262-268): x = bf16(acc) (the Linear's rounding),
+                // then o1 = bf16(bf16(x1*c) + bf16(-x2*s)), o2 = bf16(bf16(x2*c) + bf16(x1*s)) on (d, d + D/2) pairs.
+                const int half = p.rope_D >> 1;
+                const int cph = half >> 5;                      // 32-column chunks per half head (1 for d=64, 4 for d=256)
+                const int pos = row_ok ? row % p.rope_S : 0;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BLOCK_N / 32; c0 += 2 * cph) {
+#pragma unroll 1
+                    for (int j = 0; j < cph; j++) {
+                        uint32_t r1[32], r2[32];
+                        tmem_ld32(taddr + (c0 + j) * 32, r1);
+                        tmem_ld32(taddr + (c0 + j + cph) * 32, r2);
+                        tmem_ld_wait();
+                        const int col1 = n_blk * BLOCK_N + (c0 + j) * 32;
+                        const int col2 = col1 + half;
+                        if (row_ok && col1 < p.N) {
+                            bf16* d1 = p.C + (size_t)row * p.ldc + col1;
+                            bf16* d2 = p.C + (size_t)row * p.ldc + col2;
+                            const bool rot = col1 < p.rope_cols;
+                            const bf16* cp = p.rope_cos + (size_t)pos * half + j * 32;
+                            const bf16* sp = p.rope_sin + (size_t)pos * half + j * 32;
+#pragma unroll
+                            for (int v = 0; v < 4; v++) {
+                                float x1[8], x2[8], o1[8], o2[8];
+#pragma unroll
+                                for (int q = 0; q < 8; q++) {
+                                    x1[q] = bf16_round(__uint_as_float(r1[8 * v + q]));
+                                    x2[q] = bf16_round(__uint_as_float(r2[8 * v + q]));
+                                }
+                                if (rot) {
+                                    float cc[8], ss[8];
+                                    unpack8(*reinterpret_cast<const uint4*>(cp + v * 8), cc);
+                                    unpack8(*reinterpret_cast<const uint4*>(sp + v * 8), ss);
+#pragma unroll
+                                    for (int q = 0; q < 8; q++) {
+                                        o1[q] = bf16_round(x1[q] * cc[q]) + bf16_round(-x2[q] * ss[q]);
+                                        o2[q] = bf16_round(x2[q] * cc[q]) + bf16_round(x1[q] * ss[q]);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int q = 0; q < 8; q++) { o1[q] = x1[q]; o2[q] = x2[q]; }
+                                }
+                                *reinterpret_cast<uint4*>(d1 + v * 8) = pack8(o1);
+                                if (col2 < p.N) *reinterpret_cast<uint4*>(d2 + v * 8) = pack8(o2);
+                            }
+                        }
+                    }
+                }
+            } else
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N / 32; c++) {
                 uint32_t r[32];
@@ -421,8 +475,10 @@ static double plan_cost(int M, int N, int K, int block_n, int s, int sms) {
     const int s_eff = (num_kb + kb_per - 1) / kb_per;
     const double items = tiles * s_eff;
     const double waves = ceil(items / sms);
-    // 4 UMMAs of 128 x block_n x 16 per k-block; 128-wide tiles pull 33% more operand bytes per FLOP (small penalty)
-    const double kb_clk = 2.0 * block_n * (block_n == 128 ? 1.08 : 1.0);
+    // 4 UMMAs of 128 x block_n x 16 per k-block.  Measured on B200 (profiles/r1_*): 128-wide tiles top out near
+    // 800 TFLOP/s (the 128x128x16 SS-mode UMMA re-reads 8 KB of smem operands per 64 clk = the 128 B/clk smem limit)
+    // while 256-wide tiles reach 1.3-1.48 PFLOP/s, hence the 1.7x cost factor.
+    const double kb_clk = 2.0 * block_n * (block_n == 128 ? 1.7 : 1.0);
     const double tile_ovh = 150.0 + (s_eff > 1 ? 1.0 : 0.5) * block_n * 6.0;   // accumulator hand-over + epilogue pressure
     double c = waves * (kb_per * kb_clk + tile_ovh) + 2500.0;   // + fill and exposed tail epilogue
     if (s_eff > 1) c += ((double)s_eff * M * N * 8.0 + (double)M * N * 2.0) / 5000.0 + 4000.0;   // bytes / (B/clk, mostly L2) + launch
@@ -461,9 +517,34 @@ extern "C" int b200_gemm_suggest_splits(int M, int N, int K, int block_n) {
     return bs;
 }
 
+static int gemm_impl(const void* A, const void* B, void* C, const void* R, int M, int N, int K, int lda, int ldb, int ldc,
+                     int ldr, int a_mn_major, int b_mn_major, int accumulate, int block_n, int splits, void* workspace,
+                     size_t workspace_bytes, const bf16* rope_cos, const bf16* rope_sin, int rope_S, int rope_D,
+                     int rope_cols, cudaStream_t stream);
+
 extern "C" int b200_gemm_bf16(const void* A, const void* B, void* C, const void* R, int M, int N, int K, int lda, int ldb,
                               int ldc, int ldr, int a_mn_major, int b_mn_major, int accumulate, int block_n, int splits,
                               void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    return gemm_impl(A, B, C, R, M, N, K, lda, ldb, ldc, ldr, a_mn_major, b_mn_major, accumulate, block_n, splits, workspace,
+                     workspace_bytes, nullptr, nullptr, 0, 0, 0, stream);
+}
+
+// Fused QKV projection + RoPE: C[M,N] = rope(A . B^T) with both operands K-major; rows are positions r % S of their
+// sequence, columns [0, rope_cols) are heads of width head_dim that get rotated, the rest (v) is stored as is.
+extern "C" int b200_gemm_bf16_rope(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                                   const void* rope_cos, const void* rope_sin, int S, int head_dim, int rope_cols,
+                                   cudaStream_t stream) {
+    B200_CHECK_ARG(head_dim == 64 || head_dim == 128 || head_dim == 256, "gemm_rope: head_dim %d unsupported", head_dim);
+    B200_CHECK_ARG(N % 256 == 0 && rope_cols % 256 == 0, "gemm_rope: N and rope_cols must be multiples of 256");
+    B200_CHECK_ARG(S > 0 && rope_cos && rope_sin, "gemm_rope: missing tables");
+    return gemm_impl(A, B, C, nullptr, M, N, K, lda, ldb, ldc, 0, 0, 0, 0, 256, 1, nullptr, 0, (const bf16*)rope_cos,
+                     (const bf16*)rope_sin, S, head_dim, rope_cols, stream);
+}
+
+static int gemm_impl(const void* A, const void* B, void* C, const void* R, int M, int N, int K, int lda, int ldb, int ldc,
+                     int ldr, int a_mn_major, int b_mn_major, int accumulate, int block_n, int splits, void* workspace,
+                     size_t workspace_bytes, const bf16* rope_cos, const bf16* rope_sin, int rope_S, int rope_D,
+                     int rope_cols, cudaStream_t stream) {
     B200_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
     // N need not be a multiple of 8: B rows >= N are out of bounds for the tensor map (zero-filled), so the
     // epilogue may store whole 16-byte vectors up to roundup8(N) (zeros) as long as the row pitch covers them.
@@ -504,6 +585,8 @@ extern "C" int b200_gemm_bf16(const void* A, const void* B, void* C, const void*
     } else {
         p.epilogue = R ? EPI_RESIDUAL : EPI_STORE;
     }
+    p.rope_cos = rope_cos; p.rope_sin = rope_sin; p.rope_S = rope_S; p.rope_D = rope_D; p.rope_cols = rope_cols;
+    if (rope_cos) p.epilogue = EPI_ROPE;
 
     CUtensorMap tmA, tmB;
     int rc;

@@ -19,7 +19,12 @@ import torch
 
 from . import lib, ops
 
+import os
+
 BF16 = torch.bfloat16
+# RoPE fused into the QKV GEMM epilogue (forward) and into the attention backward kernels (B200_FUSE_ROPE=0 uses
+# the stand-alone kernels; both paths have the same rounding points in the forward pass)
+FUSE_ROPE = os.environ.get("B200_FUSE_ROPE", "1") != "0"
 ALIGN = 256   # elements; AdamW's no-decay flags are per 256-element block
 
 
@@ -205,23 +210,33 @@ class StackEngine:
         H, D, nh = c.hidden, c.head_dim, c.n_head
         cos, sin = ops.rope_table(inv_freq, S)
         saved = [] if save else None
+        # Residual adds are fused into the norm that follows them (x + y is formed, rounded to bf16 and written by
+        # the norm kernel), so every GEMM keeps the plain store epilogue.
+        pending = None                                   # output of the previous layer's down_proj, not yet added
         for w in self.layers:
-            n1, rstd1 = ops.rmsnorm(x, w.ln1, c.eps, want_rstd=True)
-            qkv = ops.linear(n1, w.qkv)
-            ops.rope_qk_(qkv, cos, sin, S, H, D)
+            if pending is None:
+                n1, rstd1 = ops.rmsnorm(x, w.ln1, c.eps, want_rstd=True)
+            else:
+                x, n1, rstd1 = ops.add_rmsnorm(x, pending, w.ln1, c.eps)
+            if FUSE_ROPE:
+                qkv = ops.linear_rope(n1, w.qkv, cos, sin, S, D)      # QKV GEMM with RoPE in the epilogue
+            else:
+                qkv = ops.linear(n1, w.qkv)
+                ops.rope_qk_(qkv, cos, sin, S, H, D)
             if self.tiny:
                 attn, lse = ops.attn_tiny_fwd(qkv, n_seq, S, nh, D), None
             else:
                 attn, lse = ops.attn_causal_fwd(qkv, n_seq, S, nh, D, want_lse=save)
-            h = ops.linear(attn, w.o, residual=x)
-            n2, rstd2 = ops.rmsnorm(h, w.ln2, c.eps, want_rstd=True)
+            y1 = ops.linear(attn, w.o)
+            h, n2, rstd2 = ops.add_rmsnorm(x, y1, w.ln2, c.eps)
+            del y1
             gu = ops.linear(n2, w.gu)
             act = ops.swiglu(gu)
-            x_next = ops.linear(act, w.down, residual=h)
+            pending = ops.linear(act, w.down)
             if save:
                 saved.append((x, n1, rstd1, qkv, attn, lse, h, n2, rstd2, gu, act))
-            x = x_next
-        y, rstd_f = ops.rmsnorm(x, self.norm, c.eps, want_rstd=True)
+            x = h
+        x, y, rstd_f = ops.add_rmsnorm(x, pending, self.norm, c.eps)
         sv = dict(layers=saved, x_last=x, rstd_f=rstd_f, n_seq=n_seq, S=S, cos=cos, sin=sin) if save else None
         return y, sv
 
@@ -254,12 +269,14 @@ class StackEngine:
             # ---- attention block: h = x + o(attn)
             dattn = ops.linear_dgrad(dh, w.o)
             ops.linear_wgrad(dh, attn, g.o, accumulate)
+            rope = (cos, sin) if FUSE_ROPE else None
             if self.tiny:
-                dqkv = ops.attn_tiny_bwd(qkv, dattn, n_seq, S, nh, D)
+                dqkv = ops.attn_tiny_bwd(qkv, dattn, n_seq, S, nh, D, rope=rope)
             else:
-                dqkv = ops.attn_causal_bwd(qkv, attn, dattn, lse, n_seq, S, nh, D)
+                dqkv = ops.attn_causal_bwd(qkv, attn, dattn, lse, n_seq, S, nh, D, rope=rope)
             del dattn, attn, qkv
-            ops.rope_qk_(dqkv, cos, sin, S, H, D, backward=True)
+            if not FUSE_ROPE:
+                ops.rope_qk_(dqkv, cos, sin, S, H, D, backward=True)
             dn1 = ops.linear_dgrad(dqkv, w.qkv)
             ops.linear_wgrad(dqkv, n1, g.qkv, accumulate)
             del dqkv, n1

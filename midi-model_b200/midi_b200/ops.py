@@ -72,6 +72,17 @@ def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float, want_rstd: bool = Fals
     return (y, rstd) if want_rstd else y
 
 
+def add_rmsnorm(x: torch.Tensor, res: torch.Tensor, w: torch.Tensor, eps: float):
+    """h = x + res (residual add, bf16-rounded), y = rmsnorm(h) * w  ->  (h, y, rstd) in one pass over the rows."""
+    M, H = x.shape
+    h = torch.empty_like(x)
+    y = torch.empty_like(x)
+    rstd = torch.empty((M,), dtype=torch.float32, device=x.device)
+    lib.call("b200_add_rmsnorm_fwd", x.data_ptr(), res.data_ptr(), w.data_ptr(), h.data_ptr(), y.data_ptr(), rstd.data_ptr(),
+             M, H, eps, lib.stream())
+    return h, y, rstd
+
+
 def rmsnorm_bwd(dy, x, w, rstd, dres, dw, accumulate_dw: bool) -> torch.Tensor:
     M, H = x.shape
     dx = torch.empty_like(x)
@@ -208,7 +219,8 @@ def attn_causal_fwd(qkv: torch.Tensor, B: int, S: int, n_heads: int, D: int, wan
 
 
 def attn_causal_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, lse: torch.Tensor, B: int, S: int,
-                    n_heads: int, D: int) -> torch.Tensor:
+                    n_heads: int, D: int, rope=None) -> torch.Tensor:
+    """`rope=(cos, sin)`: also apply the RoPE backward to dq, dk (gradient w.r.t. the pre-rotation projections)."""
     H = n_heads * D
     ld = qkv.stride(0)
     dqkv = torch.empty_like(qkv)
@@ -218,7 +230,8 @@ def attn_causal_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, ls
     st = torch.tensor(pk * 3 + po + po + pk * 3, dtype=torch.int64)
     b, d = qkv.data_ptr(), dqkv.data_ptr()
     lib.call("b200_attn_causal_bwd", b, b + 2 * H, b + 4 * H, out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
-             delta.data_ptr(), d, d + 2 * H, d + 4 * H, st.data_ptr(), B, n_heads, S, S, D, 1.0 / math.sqrt(D), lib.stream())
+             delta.data_ptr(), d, d + 2 * H, d + 4 * H, st.data_ptr(), B, n_heads, S, S, D, 1.0 / math.sqrt(D),
+             rope[0].data_ptr() if rope else None, rope[1].data_ptr() if rope else None, lib.stream())
     return dqkv
 
 
@@ -230,11 +243,29 @@ def attn_tiny_fwd(qkv: torch.Tensor, n_events: int, L: int, n_heads: int, D: int
     return out
 
 
-def attn_tiny_bwd(qkv: torch.Tensor, dout: torch.Tensor, n_events: int, L: int, n_heads: int, D: int) -> torch.Tensor:
+def attn_tiny_bwd(qkv: torch.Tensor, dout: torch.Tensor, n_events: int, L: int, n_heads: int, D: int, rope=None) -> torch.Tensor:
     dqkv = torch.empty_like(qkv)
     lib.call("b200_attn_tiny_bwd", qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), n_events, L, n_heads, D, qkv.stride(0),
-             dout.stride(0), 1.0 / math.sqrt(D), lib.stream())
+             dout.stride(0), 1.0 / math.sqrt(D), rope[0].data_ptr() if rope else None, rope[1].data_ptr() if rope else None,
+             lib.stream())
     return dqkv
+
+
+def linear_rope(x: torch.Tensor, w_qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, S: int, D: int) -> torch.Tensor:
+    """Packed QKV projection with RoPE applied to the q and k thirds inside the GEMM epilogue."""
+    M, K = x.shape
+    N = w_qkv.shape[0]
+    out = torch.empty((M, N), dtype=BF16, device=x.device)
+    prof = GEMM_PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    lib.call("b200_gemm_bf16_rope", x.data_ptr(), w_qkv.data_ptr(), out.data_ptr(), M, N, K, x.stride(0), w_qkv.stride(0), N,
+             cos.data_ptr(), sin.data_ptr(), S, D, 2 * N // 3, lib.stream())
+    if prof is not None:
+        e1.record()
+        prof.append((e0, e1, 2.0 * M * N * K, (M, N, K, 0, 0, 256, 1)))
+    return out
 
 
 # ------------------------------------------------------------------ loss
