@@ -96,11 +96,22 @@ int b200_gemm_bf16_rope(const void* A, const void* B, void* C, int M, int N, int
 int b200_attn_causal_fwd(const void* q, const void* k, const void* v, void* o, float* lse /*may be NULL*/,
                          const long long* strides /*4x3: q,k,v,o*/, int batch, int n_heads, int Sq, int Sk, int head_dim,
                          float scale, cudaStream_t s);
+/*      same contract on the tcgen05 tensor cores (TMA-staged 128-key K/V tiles, S and P.V accumulators in TMEM);
+ *      heads must be contiguous blocks of 64 columns (strides[.h] == 64) */
+int b200_attn_causal_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse /*may be NULL*/,
+                            const long long* strides /*4x3: q,k,v,o*/, int batch, int n_heads, int Sq, int Sk, int head_dim,
+                            float scale, cudaStream_t s);
 int b200_attn_causal_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                          float* delta /*float[batch*n_heads*Sq]*/, void* dq, void* dk, void* dv,
                          const long long* strides /*8x3: q,k,v,o,do,dq,dk,dv*/, int batch, int n_heads, int Sq, int Sk,
                          int head_dim, float scale, const void* rope_cos /*may be NULL: fuse RoPE backward into dq, dk*/,
                          const void* rope_sin, cudaStream_t s);
+/*      backward on tcgen05 (5 UMMA groups per tile pair, dQ accumulated in fp32 with red.global); training shapes only */
+size_t b200_attn_causal_bwd_tc_workspace_bytes(int batch, int n_heads, int Sq);
+int b200_attn_causal_bwd_tc(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                            void* dq, void* dk, void* dv, const long long* strides /*8x3: q,k,v,o,do,dq,dk,dv*/, int batch,
+                            int n_heads, int Sq, int Sk, int head_dim, float scale, const void* rope_cos /*may be NULL*/,
+                            const void* rope_sin, void* workspace, size_t workspace_bytes, cudaStream_t s);
 /*      inner stack: L <= 8 positions per event, head_dim 256, packed qkv rows [n_events*L, ld_qkv]. */
 int b200_attn_tiny_fwd(const void* qkv, void* out, int n_events, int L, int n_heads, int head_dim, int ld_qkv, int ld_out,
                        float scale, cudaStream_t s);

@@ -563,6 +563,16 @@ extern "C" int b200_attn_causal_fwd(const void* q, const void* k, const void* v,
     return B200_OK;
 }
 
+// delta[b,h,q] = rowsum(dO * O): shared by the mma.sync and the tcgen05 backward paths
+int b200_attn_bwd_delta_launch(const void* o, const void* d_o, float* delta, const long long* so, const long long* sdo,
+                               int batch, int n_heads, int Sq, cudaStream_t stream) {
+    B200_CHECK_ARG(n_heads % 4 == 0, "attn bwd: n_heads must be a multiple of 4");
+    Strides a{so[0], so[1], so[2]}, b{sdo[0], sdo[1], sdo[2]};
+    flash_bwd_delta_kernel<<<batch * Sq, 128, 0, stream>>>((const bf16*)o, (const bf16*)d_o, delta, a, b, n_heads, Sq);
+    B200_CHECK_LAUNCH("attn_bwd_delta");
+    return B200_OK;
+}
+
 // delta: float[batch*n_heads*Sq] workspace
 extern "C" int b200_attn_causal_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
                                     const float* lse, float* delta, void* dq, void* dk, void* dv,

@@ -1,0 +1,662 @@
+// Causal attention forward for the event-level stack on the 5th-gen tensor cores (head_dim 64):
+// S = Q.K^T and O += P.V are tcgen05.mma with accumulators in TMEM, Q / K / V tiles are staged by TMA
+// (cp.async.bulk.tensor.3d, 128B swizzle, zero fill outside the sequence) straight from the packed
+// [rows, 3*hidden] QKV activation, softmax runs in fp32 with one thread per query row (no shuffles):
+//   warp 0     : TMA producer         warp 1 : TMEM allocator + MMA issuer
+//   warps 2..5 : softmax / correction / epilogue (thread <-> TMEM lane <-> query row)
+// One CTA owns 128 query rows of one (batch, head); K/V tiles of 128 keys are double-buffered.  Two CTAs share
+// an SM (113 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
+// Semantics = hf sdpa_attention.py:92-101 (causal, scale d^-1/2): online softmax in fp32, P rounded to bf16
+// before P.V, output rounded to bf16, LSE saved for the backward pass.
+#include "tc05.cuh"
+
+namespace {
+using namespace tc05;
+
+constexpr int D = 64;
+constexpr int BQ = 128;    // query rows per CTA
+constexpr int BK = 128;    // keys per tile
+constexpr int KV_STAGES = 2;
+constexpr int NTHREADS = 192;
+constexpr float LOG2E = 1.4426950408889634f;
+
+constexpr int SM_Q = 0;                                  // 16 KB
+constexpr int SM_KV = 16384;                             // KV_STAGES x (K 16 KB + V 16 KB)
+constexpr int SM_P = SM_KV + KV_STAGES * 32768;          // 32 KB: two 64-key atoms of [128 rows x 128 B]
+constexpr int SM_BAR = SM_P + 32768;
+constexpr int SMEM_BYTES = SM_BAR + 128;
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+struct FwdParams {
+    bf16* o;
+    float* lse;
+    long long o_b, o_r;          // element strides of the output: batch, row (heads are contiguous blocks of 64)
+    int n_heads, Sq, Sk, H;      // H = columns between the q, k and v thirds when packed (used for TMA column coords)
+    int q_col0, k_col0, v_col0;  // first column of head 0 in each tensor map
+    float scale;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 2)
+attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+    uint64_t* q_full = bars + 0;
+    uint64_t* kv_full = bars + 1;     // [2]
+    uint64_t* kv_empty = bars + 3;    // [2]
+    uint64_t* s_full = bars + 5;
+    uint64_t* s_empty = bars + 6;
+    uint64_t* p_full = bars + 7;
+    uint64_t* pv_full = bars + 8;
+    uint64_t* pv_empty = bars + 9;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = gridDim.x - 1 - blockIdx.x;     // long (late) tiles first
+    const int bh = blockIdx.y;
+    const int b = bh / p.n_heads, h = bh % p.n_heads;
+    const int q0 = qt * BQ;
+    const int off = p.Sk - p.Sq;
+    int n_kv = min((p.Sk + BK - 1) / BK, (q0 + BQ - 1 + off) / BK + 1);
+    if (n_kv < 1) n_kv = 1;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < KV_STAGES; s++) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        mbar_init(s_full, 1); mbar_init(s_empty, 4); mbar_init(p_full, 4); mbar_init(pv_full, 1); mbar_init(pv_empty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tS = tmem_base, tPV = tmem_base + 128;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(q_full, BQ * D * 2);
+            tma_load_3d(smem + SM_Q, &tmQ, q_full, p.q_col0 + h * D, q0, b);
+            int stage = 0; uint32_t phase = 0;
+            for (int j = 0; j < n_kv; j++) {
+                mbar_wait(&kv_empty[stage], phase ^ 1);
+                uint8_t* sK = smem + SM_KV + stage * 32768;
+                mbar_expect_tx(&kv_full[stage], 2 * BK * D * 2);
+                tma_load_3d(sK, &tmK, &kv_full[stage], p.k_col0 + h * D, j * BK, b);
+                tma_load_3d(sK + 16384, &tmV, &kv_full[stage], p.v_col0 + h * D, j * BK, b);
+                if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc(BQ, BK, false, false);    // S[128 x 128] = Q . K^T
+            constexpr uint32_t idesc_pv = make_idesc(BQ, D, false, true);     // PV[128 x 64] = P . V (V is [keys, d]: MN-major B)
+            const uint32_t sQ = smem_u32(smem + SM_Q), sP = smem_u32(smem + SM_P);
+            mbar_wait(q_full, 0);
+            int stage = 0; uint32_t kv_phase = 0, ph = 0;
+            auto issue_s = [&](int st) {
+                const uint32_t sK = smem_u32(smem + SM_KV + st * 32768);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < D / 16; k++)
+                    umma_f16(tS, make_smem_desc(sQ + k * 32, 16, 1024), make_smem_desc(sK + k * 32, 16, 1024), idesc_s, k > 0);
+                umma_commit(s_full);
+            };
+            mbar_wait(&kv_full[0], 0);
+            issue_s(0);
+            for (int j = 0; j < n_kv; j++) {
+                const uint32_t sV = smem_u32(smem + SM_KV + stage * 32768 + 16384);
+                mbar_wait(p_full, ph);            // softmax wrote P_j (and has finished reading S_j)
+                mbar_wait(pv_empty, ph ^ 1);      // previous PV tile drained from TMEM
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < BK / 16; kk++)
+                    umma_f16(tPV, make_smem_desc(sP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                             make_smem_desc(sV + kk * 2048, 16384, 1024), idesc_pv, kk > 0);
+                umma_commit(pv_full);
+                umma_commit(&kv_empty[stage]);
+                if (++stage == KV_STAGES) { stage = 0; kv_phase ^= 1; }
+                if (j + 1 < n_kv) {
+                    mbar_wait(&kv_full[stage], kv_phase);
+                    mbar_wait(s_empty, ph);       // softmax finished reading S_j
+                    issue_s(stage);
+                }
+                ph ^= 1;
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int row_t = quarter * 32 + lane;            // row inside the tile == TMEM lane
+        const int row = q0 + row_t;
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        const float sl2 = p.scale * LOG2E;
+        float m_i = -INFINITY, l_i = 0.f;
+        float o[D];
+#pragma unroll
+        for (int i = 0; i < D; i++) o[i] = 0.f;
+        uint8_t* sP = smem + SM_P;
+        uint32_t ph = 0;
+        for (int j = 0; j < n_kv; j++) {
+            const int k0 = j * BK;
+            const bool need_mask = (k0 + BK - 1 > q0 + off) || (k0 + BK > p.Sk);
+            mbar_wait(s_full, ph);
+            tc_fence_after();
+            // pass 1: row maximum
+            float mx = m_i;
+#pragma unroll 1
+            for (int c = 0; c < BK / 32; c++) {
+                uint32_t r[32];
+                tmem_ld32(tS + lane_addr + c * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    float s = __uint_as_float(r[i]);
+                    if (need_mask) {
+                        const int key = k0 + c * 32 + i;
+                        if (key > row + off || key >= p.Sk) s = -INFINITY;
+                    }
+                    mx = fmaxf(mx, s);
+                }
+            }
+            const float msc = (mx == -INFINITY) ? 0.f : mx * sl2;
+            const float alpha = (m_i == -INFINITY) ? 0.f : exp2f(m_i * sl2 - msc);
+            m_i = mx;
+            // pass 2: probabilities -> bf16 -> swizzled P tile in shared memory
+            float rs = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < BK / 32; c++) {
+                uint32_t r[32];
+                tmem_ld32(tS + lane_addr + c * 32, r);
+                tmem_ld_wait();
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float s0 = __uint_as_float(r[i]), s1 = __uint_as_float(r[i + 1]);
+                    if (need_mask) {
+                        const int key = k0 + c * 32 + i;
+                        if (key > row + off || key >= p.Sk) s0 = -INFINITY;
+                        if (key + 1 > row + off || key + 1 >= p.Sk) s1 = -INFINITY;
+                    }
+                    const float p0 = exp2f(s0 * sl2 - msc), p1 = exp2f(s1 * sl2 - msc);
+                    rs += p0 + p1;
+                    pk[i >> 1] = pack2(p0, p1);
+                }
+                // keys c*32 .. c*32+31 of this row: atom (c >> 1), 16-byte chunks (c & 1) * 4 .. + 3
+                uint8_t* rowp = sP + (c >> 1) * 16384 + row_t * 128;
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    const int chunk = (c & 1) * 4 + v;
+                    *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row_t & 7)) << 4)) =
+                        make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+                }
+            }
+            l_i = l_i * alpha + rs;
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(s_empty); mbar_arrive(p_full); }
+            // correction + accumulate this tile's P.V
+            mbar_wait(pv_full, ph);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < D / 32; c++) {
+                uint32_t r[32];
+                tmem_ld32(tPV + lane_addr + c * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; i++) o[c * 32 + i] = o[c * 32 + i] * alpha + __uint_as_float(r[i]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pv_empty);
+            ph ^= 1;
+        }
+        if (row < p.Sq) {
+            const float inv = l_i > 0.f ? 1.f / l_i : 0.f;
+            bf16* dst = p.o + b * p.o_b + (long long)row * p.o_r + h * D;
+#pragma unroll
+            for (int v = 0; v < D / 8; v++) {
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) f[i] = o[v * 8 + i] * inv;
+                *reinterpret_cast<uint4*>(dst + v * 8) = pack8(f);
+            }
+            if (p.lse) p.lse[((long long)b * p.n_heads + h) * p.Sq + row] = m_i * p.scale + logf(l_i);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+}   // namespace
+
+// 3-D bf16 tensor map {cols, rows per sequence, batch} with 128B swizzle: rows outside a sequence are zero-filled
+int tc05_make_tmap_3d(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t row_pitch,
+                      uint64_t batch_pitch, uint32_t box_cols, uint32_t box_rows);
+
+// q, k, v: [batch, S, heads*64] views (row pitch / batch pitch in elements) of e.g. the packed QKV activation
+extern "C" int b200_attn_causal_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse,
+                                       const long long* strides /* 4 x {b,r,h}: q,k,v,o */, int batch, int n_heads, int Sq,
+                                       int Sk, int head_dim, float scale, cudaStream_t stream) {
+    B200_CHECK_ARG(head_dim == D, "attn_causal_fwd_tc: head_dim %d unsupported (64 only)", head_dim);
+    B200_CHECK_ARG(Sk >= Sq, "attn_causal_fwd_tc: Sk must be >= Sq");
+    for (int i = 0; i < 4; i++)
+        B200_CHECK_ARG(strides[3 * i + 2] == D, "attn_causal_fwd_tc: heads must be contiguous blocks of 64 columns");
+    if (batch == 0 || Sq == 0) return B200_OK;
+    const long long W = (long long)n_heads * D;
+    CUtensorMap tmQ, tmK, tmV;
+    int rc;
+    if ((rc = tc05_make_tmap_3d(&tmQ, q, W, Sq, batch, strides[1], strides[0], D, BQ))) return rc;
+    if ((rc = tc05_make_tmap_3d(&tmK, k, W, Sk, batch, strides[4], strides[3], D, BK))) return rc;
+    if ((rc = tc05_make_tmap_3d(&tmV, v, W, Sk, batch, strides[7], strides[6], D, BK))) return rc;
+    FwdParams p;
+    p.o = (bf16*)o; p.lse = lse; p.o_b = strides[9]; p.o_r = strides[10];
+    p.n_heads = n_heads; p.Sq = Sq; p.Sk = Sk; p.H = (int)W;
+    p.q_col0 = p.k_col0 = p.v_col0 = 0;
+    p.scale = scale;
+    static bool configured = false;
+    if (!configured) {
+        B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES), "attn_tc smem");
+        B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc05_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared), "attn_tc carveout");
+        configured = true;
+    }
+    dim3 grid((Sq + BQ - 1) / BQ, batch * n_heads);
+    attn_fwd_tc05_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+    B200_CHECK_LAUNCH("attn_causal_fwd_tc");
+    return B200_OK;
+}
+
+// =============================================================================================
+// backward on tcgen05: one CTA = one tile of 128 keys of one (batch, head), looping over the query tiles at or
+// after the diagonal.  Five UMMA groups per iteration, all accumulators in TMEM (448 of 512 columns):
+//   S^T  = K . Q_i^T        dP^T = V . dO_i^T                      (128 x 128 each)
+//   dV  += P^T . dO_i       dK  += dS^T . Q_i                      (128 x 64, accumulated over the whole loop)
+//   dQ_i = dS . K           (128 x 64; added to an fp32 global accumulator with red.global, like FlashAttention-2)
+// P^T and dS^T are produced by 8 compute warps (thread = key row x half of the query columns), rounded to bf16 and
+// written to 128B-swizzled shared memory where the UMMAs read them: K-major for dV / dK, and the same dS^T tile
+// viewed MN-major as the A operand of dQ -- so no transposes and no recomputation (5 matmuls, not 7).
+// =============================================================================================
+namespace {
+
+constexpr int BWD_THREADS = 320;                 // warp 0 TMA, warp 1 MMA, warps 2..9 compute
+constexpr int SB_K = 0, SB_V = 16384;
+constexpr int SB_Q = 32768;                      // 2 stages x (Q 16 KB + dO 16 KB)
+constexpr int SB_P = SB_Q + 2 * 32768;           // P^T : two 64-query atoms of [128 keys x 128 B]
+constexpr int SB_DS = SB_P + 32768;              // dS^T: same layout
+constexpr int SB_LSE = SB_DS + 32768;            // float [2][2][128]: lse, delta per stage parity
+constexpr int SB_BAR = SB_LSE + 2048;
+constexpr int SMEM_BWD_BYTES = SB_BAR + 128;
+
+struct BwdParams {
+    const float* lse;
+    const float* delta;
+    float* dq_acc;               // fp32 [batch, Sq, n_heads*64] accumulator (pre-zeroed)
+    bf16* dk;
+    bf16* dv;
+    long long dk_b, dk_r, dv_b, dv_r;
+    long long dqa_b, dqa_r;
+    const bf16* rope_cos;        // optional fused RoPE backward on dK (dQ gets it in the finalize kernel)
+    const bf16* rope_sin;
+    int n_heads, Sq, Sk;
+    float scale;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const BwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SB_BAR);
+    uint64_t* kv_full = bars + 0;
+    uint64_t* q_full = bars + 1;      // [2]
+    uint64_t* q_empty = bars + 3;     // [2]
+    uint64_t* s_full = bars + 5;
+    uint64_t* pds_full = bars + 6;
+    uint64_t* dq_full = bars + 7;
+    uint64_t* dq_empty = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    float* lse_s = reinterpret_cast<float*>(smem + SB_LSE);          // [2][128]
+    float* delta_s = lse_s + 256;                                      // [2][128]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kt = blockIdx.x;
+    const int bh = blockIdx.y;
+    const int b = bh / p.n_heads, h = bh % p.n_heads;
+    const int k0 = kt * BK;
+    const int off = p.Sk - p.Sq;
+    const int n_q = (p.Sq + BQ - 1) / BQ;
+    int i0 = (k0 - off) / BQ;
+    if (k0 - off < 0) i0 = 0;
+    const int n_it = n_q - i0;                     // may be <= 0 when every query sits before this key tile
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmdO);
+        mbar_init(kv_full, 1);
+        for (int s = 0; s < 2; s++) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
+        mbar_init(s_full, 1); mbar_init(pds_full, 8); mbar_init(dq_full, 1); mbar_init(dq_empty, 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320, tdQ = tmem_base + 384;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(kv_full, 2 * BK * D * 2);
+            tma_load_3d(smem + SB_K, &tmK, kv_full, h * D, k0, b);
+            tma_load_3d(smem + SB_V, &tmV, kv_full, h * D, k0, b);
+            int stage = 0; uint32_t phase = 0;
+            for (int it = 0; it < n_it; it++) {
+                mbar_wait(&q_empty[stage], phase ^ 1);
+                uint8_t* sQ = smem + SB_Q + stage * 32768;
+                mbar_expect_tx(&q_full[stage], 2 * BQ * D * 2);
+                tma_load_3d(sQ, &tmQ, &q_full[stage], h * D, (i0 + it) * BQ, b);
+                tma_load_3d(sQ + 16384, &tmdO, &q_full[stage], h * D, (i0 + it) * BQ, b);
+                if (++stage == 2) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && n_it > 0) {
+            constexpr uint32_t id_s = make_idesc(128, 128, false, false);     // S^T, dP^T
+            constexpr uint32_t id_kv = make_idesc(128, 64, false, true);      // dV, dK : A K-major (smem P^T/dS^T), B MN-major
+            constexpr uint32_t id_dq = make_idesc(128, 64, true, true);       // dQ     : A = dS (MN-major view of dS^T), B = K MN-major
+            const uint32_t sK = smem_u32(smem + SB_K), sV = smem_u32(smem + SB_V);
+            const uint32_t sP = smem_u32(smem + SB_P), sDS = smem_u32(smem + SB_DS);
+            mbar_wait(kv_full, 0);
+            int stage = 0; uint32_t qphase = 0, ph = 0;
+            auto issue_s = [&](int st) {
+                const uint32_t sQ = smem_u32(smem + SB_Q + st * 32768), sdO = sQ + 16384;
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < D / 16; k++)
+                    umma_f16(tS, make_smem_desc(sK + k * 32, 16, 1024), make_smem_desc(sQ + k * 32, 16, 1024), id_s, k > 0);
+#pragma unroll
+                for (int k = 0; k < D / 16; k++)
+                    umma_f16(tdP, make_smem_desc(sV + k * 32, 16, 1024), make_smem_desc(sdO + k * 32, 16, 1024), id_s, k > 0);
+                umma_commit(s_full);
+            };
+            mbar_wait(&q_full[0], 0);
+            issue_s(0);
+            for (int it = 0; it < n_it; it++) {
+                const uint32_t sQ = smem_u32(smem + SB_Q + stage * 32768), sdO = sQ + 16384;
+                mbar_wait(pds_full, ph);          // P^T, dS^T of this iteration are in shared memory; S^T/dP^T TMEM is free
+                mbar_wait(dq_empty, ph ^ 1);      // previous dQ tile drained
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < BQ / 16; kk++) {
+                    const uint32_t a_off = (kk >> 2) * 16384 + (kk & 3) * 32;
+                    umma_f16(tdV, make_smem_desc(sP + a_off, 16, 1024), make_smem_desc(sdO + kk * 2048, 16384, 1024), id_kv,
+                             (it > 0 || kk > 0) ? 1u : 0u);
+                }
+#pragma unroll
+                for (int kk = 0; kk < BQ / 16; kk++) {
+                    const uint32_t a_off = (kk >> 2) * 16384 + (kk & 3) * 32;
+                    umma_f16(tdK, make_smem_desc(sDS + a_off, 16, 1024), make_smem_desc(sQ + kk * 2048, 16384, 1024), id_kv,
+                             (it > 0 || kk > 0) ? 1u : 0u);
+                }
+#pragma unroll
+                for (int kk = 0; kk < BK / 16; kk++)   // K dimension = keys: 16 key rows per step
+                    umma_f16(tdQ, make_smem_desc(sDS + kk * 2048, 16384, 1024), make_smem_desc(sK + kk * 2048, 16384, 1024),
+                             id_dq, kk > 0);
+                umma_commit(dq_full);
+                umma_commit(&q_empty[stage]);
+                if (++stage == 2) { stage = 0; qphase ^= 1; }
+                if (it + 1 < n_it) {
+                    mbar_wait(&q_full[stage], qphase);
+                    issue_s(stage);
+                }
+                ph ^= 1;
+            }
+        }
+    } else {
+        const int cw = warp - 2;                       // 0..7
+        const int quarter = warp & 3;
+        const int half = cw >> 2;                      // which 64 query columns of the tile this thread handles
+        const int key_t = quarter * 32 + lane;         // key row inside the tile == TMEM lane
+        const int key = k0 + key_t;
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        const float sl2 = p.scale * LOG2E;
+        const int ctid = threadIdx.x - 64;             // 0..255
+        const float* lse_g = p.lse + ((long long)b * p.n_heads + h) * p.Sq;
+        const float* delta_g = p.delta + ((long long)b * p.n_heads + h) * p.Sq;
+        uint8_t* sP = smem + SB_P + half * 16384 + key_t * 128;
+        uint8_t* sDS = smem + SB_DS + half * 16384 + key_t * 128;
+        uint32_t ph = 0;
+        for (int it = 0; it < n_it; it++) {
+            const int q0 = (i0 + it) * BQ;
+            {   // stage this tile's lse / delta rows in shared memory (one value per thread)
+                const int par = it & 1;
+                const int qi = q0 + (ctid & 127);
+                const float v = qi < p.Sq ? (ctid < 128 ? lse_g[qi] * LOG2E : delta_g[qi]) : 0.f;
+                (ctid < 128 ? lse_s : delta_s)[par * 128 + (ctid & 127)] = v;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            const float* lse_t = lse_s + (it & 1) * 128 + half * 64;
+            const float* delta_t = delta_s + (it & 1) * 128 + half * 64;
+            const bool need_mask = (k0 + BK - 1 > q0 + off) || (k0 + BK > p.Sk) || (q0 + BQ > p.Sq);
+            mbar_wait(s_full, ph);
+            tc_fence_after();
+            if (it > 0) {
+                // previous iteration's dQ tile: drain TMEM -> fp32 global accumulator (this thread: 32 of the 64 columns)
+                // (done here, after s_full, so the reds overlap this iteration's S^T / dP^T MMAs)
+            }
+#pragma unroll 1
+            for (int c = 0; c < 2; c++) {
+                uint32_t rs[32], rd[32];
+                tmem_ld32(tS + lane_addr + half * 64 + c * 32, rs);
+                tmem_ld32(tdP + lane_addr + half * 64 + c * 32, rd);
+                tmem_ld_wait();
+                uint32_t pk[16], dk_[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float pv[2], dsv[2];
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int qq = c * 32 + i + e;                 // column inside this thread's 64
+                        float pr = exp2f(__uint_as_float(rs[i + e]) * sl2 - lse_t[qq]);
+                        if (need_mask) {
+                            const int qrow = q0 + half * 64 + qq;
+                            if (key > qrow + off || key >= p.Sk || qrow >= p.Sq) pr = 0.f;
+                        }
+                        pv[e] = pr;
+                        dsv[e] = pr * (__uint_as_float(rd[i + e]) - delta_t[qq]);
+                    }
+                    pk[i >> 1] = pack2(pv[0], pv[1]);
+                    dk_[i >> 1] = pack2(dsv[0], dsv[1]);
+                }
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    const int chunk = c * 4 + v;
+                    const int sw = (chunk ^ (key_t & 7)) << 4;
+                    *reinterpret_cast<uint4*>(sP + sw) = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+                    *reinterpret_cast<uint4*>(sDS + sw) = make_uint4(dk_[4 * v], dk_[4 * v + 1], dk_[4 * v + 2], dk_[4 * v + 3]);
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pds_full);
+            // dQ_i tile: TMEM lane = query row, this thread owns columns half*32 .. +31
+            mbar_wait(dq_full, ph);
+            tc_fence_after();
+            {
+                uint32_t r[32];
+                tmem_ld32(tdQ + lane_addr + half * 32, r);
+                tmem_ld_wait();
+                const int qrow = q0 + key_t;                           // (lane index now means query row)
+                if (qrow < p.Sq) {
+                    float* dst = p.dq_acc + b * p.dqa_b + (long long)qrow * p.dqa_r + h * D + half * 32;
+#pragma unroll
+                    for (int v = 0; v < 8; v++)
+                        red_add_v4(dst + v * 4, __uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
+                                   __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dq_empty);
+            ph ^= 1;
+        }
+        // epilogue: dV, dK for this key tile (warps 2..5 hold one full row each)
+        if (cw < 4 && key < p.Sk) {
+            float dvv[D], dkv[D];
+            if (n_it > 0) {
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    uint32_t r[32];
+                    tmem_ld32(tdV + lane_addr + c * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; i++) dvv[c * 32 + i] = __uint_as_float(r[i]);
+                    tmem_ld32(tdK + lane_addr + c * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; i++) dkv[c * 32 + i] = __uint_as_float(r[i]) * p.scale;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < D; i++) { dvv[i] = 0.f; dkv[i] = 0.f; }
+            }
+            if (p.rope_cos) {
+                const bf16* cp = p.rope_cos + (size_t)key * 32;
+                const bf16* sp = p.rope_sin + (size_t)key * 32;
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    const float c = __bfloat162float(cp[i]), s = __bfloat162float(sp[i]);
+                    const float a = dkv[i], bb = dkv[i + 32];
+                    dkv[i] = a * c + bb * s;
+                    dkv[i + 32] = bb * c - a * s;
+                }
+            }
+            bf16* dkd = p.dk + b * p.dk_b + (long long)key * p.dk_r + h * D;
+            bf16* dvd = p.dv + b * p.dv_b + (long long)key * p.dv_r + h * D;
+#pragma unroll
+            for (int v = 0; v < D / 8; v++) {
+                *reinterpret_cast<uint4*>(dkd + v * 8) = pack8(dkv + v * 8);
+                *reinterpret_cast<uint4*>(dvd + v * 8) = pack8(dvv + v * 8);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// dq[rows, heads*64] (bf16, row pitch ld) = scale * (optional RoPE^T) dq_acc (fp32)
+__global__ void attn_bwd_dq_finalize_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, long long rows, int W, int ld,
+                                            int S, float scale, const bf16* __restrict__ rope_cos,
+                                            const bf16* __restrict__ rope_sin) {
+    // one thread = 8 columns d0..d0+7 of the first half of a head and the matching 8 of the second half
+    const long long n = rows * (W / 16);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / (W / 16);
+        const int u = (int)(i % (W / 16));
+        const int hd = u >> 2, d0 = (u & 3) * 8;
+        const float* src = acc + r * W + hd * 64 + d0;
+        float a[8], bq[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) { a[j] = src[j] * scale; bq[j] = src[32 + j] * scale; }
+        if (rope_cos) {
+            const int pos = (int)(r % S);
+            float c[8], s[8];
+            unpack8(*reinterpret_cast<const uint4*>(rope_cos + (size_t)pos * 32 + d0), c);
+            unpack8(*reinterpret_cast<const uint4*>(rope_sin + (size_t)pos * 32 + d0), s);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float x = a[j], y = bq[j];
+                a[j] = x * c[j] + y * s[j];
+                bq[j] = y * c[j] - x * s[j];
+            }
+        }
+        bf16* dst = dq + r * ld + hd * 64 + d0;
+        *reinterpret_cast<uint4*>(dst) = pack8(a);
+        *reinterpret_cast<uint4*>(dst + 32) = pack8(bq);
+    }
+}
+
+}   // namespace
+
+// defined in attn_flash.cu
+int b200_attn_bwd_delta_launch(const void* o, const void* d_o, float* delta, const long long* so, const long long* sdo,
+                               int batch, int n_heads, int Sq, cudaStream_t stream);
+
+extern "C" size_t b200_attn_causal_bwd_tc_workspace_bytes(int batch, int n_heads, int Sq) {
+    return (size_t)batch * Sq * n_heads * D * sizeof(float) + (size_t)batch * n_heads * Sq * sizeof(float);
+}
+
+// Same contract as b200_attn_causal_bwd; workspace = fp32 dQ accumulator + delta (b200_attn_causal_bwd_tc_workspace_bytes).
+// q/k/v/dq/dk/dv are thirds of packed [batch*S, ld] activations with heads as contiguous 64-column blocks.
+extern "C" int b200_attn_causal_bwd_tc(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                                       const float* lse, void* dq, void* dk, void* dv,
+                                       const long long* strides /* 8 x {b,r,h}: q,k,v,o,do,dq,dk,dv */, int batch,
+                                       int n_heads, int Sq, int Sk, int head_dim, float scale, const void* rope_cos,
+                                       const void* rope_sin, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    B200_CHECK_ARG(head_dim == D, "attn_causal_bwd_tc: head_dim %d unsupported (64 only)", head_dim);
+    B200_CHECK_ARG(Sk == Sq, "attn_causal_bwd_tc: training shapes only (Sk == Sq)");
+    B200_CHECK_ARG(n_heads % 4 == 0, "attn_causal_bwd_tc: n_heads must be a multiple of 4");
+    for (int i = 0; i < 8; i++)
+        B200_CHECK_ARG(strides[3 * i + 2] == D, "attn_causal_bwd_tc: heads must be contiguous blocks of 64 columns");
+    B200_CHECK_ARG(strides[15] == (long long)Sq * strides[16], "attn_causal_bwd_tc: dq batches must be contiguous");
+    B200_CHECK_ARG(workspace_bytes >= b200_attn_causal_bwd_tc_workspace_bytes(batch, n_heads, Sq),
+                   "attn_causal_bwd_tc: workspace too small");
+    if (batch == 0 || Sq == 0) return B200_OK;
+    const long long W = (long long)n_heads * D;
+    float* dq_acc = (float*)workspace;
+    float* delta = dq_acc + (size_t)batch * Sq * W;
+    B200_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)batch * Sq * W * sizeof(float), stream), "attn_bwd_tc memset");
+    {   // delta = rowsum(dO * O), shared with the mma.sync path
+        int rc = b200_attn_bwd_delta_launch(o, d_o, delta, strides + 9, strides + 12, batch, n_heads, Sq, stream);
+        if (rc) return rc;
+    }
+    CUtensorMap tmQ, tmK, tmV, tmdO;
+    int rc;
+    if ((rc = tc05_make_tmap_3d(&tmQ, q, W, Sq, batch, strides[1], strides[0], D, BQ))) return rc;
+    if ((rc = tc05_make_tmap_3d(&tmK, k, W, Sk, batch, strides[4], strides[3], D, BK))) return rc;
+    if ((rc = tc05_make_tmap_3d(&tmV, v, W, Sk, batch, strides[7], strides[6], D, BK))) return rc;
+    if ((rc = tc05_make_tmap_3d(&tmdO, d_o, W, Sq, batch, strides[13], strides[12], D, BQ))) return rc;
+    BwdParams p;
+    p.lse = lse; p.delta = delta; p.dq_acc = dq_acc;
+    p.dk = (bf16*)dk; p.dv = (bf16*)dv;
+    p.dk_b = strides[18]; p.dk_r = strides[19]; p.dv_b = strides[21]; p.dv_r = strides[22];
+    p.dqa_b = (long long)Sq * W; p.dqa_r = W;
+    p.rope_cos = (const bf16*)rope_cos; p.rope_sin = (const bf16*)rope_sin;
+    p.n_heads = n_heads; p.Sq = Sq; p.Sk = Sk; p.scale = scale;
+    static bool configured = false;
+    if (!configured) {
+        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
+        configured = true;
+    }
+    dim3 grid((Sk + BK - 1) / BK, batch * n_heads);
+    attn_bwd_tc05_kernel<<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, p);
+    B200_CHECK_LAUNCH("attn_causal_bwd_tc");
+    const long long rows = (long long)batch * Sq;
+    long long nthr = rows * (W / 16);
+    int blocks = (int)((nthr + 255) / 256);
+    if (blocks > b200_num_sms() * 16) blocks = b200_num_sms() * 16;
+    attn_bwd_dq_finalize_kernel<<<blocks, 256, 0, stream>>>(dq_acc, (bf16*)dq, rows, (int)W, (int)strides[16], Sq, scale,
+                                                            (const bf16*)rope_cos, (const bf16*)rope_sin);
+    B200_CHECK_LAUNCH("attn_bwd_dq_finalize");
+    return B200_OK;
+}

@@ -11,7 +11,7 @@
 // in hf :325/:331); fp32 split-K partials reduced by splitk_reduce_kernel.
 #include <math.h>
 
-#include "common.cuh"
+#include "tc05.cuh"
 
 namespace {
 
@@ -39,107 +39,7 @@ struct GemmParams {
     int rope_S, rope_D, rope_cols;
 };
 
-// ---------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must trap (error return on the host), never hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
-            printf("b200 gemm: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            smem_u32(dst)),
-        "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
-        "%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// Shared-memory matrix descriptor (sm_100 format): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
-// version=1 [46,48) | layout_type [61,64) (2 = SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-
-// Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
+using namespace tc05;
 
 template <int BLOCK_N>
 struct SmemLayout {
@@ -397,9 +297,28 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, bf16* __restr
     }
 }
 
+template <int BLOCK_N, bool A_MN, bool B_MN>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+    using L = SmemLayout<BLOCK_N>;
+    auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN>;
+    static bool configured = false;
+    if (!configured) {
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL), "gemm smem attr");
+        configured = true;
+    }
+    const int items = p.m_tiles * p.n_tiles * p.splits;
+    const int grid = items < b200_num_sms() ? items : b200_num_sms();
+    kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, p);
+    B200_CHECK_LAUNCH("gemm_tcgen05");
+    return B200_OK;
+}
+
+}   // namespace
+
 // ---------------------------------------------------------------------------
 // host side: tensor maps through the driver entry point (no -lcuda link dependency)
 // ---------------------------------------------------------------------------
+namespace {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -417,8 +336,10 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of pitch `ld` elements, 128B swizzle, zero OOB fill.
-int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
-              uint32_t box_outer) {
+}   // namespace
+
+int tc05::make_tmap_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                       uint32_t box_outer) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         b200_set_error("gemm: cuTensorMapEncodeTiled entry point unavailable");
@@ -439,23 +360,31 @@ int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, 
     return B200_OK;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-    using L = SmemLayout<BLOCK_N>;
-    auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN>;
-    static bool configured = false;
-    if (!configured) {
-        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL), "gemm smem attr");
-        configured = true;
+// 3-D variant {cols, rows-per-sequence, batch}: rows outside a sequence are zero-filled (attention tiles)
+int tc05_make_tmap_3d(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t row_pitch,
+                      uint64_t batch_pitch, uint32_t box_cols, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        b200_set_error("tmap3d: cuTensorMapEncodeTiled entry point unavailable");
+        return B200_ERR_CUDA;
     }
-    const int items = p.m_tiles * p.n_tiles * p.splits;
-    const int grid = items < b200_num_sms() ? items : b200_num_sms();
-    kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, p);
-    B200_CHECK_LAUNCH("gemm_tcgen05");
+    cuuint64_t gdim[3] = {cols, rows, batch};
+    cuuint64_t gstride[2] = {row_pitch * 2, batch_pitch * 2};
+    cuuint32_t box[3] = {box_cols, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        b200_set_error("tmap3d: cuTensorMapEncodeTiled failed (%d) ptr=%p cols=%llu rows=%llu batch=%llu pitch=%llu/%llu",
+                       (int)r, ptr, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)batch,
+                       (unsigned long long)row_pitch, (unsigned long long)batch_pitch);
+        return B200_ERR_CUDA;
+    }
     return B200_OK;
 }
 
-}   // namespace
+
 
 // ---------------------------------------------------------------------------
 // C ABI (declared in include/midi_b200.h)
@@ -590,11 +519,11 @@ static int gemm_impl(const void* A, const void* B, void* C, const void* R, int M
 
     CUtensorMap tmA, tmB;
     int rc;
-    if (!a_mn_major) rc = make_tmap(&tmA, A, K, M, lda, BLOCK_K, BLOCK_M);
-    else             rc = make_tmap(&tmA, A, M, K, lda, 64, BLOCK_K);
+    if (!a_mn_major) rc = tc05::make_tmap_2d(&tmA, A, K, M, lda, BLOCK_K, BLOCK_M);
+    else             rc = tc05::make_tmap_2d(&tmA, A, M, K, lda, 64, BLOCK_K);
     if (rc) return rc;
-    if (!b_mn_major) rc = make_tmap(&tmB, B, K, N, ldb, BLOCK_K, block_n);
-    else             rc = make_tmap(&tmB, B, N, K, ldb, 64, BLOCK_K);
+    if (!b_mn_major) rc = tc05::make_tmap_2d(&tmB, B, K, N, ldb, BLOCK_K, block_n);
+    else             rc = tc05::make_tmap_2d(&tmB, B, N, K, ldb, 64, BLOCK_K);
     if (rc) return rc;
 
 #define B200_DISPATCH(BN)                                                                   \

@@ -22,9 +22,12 @@ from . import lib, ops
 import os
 
 BF16 = torch.bfloat16
-# RoPE fused into the QKV GEMM epilogue (forward) and into the attention backward kernels (B200_FUSE_ROPE=0 uses
-# the stand-alone kernels; both paths have the same rounding points in the forward pass)
+# RoPE backward is fused into the attention backward kernels (B200_FUSE_ROPE=0 -> stand-alone kernel).
+# The forward fusion into the QKV GEMM epilogue exists (ops.linear_rope, bit-identical) but is OFF by default:
+# measured on B200 (profiles/r1_*) the per-row cos/sin gathers make the epilogue longer than the K=1024 main loop
+# (QKV GEMM 1213 -> 843 TFLOP/s), a net loss of 0.8 ms/step against the HBM-roofline stand-alone kernel.
 FUSE_ROPE = os.environ.get("B200_FUSE_ROPE", "1") != "0"
+FUSE_ROPE_FWD = os.environ.get("B200_FUSE_ROPE_FWD", "0") != "0"
 ALIGN = 256   # elements; AdamW's no-decay flags are per 256-element block
 
 
@@ -218,7 +221,7 @@ class StackEngine:
                 n1, rstd1 = ops.rmsnorm(x, w.ln1, c.eps, want_rstd=True)
             else:
                 x, n1, rstd1 = ops.add_rmsnorm(x, pending, w.ln1, c.eps)
-            if FUSE_ROPE:
+            if FUSE_ROPE_FWD:
                 qkv = ops.linear_rope(n1, w.qkv, cos, sin, S, D)      # QKV GEMM with RoPE in the epilogue
             else:
                 qkv = ops.linear(n1, w.qkv)

@@ -205,7 +205,14 @@ def _strides_packed(S: int, H: int, D: int, col0: int, ld: int):
     return [S * ld, ld, D]
 
 
-def attn_causal_fwd(qkv: torch.Tensor, B: int, S: int, n_heads: int, D: int, want_lse: bool):
+import os as _os
+
+# "tc" = tcgen05 / TMEM / TMA kernel (csrc/attn_tc05.cu); "mma" = mma.sync kernel (csrc/attn_flash.cu)
+ATTN_FWD_IMPL = _os.environ.get("B200_ATTN_FWD", "mma")
+ATTN_BWD_IMPL = _os.environ.get("B200_ATTN_BWD", "mma")
+
+
+def attn_causal_fwd(qkv: torch.Tensor, B: int, S: int, n_heads: int, D: int, want_lse: bool, impl: Optional[str] = None):
     """qkv: [B*S, 3H] packed post-RoPE -> out [B*S, H], lse [B, h, S] fp32."""
     H = n_heads * D
     ld = qkv.stride(0)
@@ -213,14 +220,17 @@ def attn_causal_fwd(qkv: torch.Tensor, B: int, S: int, n_heads: int, D: int, wan
     lse = torch.empty((B, n_heads, S), dtype=torch.float32, device=qkv.device) if want_lse else None
     st = torch.tensor([S * ld, ld, D] * 3 + [S * H, H, D], dtype=torch.int64)
     base = qkv.data_ptr()
-    lib.call("b200_attn_causal_fwd", base, base + 2 * H, base + 4 * H, out.data_ptr(), lib.ptr(lse), st.data_ptr(), B,
+    fn = "b200_attn_causal_fwd_tc" if (impl or ATTN_FWD_IMPL) == "tc" else "b200_attn_causal_fwd"
+    lib.call(fn, base, base + 2 * H, base + 4 * H, out.data_ptr(), lib.ptr(lse), st.data_ptr(), B,
              n_heads, S, S, D, 1.0 / math.sqrt(D), lib.stream())
     return out, lse
 
 
 def attn_causal_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, lse: torch.Tensor, B: int, S: int,
-                    n_heads: int, D: int, rope=None) -> torch.Tensor:
+                    n_heads: int, D: int, rope=None, impl: Optional[str] = None) -> torch.Tensor:
     """`rope=(cos, sin)`: also apply the RoPE backward to dq, dk (gradient w.r.t. the pre-rotation projections)."""
+    if (impl or ATTN_BWD_IMPL) == "tc":
+        return _attn_causal_bwd_tc(qkv, out, dout, lse, B, S, n_heads, D, rope)
     H = n_heads * D
     ld = qkv.stride(0)
     dqkv = torch.empty_like(qkv)
@@ -232,6 +242,22 @@ def attn_causal_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, ls
     lib.call("b200_attn_causal_bwd", b, b + 2 * H, b + 4 * H, out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
              delta.data_ptr(), d, d + 2 * H, d + 4 * H, st.data_ptr(), B, n_heads, S, S, D, 1.0 / math.sqrt(D),
              rope[0].data_ptr() if rope else None, rope[1].data_ptr() if rope else None, lib.stream())
+    return dqkv
+
+
+def _attn_causal_bwd_tc(qkv, out, dout, lse, B, S, n_heads, D, rope):
+    H = n_heads * D
+    ld = qkv.stride(0)
+    dqkv = torch.empty_like(qkv)
+    pk = [S * ld, ld, D]
+    po = [S * H, H, D]
+    st = torch.tensor(pk * 3 + po + po + pk * 3, dtype=torch.int64)
+    nbytes = lib.query("b200_attn_causal_bwd_tc_workspace_bytes", B, n_heads, S)
+    ws = _ws("attn_bwd_tc", nbytes, qkv.device)
+    b, d = qkv.data_ptr(), dqkv.data_ptr()
+    lib.call("b200_attn_causal_bwd_tc", b, b + 2 * H, b + 4 * H, out.data_ptr(), dout.data_ptr(), lse.data_ptr(), d, d + 2 * H,
+             d + 4 * H, st.data_ptr(), B, n_heads, S, S, D, 1.0 / math.sqrt(D), rope[0].data_ptr() if rope else None,
+             rope[1].data_ptr() if rope else None, ws.data_ptr(), ws.numel(), lib.stream())
     return dqkv
 
 

@@ -206,6 +206,72 @@ def check_attn_flash():
     return out
 
 
+def check_attn_tc05():
+    """tcgen05 / TMEM / TMA attention forward vs fp32 SDPA and vs the mma.sync kernel (same semantics)."""
+    out = {}
+    for (B, S, nh) in ((1, 128, 4), (2, 384, 16), (1, 200, 16), (2, 2047, 16), (8, 2048, 16)):
+        D, H = 64, nh * 64
+        qkv = randn(B * S, 3 * H, seed=S + B)
+        o, lse = ops.attn_causal_fwd(qkv, B, S, nh, D, want_lse=True, impl="tc")
+        o2, lse2 = ops.attn_causal_fwd(qkv, B, S, nh, D, want_lse=True, impl="mma")
+        torch.cuda.synchronize()
+        out[f"tc_vs_mma_fwd_B{B}_S{S}"] = rel(o.float(), o2.float())
+        out[f"tc_vs_mma_lse_B{B}_S{S}"] = rel(lse, lse2)
+        if B * S <= 4096:
+            q32 = qkv.float().view(B, S, 3, nh, D).permute(2, 0, 3, 1, 4)
+            ref = _sdpa_ref(q32[0], q32[1], q32[2], 0)
+            out[f"tc_fwd_S{S}"] = rel(o.float().view(B, S, nh, D).transpose(1, 2), ref)
+    # backward: tcgen05 kernel vs the mma.sync kernels and vs fp32 autograd
+    for (B, S, nh) in ((1, 128, 4), (2, 384, 16), (1, 200, 16), (2, 2047, 16)):
+        D, H = 64, nh * 64
+        qkv = randn(B * S, 3 * H, seed=S + B + 7)
+        do = randn(B * S, H, seed=S + B + 8)
+        o, lse = ops.attn_causal_fwd(qkv, B, S, nh, D, want_lse=True, impl="mma")
+        g_tc = ops.attn_causal_bwd(qkv, o, do, lse, B, S, nh, D, impl="tc")
+        g_mm = ops.attn_causal_bwd(qkv, o, do, lse, B, S, nh, D, impl="mma")
+        torch.cuda.synchronize()
+        out[f"tc_vs_mma_bwd_dq_S{S}"] = rel(g_tc[:, :H].float(), g_mm[:, :H].float())
+        out[f"tc_vs_mma_bwd_dk_S{S}"] = rel(g_tc[:, H:2 * H].float(), g_mm[:, H:2 * H].float())
+        out[f"tc_vs_mma_bwd_dv_S{S}"] = rel(g_tc[:, 2 * H:].float(), g_mm[:, 2 * H:].float())
+        q32 = qkv.float().view(B, S, 3, nh, D).permute(2, 0, 3, 1, 4).clone().requires_grad_(True)
+        _sdpa_ref(q32[0], q32[1], q32[2], 0).backward(do.float().view(B, S, nh, D).transpose(1, 2))
+        g = q32.grad.permute(1, 3, 0, 2, 4).reshape(B * S, 3 * H)
+        out[f"tc_bwd_S{S}"] = rel(g_tc.float(), g)
+        # with the RoPE backward fused
+        inv = O.default_inv_freq(D).to(BF).to(DEV)
+        cos, sin = ops.rope_table(inv, S)
+        a = ops.attn_causal_bwd(qkv, o, do, lse, B, S, nh, D, rope=(cos, sin), impl="tc")
+        bref = ops.attn_causal_bwd(qkv, o, do, lse, B, S, nh, D, rope=(cos, sin), impl="mma")
+        out[f"tc_vs_mma_bwd_rope_S{S}"] = rel(a.float(), bref.float())
+    # timing at the benchmark shape (B=8, S=2048, 16 heads): CUDA events, 10 launches each
+    qkv = randn(8 * 2048, 3 * 1024, seed=1)
+    do = randn(8 * 2048, 1024, seed=2)
+    o, lse = ops.attn_causal_fwd(qkv, 8, 2048, 16, 64, want_lse=True, impl="mma")
+    for impl in ("tc", "mma"):
+        for _ in range(3):
+            ops.attn_causal_bwd(qkv, o, do, lse, 8, 2048, 16, 64, impl=impl)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.attn_causal_bwd(qkv, o, do, lse, 8, 2048, 16, 64, impl=impl)
+        e1.record()
+        torch.cuda.synchronize()
+        out[f"time_ms_bwd_{impl}"] = e0.elapsed_time(e1) / 10
+    for impl in ("tc", "mma"):
+        for _ in range(3):
+            ops.attn_causal_fwd(qkv, 8, 2048, 16, 64, want_lse=True, impl=impl)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.attn_causal_fwd(qkv, 8, 2048, 16, 64, want_lse=True, impl=impl)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        out[f"time_ms_{impl}"] = ms
+        out[f"tflops_{impl}"] = 4 * 8 * 16 * 2048 * 2049 / 2 * 64 / (ms * 1e-3) / 1e12
+    return out
+
+
 def check_attn_tiny():
     out = {}
     nh, D = 4, 256
@@ -671,7 +737,7 @@ def check_model_peaked_greedy():
 
 GROUPS = {
     "gemm_fwd": check_gemm_fwd, "gemm_dgrad": check_gemm_dgrad, "gemm_wgrad": check_gemm_wgrad,
-    "elementwise": check_elementwise, "fused_rope": check_fused_rope, "attn_flash": check_attn_flash, "attn_tiny": check_attn_tiny,
+    "elementwise": check_elementwise, "fused_rope": check_fused_rope, "attn_flash": check_attn_flash, "attn_tc05": check_attn_tc05, "attn_tiny": check_attn_tiny,
     "loss_optim": check_loss_optim, "decode": check_decode, "model_forward": check_model_forward,
     "model_layer_tf": check_model_layer_teacher_forced, "model_train": check_model_train,
     "model_generate": check_model_generate, "model_peaked_greedy": check_model_peaked_greedy,
@@ -685,6 +751,7 @@ THRESH = [
     ("rope_table_mismatch", 8.0), ("rope_fwd_mismatch", 64.0), ("rope_bwd_adjoint", 2e-2),
     ("swiglu_fwd_mismatch", 2e-2), ("swiglu_bwd", 4e-3),
     ("linear_rope_mismatch", 0.0), ("attn_bwd_fused_rope_v_mismatch", 0.0), ("attn_bwd_fused_rope", 5e-3),
+    ("tc_vs_mma_bwd", 8e-3), ("tc_bwd", 1.2e-2), ("tc_vs_mma", 4e-3), ("tc_fwd", 6e-3),
     ("flash_fwd", 6e-3), ("flash_lse", 1e-4), ("flash_bwd", 1.2e-2), ("tiny_fwd", 6e-3), ("tiny_bwd", 1.2e-2),
     ("ce_loss_abs", 2e-3), ("ce_count_abs", 0.0), ("ce_bwd_padcols_absmax", 0.0), ("ce_bwd", 6e-3),
     ("ce_all_ignored_loss", 0.0), ("gradnorm_rel", 1e-4), ("adamw_maxabs", 2e-3),
