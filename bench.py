@@ -178,23 +178,18 @@ def run_native(args):
     n_batches = 4
     host = [synth_batch(tok, B_PER_GPU, S_EVENTS + 1, seed=1234 + rank + 101 * i).pin_memory() for i in range(n_batches)]
     resident = [b.to(dev) for b in host]
-    comm = torch.cuda.Stream(device=dev) if world > 1 else None
-
-    def allreduce_grads():
-        if world == 1:
-            return
-        # one flat bf16 buffer: a single NCCL all-reduce (average) over NVLink, issued on a side stream
-        comm.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(comm):
-            dist.all_reduce(rt.store.gflat, op=dist.ReduceOp.AVG)
-        torch.cuda.current_stream().wait_stream(comm)
+    from midi_b200 import ddp
+    # gradient averaging: NCCL all-reduce of the flat bf16 gradient buffer in 128 MB buckets on a side stream; the
+    # token-level stack + lm_head slice is reduced while the event-level stack's backward is still running
+    sync = ddp.GradSync(rt.store.gflat) if world > 1 else None
 
     state = {"step": 0}
 
     def step(batch_dev):
         state["step"] += 1
-        loss = model.training_loss(batch_dev)
-        allreduce_grads()
+        loss = model.training_loss(batch_dev, grad_ready=sync.ready if sync else None)
+        if sync:
+            sync.wait()
         lr = LR * min(1.0, state["step"] / WARMUP_STEPS)
         model.fused_optimizer_step(lr=lr, step=state["step"])
         return loss

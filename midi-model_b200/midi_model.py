@@ -428,10 +428,13 @@ class MIDIModel(PreTrainedModel):
         return seq[:, :cur_len].cpu().numpy()
 
     # ------------------------------------------------------------------ fused training path (non-reference API)
-    def training_loss(self, batch: torch.Tensor, backward: bool = True, accumulate: bool = False):
+    def training_loss(self, batch: torch.Tensor, backward: bool = True, accumulate: bool = False, grad_ready=None):
         """train.py:168-185 (sample_seq=False) fused: x = batch[:, :-1], y = batch[:, 1:], both stacks, lm_head,
         mean CE with ignore_index=pad -- and, if `backward`, every gradient written to the flat gradient buffer
-        (`.grad` of each parameter is a view of it).  Returns a 0-dim fp32 tensor (no host sync)."""
+        (`.grad` of each parameter is a view of it).  Returns a 0-dim fp32 tensor (no host sync).
+        `grad_ready(start, end)` (optional) is called as soon as a slice of the flat gradient buffer is final --
+        first the token-level stack + lm_head, then the event-level stack -- so a data-parallel trainer can start
+        the all-reduce of the first slice while the second is still being computed (midi_b200/ddp.py)."""
         rt = self._rt()
         tok = self.tokenizer
         B, S1, T = batch.shape
@@ -455,9 +458,13 @@ class MIDIModel(PreTrainedModel):
             dhidden, = _inner_backward(rt, self, sv_i, hs, logits, ids_in, B * S, T, T - 1, True, g_i, rt.g_lm_head,
                                        accumulate)
             del logits, hs
+            if grad_ready is not None:
+                grad_ready(rt.inner.seg_start, rt.store.numel)
             de = rt.outer.backward(sv_o, dhidden, g_o, accumulate=accumulate)
             _ops.embed_bwd(x.view(-1), de, g_o.embed, per_row=T, row_stride=1, row_inner=0, row_off=0,
                            pad_id=self.config.net_config.pad_token_id, accumulate=accumulate)
+            if grad_ready is not None:
+                grad_ready(0, rt.inner.seg_start)
             rt.store.publish_grads()
         return loss
 
