@@ -516,8 +516,9 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (lane == 0) mbar_arrive(dq_empty);
             ph ^= 1;
         }
-        // epilogue: dV, dK for this key tile (warps 2..5 hold one full row each)
-        if (cw < 4 && key < p.Sk) {
+        // epilogue: dV, dK for this key tile (warps 2..5 hold one full row each).  The TMEM loads are warp-collective
+        // (.sync.aligned): every lane executes them, only the global stores are predicated on key < Sk.
+        if (cw < 4) {
             float dvv[D], dkv[D];
             if (n_it > 0) {
 #pragma unroll
@@ -536,7 +537,7 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
                 for (int i = 0; i < D; i++) { dvv[i] = 0.f; dkv[i] = 0.f; }
             }
-            if (p.rope_cos) {
+            if (p.rope_cos && key < p.Sk) {
                 const bf16* cp = p.rope_cos + (size_t)key * 32;
                 const bf16* sp = p.rope_sin + (size_t)key * 32;
 #pragma unroll
@@ -547,6 +548,7 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     dkv[i + 32] = bb * c - a * s;
                 }
             }
+          if (key < p.Sk) {
             bf16* dkd = p.dk + b * p.dk_b + (long long)key * p.dk_r + h * D;
             bf16* dvd = p.dv + b * p.dv_b + (long long)key * p.dv_r + h * D;
 #pragma unroll
@@ -554,6 +556,7 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 *reinterpret_cast<uint4*>(dkd + v * 8) = pack8(dkv + v * 8);
                 *reinterpret_cast<uint4*>(dvd + v * 8) = pack8(dvv + v * 8);
             }
+          }
         }
     }
     tc_fence_before();

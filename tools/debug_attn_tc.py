@@ -34,4 +34,21 @@ for (B, S, nh) in shapes:
         torch.cuda.synchronize()
         P("  done in %.3fs" % (time.time() - t), "dq", G.rel(g_tc[:, :H].float(), g_mm[:, :H].float()),
           "dk", G.rel(g_tc[:, H:2 * H].float(), g_mm[:, H:2 * H].float()), "dv", G.rel(g_tc[:, 2 * H:].float(), g_mm[:, 2 * H:].float()))
+# timing at the benchmark shape
+B, S, nh, D, H = 8, 2048, 16, 64, 1024
+qkv = G.randn(B * S, 3 * H, seed=1)
+do = G.randn(B * S, H, seed=2)
+o, lse = ops.attn_causal_fwd(qkv, B, S, nh, D, want_lse=True, impl="mma")
+for impl in ("tc", "mma"):
+    f = (lambda: ops.attn_causal_fwd(qkv, B, S, nh, D, want_lse=True, impl=impl)) if which == "fwd" else \
+        (lambda: ops.attn_causal_bwd(qkv, o, do, lse, B, S, nh, D, impl=impl))
+    for _ in range(3):
+        f()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        f()
+    e1.record()
+    torch.cuda.synchronize()
+    P(which, impl, "ms per call: %.3f" % (e0.elapsed_time(e1) / 10))
 P("ALL DONE")
