@@ -185,7 +185,7 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                         if (key > row + off || key >= p.Sk) s0 = -INFINITY;
                         if (key + 1 > row + off || key + 1 >= p.Sk) s1 = -INFINITY;
                     }
-                    const float p0 = exp2f(s0 * sl2 - msc), p1 = exp2f(s1 * sl2 - msc);
+                    const float p0 = ex2_approx(fmaf(s0, sl2, -msc)), p1 = ex2_approx(fmaf(s1, sl2, -msc));
                     rs += p0 + p1;
                     pk[i >> 1] = pack2(p0, p1);
                 }
@@ -441,13 +441,19 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         uint8_t* sP = smem + SB_P + half * 16384 + key_t * 128;
         uint8_t* sDS = smem + SB_DS + half * 16384 + key_t * 128;
         uint32_t ph = 0;
+        // lse / delta of the query tile: one value per compute thread, fetched one iteration ahead so the global
+        // load latency hides behind the previous iteration
+        auto fetch_ld = [&](int it_) -> float {
+            const int qi = (i0 + it_) * BQ + (ctid & 127);
+            if (it_ >= n_it || qi >= p.Sq) return 0.f;
+            return ctid < 128 ? lse_g[qi] * LOG2E : delta_g[qi];
+        };
+        float ld_next = fetch_ld(0);
         for (int it = 0; it < n_it; it++) {
             const int q0 = (i0 + it) * BQ;
-            {   // stage this tile's lse / delta rows in shared memory (one value per thread)
-                const int par = it & 1;
-                const int qi = q0 + (ctid & 127);
-                const float v = qi < p.Sq ? (ctid < 128 ? lse_g[qi] * LOG2E : delta_g[qi]) : 0.f;
-                (ctid < 128 ? lse_s : delta_s)[par * 128 + (ctid & 127)] = v;
+            {
+                (ctid < 128 ? lse_s : delta_s)[(it & 1) * 128 + (ctid & 127)] = ld_next;
+                ld_next = fetch_ld(it + 1);
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             const float* lse_t = lse_s + (it & 1) * 128 + half * 64;
@@ -472,7 +478,7 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
                     for (int e = 0; e < 2; e++) {
                         const int qq = c * 32 + i + e;                 // column inside this thread's 64
-                        float pr = exp2f(__uint_as_float(rs[i + e]) * sl2 - lse_t[qq]);
+                        float pr = ex2_approx(fmaf(__uint_as_float(rs[i + e]), sl2, -lse_t[qq]));
                         if (need_mask) {
                             const int qrow = q0 + half * 64 + qq;
                             if (key > qrow + off || key >= p.Sk || qrow >= p.Sq) pr = 0.f;

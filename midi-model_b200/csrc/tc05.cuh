@@ -30,16 +30,37 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must trap (error return on the host), never hang the GPU.
+// try_wait with a suspend-time hint: the waiting thread is parked by the hardware (no issue slots burnt) until the
+// phase completes or ~hint_ns elapse
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (error return on the host), never hang the GPU.  Waiters sleep in hardware
+// between polls so they do not steal issue slots from the math warps.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
+    for (uint32_t spins = 0; !mbar_try_wait_hint(bar, parity, 20000u); spins++) {
+        if (spins > 400000u) {   // >= several seconds even if every poll returns immediately
             printf("b200: mbarrier wait timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
             __trap();
         }
     }
+}
+// 2^x on the SFU (ex2.approx): one MUFU op, exact enough for softmax probabilities that are rounded to bf16
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
     asm volatile(
