@@ -36,6 +36,9 @@ for p in (os.path.join(ROOT, "midi-model_b200"), ROOT):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the single JSON line
+
 import torch  # noqa: E402
 
 METRIC = "train_tokens_per_sec"

@@ -244,7 +244,18 @@ class StackEngine:
         return y, sv
 
     # ------------------------------------------------------------------ backward
-    def backward(self, sv: dict, dy: torch.Tensor, grads: StackGrads, accumulate: bool = False) -> torch.Tensor:
+    def layer_range(self, li: int):
+        """[start, end) of layer `li`'s parameters inside the flat parameter / gradient buffers."""
+        p = self.cfg.prefix
+        first = self.store.offsets[f"{p}.layers.{li}.self_attn.q_proj.weight"]
+        if li + 1 < self.cfg.n_layer:
+            end = self.store.offsets[f"{p}.layers.{li + 1}.self_attn.q_proj.weight"]
+        else:
+            end = self.store.offsets[f"{p}.norm.weight"]
+        return first, end
+
+    def backward(self, sv: dict, dy: torch.Tensor, grads: StackGrads, accumulate: bool = False,
+                 layer_done=None) -> torch.Tensor:
         """dy: grad of the final-normed output.  Writes (or accumulates) every weight gradient of the stack into
         `grads` and returns the gradient w.r.t. the stack input (inputs_embeds)."""
         c = self.cfg
@@ -285,5 +296,7 @@ class StackEngine:
             del dqkv, n1
             dx = ops.rmsnorm_bwd(dn1, x, w.ln1, rstd1, dh, g.ln1, accumulate)
             del dn1, dh, x
+            if layer_done is not None:
+                layer_done(li)
         sv["layers"] = None
         return dx

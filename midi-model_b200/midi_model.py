@@ -460,11 +460,22 @@ class MIDIModel(PreTrainedModel):
             del logits, hs
             if grad_ready is not None:
                 grad_ready(rt.inner.seg_start, rt.store.numel)
-            de = rt.outer.backward(sv_o, dhidden, g_o, accumulate=accumulate)
+            layer_done = None
+            if grad_ready is not None:
+                # event-level stack: hand finished gradients over in groups of 3 layers while backward continues
+                nl = rt.outer.cfg.n_layer
+                hi = [rt.inner.seg_start]
+
+                def layer_done(li):
+                    if li % 3 == 0:
+                        lo = rt.outer.layer_range(li)[0]
+                        grad_ready(lo, hi[0])
+                        hi[0] = lo
+            de = rt.outer.backward(sv_o, dhidden, g_o, accumulate=accumulate, layer_done=layer_done)
             _ops.embed_bwd(x.view(-1), de, g_o.embed, per_row=T, row_stride=1, row_inner=0, row_off=0,
                            pad_id=self.config.net_config.pad_token_id, accumulate=accumulate)
             if grad_ready is not None:
-                grad_ready(0, rt.inner.seg_start)
+                grad_ready(0, hi[0])          # embedding table (+ whatever is left)
             rt.store.publish_grads()
         return loss
 
