@@ -291,7 +291,8 @@ extern "C" int b200_attn_causal_fwd_tc(const void* q, const void* k, const void*
 // =============================================================================================
 namespace {
 
-constexpr int BWD_THREADS = 320;                 // warp 0 TMA, warp 1 MMA, warps 2..9 compute
+constexpr int BWD_CWARPS = 16;                   // compute warps: thread = (key row, 32 of the 128 query columns)
+constexpr int BWD_THREADS = 64 + 32 * BWD_CWARPS; // warp 0 TMA, warp 1 MMA, warps 2..17 compute
 constexpr int SB_K = 0, SB_V = 16384;
 constexpr int SB_Q = 32768;                      // 2 stages x (Q 16 KB + dO 16 KB)
 constexpr int SB_P = SB_Q + 2 * 32768;           // P^T : two 64-query atoms of [128 keys x 128 B]
@@ -349,7 +350,7 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmdO);
         mbar_init(kv_full, 1);
         for (int s = 0; s < 2; s++) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
-        mbar_init(s_full, 1); mbar_init(pds_full, 8); mbar_init(dq_full, 1); mbar_init(dq_empty, 8);
+        mbar_init(s_full, 1); mbar_init(pds_full, BWD_CWARPS); mbar_init(dq_full, 1); mbar_init(dq_empty, BWD_CWARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -428,48 +429,41 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             }
         }
     } else {
-        const int cw = warp - 2;                       // 0..7
+        const int cw = warp - 2;                       // 0..15
         const int quarter = warp & 3;
-        const int half = cw >> 2;                      // which 64 query columns of the tile this thread handles
+        const int cg = cw >> 2;                        // which 32 query columns of the tile this thread handles
         const int key_t = quarter * 32 + lane;         // key row inside the tile == TMEM lane
         const int key = k0 + key_t;
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         const float sl2 = p.scale * LOG2E;
-        const int ctid = threadIdx.x - 64;             // 0..255
+        const int ctid = threadIdx.x - 64;             // 0..511
         const float* lse_g = p.lse + ((long long)b * p.n_heads + h) * p.Sq;
         const float* delta_g = p.delta + ((long long)b * p.n_heads + h) * p.Sq;
-        uint8_t* sP = smem + SB_P + half * 16384 + key_t * 128;
-        uint8_t* sDS = smem + SB_DS + half * 16384 + key_t * 128;
+        uint8_t* sP = smem + SB_P + (cg >> 1) * 16384 + key_t * 128;
+        uint8_t* sDS = smem + SB_DS + (cg >> 1) * 16384 + key_t * 128;
         uint32_t ph = 0;
-        // lse / delta of the query tile: one value per compute thread, fetched one iteration ahead so the global
-        // load latency hides behind the previous iteration
+        // lse / delta of the query tile: one value per thread of the first 8 compute warps, fetched one iteration
+        // ahead so the global load latency hides behind the previous iteration
         auto fetch_ld = [&](int it_) -> float {
             const int qi = (i0 + it_) * BQ + (ctid & 127);
-            if (it_ >= n_it || qi >= p.Sq) return 0.f;
+            if (ctid >= 256 || it_ >= n_it || qi >= p.Sq) return 0.f;
             return ctid < 128 ? lse_g[qi] * LOG2E : delta_g[qi];
         };
         float ld_next = fetch_ld(0);
         for (int it = 0; it < n_it; it++) {
             const int q0 = (i0 + it) * BQ;
-            {
-                (ctid < 128 ? lse_s : delta_s)[(it & 1) * 128 + (ctid & 127)] = ld_next;
-                ld_next = fetch_ld(it + 1);
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-            }
-            const float* lse_t = lse_s + (it & 1) * 128 + half * 64;
-            const float* delta_t = delta_s + (it & 1) * 128 + half * 64;
+            if (ctid < 256) (ctid < 128 ? lse_s : delta_s)[(it & 1) * 128 + (ctid & 127)] = ld_next;
+            ld_next = fetch_ld(it + 1);
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            const float* lse_t = lse_s + (it & 1) * 128 + cg * 32;
+            const float* delta_t = delta_s + (it & 1) * 128 + cg * 32;
             const bool need_mask = (k0 + BK - 1 > q0 + off) || (k0 + BK > p.Sk) || (q0 + BQ > p.Sq);
             mbar_wait(s_full, ph);
             tc_fence_after();
-            if (it > 0) {
-                // previous iteration's dQ tile: drain TMEM -> fp32 global accumulator (this thread: 32 of the 64 columns)
-                // (done here, after s_full, so the reds overlap this iteration's S^T / dP^T MMAs)
-            }
-#pragma unroll 1
-            for (int c = 0; c < 2; c++) {
+            {
                 uint32_t rs[32], rd[32];
-                tmem_ld32(tS + lane_addr + half * 64 + c * 32, rs);
-                tmem_ld32(tdP + lane_addr + half * 64 + c * 32, rd);
+                tmem_ld32(tS + lane_addr + cg * 32, rs);
+                tmem_ld32(tdP + lane_addr + cg * 32, rd);
                 tmem_ld_wait();
                 uint32_t pk[16], dk_[16];
 #pragma unroll
@@ -477,21 +471,21 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     float pv[2], dsv[2];
 #pragma unroll
                     for (int e = 0; e < 2; e++) {
-                        const int qq = c * 32 + i + e;                 // column inside this thread's 64
-                        float pr = ex2_approx(fmaf(__uint_as_float(rs[i + e]), sl2, -lse_t[qq]));
+                        const int qq = i + e;
+                        float pr = ex2_approx(fmaf(__uint_as_float(rs[qq]), sl2, -lse_t[qq]));
                         if (need_mask) {
-                            const int qrow = q0 + half * 64 + qq;
+                            const int qrow = q0 + cg * 32 + qq;
                             if (key > qrow + off || key >= p.Sk || qrow >= p.Sq) pr = 0.f;
                         }
                         pv[e] = pr;
-                        dsv[e] = pr * (__uint_as_float(rd[i + e]) - delta_t[qq]);
+                        dsv[e] = pr * (__uint_as_float(rd[qq]) - delta_t[qq]);
                     }
                     pk[i >> 1] = pack2(pv[0], pv[1]);
                     dk_[i >> 1] = pack2(dsv[0], dsv[1]);
                 }
 #pragma unroll
                 for (int v = 0; v < 4; v++) {
-                    const int chunk = c * 4 + v;
+                    const int chunk = (cg & 1) * 4 + v;
                     const int sw = (chunk ^ (key_t & 7)) << 4;
                     *reinterpret_cast<uint4*>(sP + sw) = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
                     *reinterpret_cast<uint4*>(sDS + sw) = make_uint4(dk_[4 * v], dk_[4 * v + 1], dk_[4 * v + 2], dk_[4 * v + 3]);
@@ -501,18 +495,18 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(pds_full);
-            // dQ_i tile: TMEM lane = query row, this thread owns columns half*32 .. +31
+            // dQ_i tile: TMEM lane = query row, this thread owns columns cg*16 .. +15
             mbar_wait(dq_full, ph);
             tc_fence_after();
             {
-                uint32_t r[32];
-                tmem_ld32(tdQ + lane_addr + half * 32, r);
+                uint32_t r[16];
+                tmem_ld16(tdQ + lane_addr + cg * 16, r);
                 tmem_ld_wait();
                 const int qrow = q0 + key_t;                           // (lane index now means query row)
                 if (qrow < p.Sq) {
-                    float* dst = p.dq_acc + b * p.dqa_b + (long long)qrow * p.dqa_r + h * D + half * 32;
+                    float* dst = p.dq_acc + b * p.dqa_b + (long long)qrow * p.dqa_r + h * D + cg * 16;
 #pragma unroll
-                    for (int v = 0; v < 8; v++)
+                    for (int v = 0; v < 4; v++)
                         red_add_v4(dst + v * 4, __uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
                                    __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
                 }
@@ -522,47 +516,56 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (lane == 0) mbar_arrive(dq_empty);
             ph ^= 1;
         }
-        // epilogue: dV, dK for this key tile (warps 2..5 hold one full row each).  The TMEM loads are warp-collective
-        // (.sync.aligned): every lane executes them, only the global stores are predicated on key < Sk.
-        if (cw < 4) {
-            float dvv[D], dkv[D];
+        // epilogue: warps 2..9 write dK (two 16-column groups that form RoPE pairs d, d+32), warps 10..17 write dV
+        // (32 columns each).  TMEM loads are warp-collective: every lane executes them, only the stores are predicated.
+        {
+            const int part = (cw >> 2) & 1;
+            const bool is_dk = cw < 8;
+            float v0[16], v1[16];
             if (n_it > 0) {
+                uint32_t r[16];
+                const uint32_t tsrc = (is_dk ? tdK : tdV) + lane_addr;
+                const int c0 = is_dk ? part * 16 : part * 32, c1 = is_dk ? 32 + part * 16 : part * 32 + 16;
+                tmem_ld16(tsrc + c0, r);
+                tmem_ld_wait();
 #pragma unroll
-                for (int c = 0; c < 2; c++) {
-                    uint32_t r[32];
-                    tmem_ld32(tdV + lane_addr + c * 32, r);
-                    tmem_ld_wait();
+                for (int i = 0; i < 16; i++) v0[i] = __uint_as_float(r[i]);
+                tmem_ld16(tsrc + c1, r);
+                tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; i++) dvv[c * 32 + i] = __uint_as_float(r[i]);
-                    tmem_ld32(tdK + lane_addr + c * 32, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; i++) dkv[c * 32 + i] = __uint_as_float(r[i]) * p.scale;
-                }
+                for (int i = 0; i < 16; i++) v1[i] = __uint_as_float(r[i]);
             } else {
 #pragma unroll
-                for (int i = 0; i < D; i++) { dvv[i] = 0.f; dkv[i] = 0.f; }
+                for (int i = 0; i < 16; i++) { v0[i] = 0.f; v1[i] = 0.f; }
             }
-            if (p.rope_cos && key < p.Sk) {
-                const bf16* cp = p.rope_cos + (size_t)key * 32;
-                const bf16* sp = p.rope_sin + (size_t)key * 32;
+            if (key < p.Sk) {
+                if (is_dk) {
 #pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    const float c = __bfloat162float(cp[i]), s = __bfloat162float(sp[i]);
-                    const float a = dkv[i], bb = dkv[i + 32];
-                    dkv[i] = a * c + bb * s;
-                    dkv[i + 32] = bb * c - a * s;
+                    for (int i = 0; i < 16; i++) { v0[i] *= p.scale; v1[i] *= p.scale; }
+                    if (p.rope_cos) {
+                        const bf16* cp = p.rope_cos + (size_t)key * 32 + part * 16;
+                        const bf16* sp = p.rope_sin + (size_t)key * 32 + part * 16;
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            const float c = __bfloat162float(cp[i]), sn = __bfloat162float(sp[i]);
+                            const float a = v0[i], bb = v1[i];
+                            v0[i] = a * c + bb * sn;
+                            v1[i] = bb * c - a * sn;
+                        }
+                    }
+                    bf16* d0 = p.dk + b * p.dk_b + (long long)key * p.dk_r + h * D + part * 16;
+                    *reinterpret_cast<uint4*>(d0) = pack8(v0);
+                    *reinterpret_cast<uint4*>(d0 + 8) = pack8(v0 + 8);
+                    *reinterpret_cast<uint4*>(d0 + 32) = pack8(v1);
+                    *reinterpret_cast<uint4*>(d0 + 40) = pack8(v1 + 8);
+                } else {
+                    bf16* d0 = p.dv + b * p.dv_b + (long long)key * p.dv_r + h * D + part * 32;
+                    *reinterpret_cast<uint4*>(d0) = pack8(v0);
+                    *reinterpret_cast<uint4*>(d0 + 8) = pack8(v0 + 8);
+                    *reinterpret_cast<uint4*>(d0 + 16) = pack8(v1);
+                    *reinterpret_cast<uint4*>(d0 + 24) = pack8(v1 + 8);
                 }
             }
-          if (key < p.Sk) {
-            bf16* dkd = p.dk + b * p.dk_b + (long long)key * p.dk_r + h * D;
-            bf16* dvd = p.dv + b * p.dv_b + (long long)key * p.dv_r + h * D;
-#pragma unroll
-            for (int v = 0; v < D / 8; v++) {
-                *reinterpret_cast<uint4*>(dkd + v * 8) = pack8(dkv + v * 8);
-                *reinterpret_cast<uint4*>(dvd + v * 8) = pack8(dvv + v * 8);
-            }
-          }
         }
     }
     tc_fence_before();
