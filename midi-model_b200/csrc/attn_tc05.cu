@@ -319,6 +319,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+template <bool WITH_DQ>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const BwdParams p) {
@@ -400,7 +401,7 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             for (int it = 0; it < n_it; it++) {
                 const uint32_t sQ = smem_u32(smem + SB_Q + stage * 32768), sdO = sQ + 16384;
                 mbar_wait(pds_full, ph);          // P^T, dS^T of this iteration are in shared memory; S^T/dP^T TMEM is free
-                mbar_wait(dq_empty, ph ^ 1);      // previous dQ tile drained
+                if (WITH_DQ) mbar_wait(dq_empty, ph ^ 1);      // previous dQ tile drained
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < BQ / 16; kk++) {
@@ -414,10 +415,12 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     umma_f16(tdK, make_smem_desc(sDS + a_off, 16, 1024), make_smem_desc(sQ + kk * 2048, 16384, 1024), id_kv,
                              (it > 0 || kk > 0) ? 1u : 0u);
                 }
+                if (WITH_DQ) {
 #pragma unroll
-                for (int kk = 0; kk < BK / 16; kk++)   // K dimension = keys: 16 key rows per step
-                    umma_f16(tdQ, make_smem_desc(sDS + kk * 2048, 16384, 1024), make_smem_desc(sK + kk * 2048, 16384, 1024),
-                             id_dq, kk > 0);
+                    for (int kk = 0; kk < BK / 16; kk++)   // K dimension = keys: 16 key rows per step
+                        umma_f16(tdQ, make_smem_desc(sDS + kk * 2048, 16384, 1024), make_smem_desc(sK + kk * 2048, 16384, 1024),
+                                 id_dq, kk > 0);
+                }
                 umma_commit(dq_full);
                 umma_commit(&q_empty[stage]);
                 if (++stage == 2) { stage = 0; qphase ^= 1; }
@@ -496,9 +499,9 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(pds_full);
             // dQ_i tile: TMEM lane = query row, this thread owns columns cg*16 .. +15
-            mbar_wait(dq_full, ph);
+            mbar_wait(dq_full, ph);           // dV / dK (/ dQ) MMAs of this iteration retired: P^T, dS^T smem reusable
             tc_fence_after();
-            {
+            if (WITH_DQ) {
                 uint32_t r[16];
                 tmem_ld16(tdQ + lane_addr + cg * 16, r);
                 tmem_ld_wait();
@@ -511,9 +514,11 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                                    __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(dq_empty);
+            if (WITH_DQ) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(dq_empty);
+            }
             ph ^= 1;
         }
         // epilogue: warps 2..9 write dK (two 16-column groups that form RoPE pairs d, d+32), warps 10..17 write dV
@@ -565,6 +570,211 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     *reinterpret_cast<uint4*>(d0 + 16) = pack8(v1);
                     *reinterpret_cast<uint4*>(d0 + 24) = pack8(v1 + 8);
                 }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dQ kernel (no atomics): one CTA = 128 query rows of one (batch, head), looping over the key tiles up to the
+// diagonal.  S = Q.K_j^T and dP = dO.V_j^T are recomputed on the tensor cores (cheap: the tensor pipe is mostly idle
+// in the backward pass, while a red.global-based accumulation of dQ saturates the L2 atomic units -- measured),
+// dS = P o (dP - delta) is written row-wise to swizzled shared memory and dQ += dS . K_j accumulates in TMEM.
+// ---------------------------------------------------------------------------------------------
+constexpr int SQ_Q = 0, SQ_DO = 16384;
+constexpr int SQ_KV = 32768;                     // 2 stages x (K 16 KB + V 16 KB)
+constexpr int SQ_DS = SQ_KV + 2 * 32768;         // dS [128 q x 128 keys]: two 64-key atoms
+constexpr int SQ_BAR = SQ_DS + 32768;
+constexpr int SMEM_DQ_BYTES = SQ_BAR + 128;
+
+struct DqParams {
+    const float* lse;
+    const float* delta;
+    bf16* dq;
+    long long dq_b, dq_r;
+    const bf16* rope_cos;
+    const bf16* rope_sin;
+    int n_heads, Sq, Sk;
+    float scale;
+};
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_bwd_dq_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const DqParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SQ_BAR);
+    uint64_t* q_full = bars + 0;
+    uint64_t* kv_full = bars + 1;     // [2]
+    uint64_t* kv_empty = bars + 3;    // [2]
+    uint64_t* s_full = bars + 5;
+    uint64_t* ds_full = bars + 6;
+    uint64_t* dq_done = bars + 7;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = gridDim.x - 1 - blockIdx.x;       // long tiles first
+    const int bh = blockIdx.y;
+    const int b = bh / p.n_heads, h = bh % p.n_heads;
+    const int q0 = qt * BQ;
+    const int off = p.Sk - p.Sq;
+    int n_kv = min((p.Sk + BK - 1) / BK, (q0 + BQ - 1 + off) / BK + 1);
+    if (n_kv < 1) n_kv = 1;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmdO);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < 2; s++) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        mbar_init(s_full, 1); mbar_init(ds_full, BWD_CWARPS); mbar_init(dq_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdQ = tmem_base + 256;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(q_full, 2 * BQ * D * 2);
+            tma_load_3d(smem + SQ_Q, &tmQ, q_full, h * D, q0, b);
+            tma_load_3d(smem + SQ_DO, &tmdO, q_full, h * D, q0, b);
+            int stage = 0; uint32_t phase = 0;
+            for (int j = 0; j < n_kv; j++) {
+                mbar_wait(&kv_empty[stage], phase ^ 1);
+                uint8_t* sK = smem + SQ_KV + stage * 32768;
+                mbar_expect_tx(&kv_full[stage], 2 * BK * D * 2);
+                tma_load_3d(sK, &tmK, &kv_full[stage], h * D, j * BK, b);
+                tma_load_3d(sK + 16384, &tmV, &kv_full[stage], h * D, j * BK, b);
+                if (++stage == 2) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t id_s = make_idesc(128, 128, false, false);
+            constexpr uint32_t id_dq = make_idesc(128, 64, false, true);      // A = dS (K-major over keys), B = K MN-major
+            const uint32_t sQ = smem_u32(smem + SQ_Q), sdO = smem_u32(smem + SQ_DO), sDS = smem_u32(smem + SQ_DS);
+            mbar_wait(q_full, 0);
+            int stage = 0; uint32_t kv_phase = 0, ph = 0;
+            auto issue_s = [&](int st) {
+                const uint32_t sK = smem_u32(smem + SQ_KV + st * 32768), sV = sK + 16384;
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < D / 16; k++)
+                    umma_f16(tS, make_smem_desc(sQ + k * 32, 16, 1024), make_smem_desc(sK + k * 32, 16, 1024), id_s, k > 0);
+#pragma unroll
+                for (int k = 0; k < D / 16; k++)
+                    umma_f16(tdP, make_smem_desc(sdO + k * 32, 16, 1024), make_smem_desc(sV + k * 32, 16, 1024), id_s, k > 0);
+                umma_commit(s_full);
+            };
+            mbar_wait(&kv_full[0], 0);
+            issue_s(0);
+            for (int j = 0; j < n_kv; j++) {
+                const uint32_t sK = smem_u32(smem + SQ_KV + stage * 32768);
+                mbar_wait(ds_full, ph);           // dS_j in shared memory; S / dP TMEM free again
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < BK / 16; kk++)
+                    umma_f16(tdQ, make_smem_desc(sDS + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                             make_smem_desc(sK + kk * 2048, 16384, 1024), id_dq, (j > 0 || kk > 0) ? 1u : 0u);
+                umma_commit(&kv_empty[stage]);
+                if (++stage == 2) { stage = 0; kv_phase ^= 1; }
+                if (j + 1 < n_kv) {
+                    mbar_wait(&kv_full[stage], kv_phase);
+                    issue_s(stage);               // in order behind the dQ MMAs: they have finished reading dS_j by then
+                } else {
+                    umma_commit(dq_done);
+                }
+                ph ^= 1;
+            }
+        }
+    } else {
+        const int cw = warp - 2;
+        const int quarter = warp & 3;
+        const int cg = cw >> 2;                        // 32 of the 128 key columns
+        const int row_t = quarter * 32 + lane;
+        const int row = q0 + row_t;
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        const float sl2 = p.scale * LOG2E;
+        const long long sidx = ((long long)b * p.n_heads + h) * p.Sq + row;
+        const float lse_r = row < p.Sq ? p.lse[sidx] * LOG2E : 0.f;
+        const float delta_r = row < p.Sq ? p.delta[sidx] : 0.f;
+        uint8_t* sDS = smem + SQ_DS + (cg >> 1) * 16384 + row_t * 128;
+        uint32_t ph = 0;
+        for (int j = 0; j < n_kv; j++) {
+            const int k0 = j * BK;
+            const bool need_mask = (k0 + BK - 1 > q0 + off) || (k0 + BK > p.Sk) || (q0 + BQ > p.Sq);
+            mbar_wait(s_full, ph);
+            tc_fence_after();
+            uint32_t rs[32], rd[32];
+            tmem_ld32(tS + lane_addr + cg * 32, rs);
+            tmem_ld32(tdP + lane_addr + cg * 32, rd);
+            tmem_ld_wait();
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+                float dsv[2];
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    float pr = ex2_approx(fmaf(__uint_as_float(rs[i + e]), sl2, -lse_r));
+                    if (need_mask) {
+                        const int key = k0 + cg * 32 + i + e;
+                        if (key > row + off || key >= p.Sk || row >= p.Sq) pr = 0.f;
+                    }
+                    dsv[e] = pr * (__uint_as_float(rd[i + e]) - delta_r);
+                }
+                pk[i >> 1] = pack2(dsv[0], dsv[1]);
+            }
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const int chunk = (cg & 1) * 4 + v;
+                *reinterpret_cast<uint4*>(sDS + ((chunk ^ (row_t & 7)) << 4)) =
+                    make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ds_full);
+            ph ^= 1;
+        }
+        // epilogue: dQ = scale * tdQ (+ RoPE backward on the (d, d+32) pairs); warps 2..9 write, 16+16 columns each
+        mbar_wait(dq_done, 0);
+        tc_fence_after();
+        if (cw < 8) {
+            const int part = (cw >> 2) & 1;
+            float v0[16], v1[16];
+            uint32_t r[16];
+            tmem_ld16(tdQ + lane_addr + part * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; i++) v0[i] = __uint_as_float(r[i]) * p.scale;
+            tmem_ld16(tdQ + lane_addr + 32 + part * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; i++) v1[i] = __uint_as_float(r[i]) * p.scale;
+            if (row < p.Sq) {
+                if (p.rope_cos) {
+                    const bf16* cp = p.rope_cos + (size_t)(row + off) * 32 + part * 16;
+                    const bf16* sp = p.rope_sin + (size_t)(row + off) * 32 + part * 16;
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const float c = __bfloat162float(cp[i]), sn = __bfloat162float(sp[i]);
+                        const float a = v0[i], bb = v1[i];
+                        v0[i] = a * c + bb * sn;
+                        v1[i] = bb * c - a * sn;
+                    }
+                }
+                bf16* d0 = p.dq + b * p.dq_b + (long long)row * p.dq_r + h * D + part * 16;
+                *reinterpret_cast<uint4*>(d0) = pack8(v0);
+                *reinterpret_cast<uint4*>(d0 + 8) = pack8(v0 + 8);
+                *reinterpret_cast<uint4*>(d0 + 32) = pack8(v1);
+                *reinterpret_cast<uint4*>(d0 + 40) = pack8(v1 + 8);
             }
         }
     }
@@ -637,7 +847,6 @@ extern "C" int b200_attn_causal_bwd_tc(const void* q, const void* k, const void*
     const long long W = (long long)n_heads * D;
     float* dq_acc = (float*)workspace;
     float* delta = dq_acc + (size_t)batch * Sq * W;
-    B200_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)batch * Sq * W * sizeof(float), stream), "attn_bwd_tc memset");
     {   // delta = rowsum(dO * O), shared with the mma.sync path
         int rc = b200_attn_bwd_delta_launch(o, d_o, delta, strides + 9, strides + 12, batch, n_heads, Sq, stream);
         if (rc) return rc;
@@ -655,20 +864,40 @@ extern "C" int b200_attn_causal_bwd_tc(const void* q, const void* k, const void*
     p.dqa_b = (long long)Sq * W; p.dqa_r = W;
     p.rope_cos = (const bf16*)rope_cos; p.rope_sin = (const bf16*)rope_sin;
     p.n_heads = n_heads; p.Sq = Sq; p.Sk = Sk; p.scale = scale;
+    static int use_atomics = -1;
+    if (use_atomics < 0) {
+        const char* e = getenv("B200_ATTN_BWD_ATOMIC_DQ");
+        use_atomics = (e && e[0] == '1') ? 1 : 0;
+    }
     static bool configured = false;
     if (!configured) {
-        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
+        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
+        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
+        B200_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ_BYTES), "attn_bwd_dq smem");
         configured = true;
     }
     dim3 grid((Sk + BK - 1) / BK, batch * n_heads);
-    attn_bwd_tc05_kernel<<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, p);
-    B200_CHECK_LAUNCH("attn_causal_bwd_tc");
-    const long long rows = (long long)batch * Sq;
-    long long nthr = rows * (W / 16);
-    int blocks = (int)((nthr + 255) / 256);
-    if (blocks > b200_num_sms() * 16) blocks = b200_num_sms() * 16;
-    attn_bwd_dq_finalize_kernel<<<blocks, 256, 0, stream>>>(dq_acc, (bf16*)dq, rows, (int)W, (int)strides[16], Sq, scale,
-                                                            (const bf16*)rope_cos, (const bf16*)rope_sin);
-    B200_CHECK_LAUNCH("attn_bwd_dq_finalize");
+    if (use_atomics) {
+        B200_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)batch * Sq * W * sizeof(float), stream), "attn_bwd_tc memset");
+        attn_bwd_tc05_kernel<true><<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, p);
+        B200_CHECK_LAUNCH("attn_causal_bwd_tc");
+        const long long rows = (long long)batch * Sq;
+        long long nthr = rows * (W / 16);
+        int blocks = (int)((nthr + 255) / 256);
+        if (blocks > b200_num_sms() * 16) blocks = b200_num_sms() * 16;
+        attn_bwd_dq_finalize_kernel<<<blocks, 256, 0, stream>>>(dq_acc, (bf16*)dq, rows, (int)W, (int)strides[16], Sq, scale,
+                                                                (const bf16*)rope_cos, (const bf16*)rope_sin);
+        B200_CHECK_LAUNCH("attn_bwd_dq_finalize");
+    } else {
+        attn_bwd_tc05_kernel<false><<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, p);
+        B200_CHECK_LAUNCH("attn_causal_bwd_tc_dkv");
+        DqParams dp;
+        dp.lse = lse; dp.delta = delta; dp.dq = (bf16*)dq; dp.dq_b = strides[15]; dp.dq_r = strides[16];
+        dp.rope_cos = (const bf16*)rope_cos; dp.rope_sin = (const bf16*)rope_sin;
+        dp.n_heads = n_heads; dp.Sq = Sq; dp.Sk = Sk; dp.scale = scale;
+        dim3 gq((Sq + BQ - 1) / BQ, batch * n_heads);
+        attn_bwd_dq_tc05_kernel<<<gq, BWD_THREADS, SMEM_DQ_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, dp);
+        B200_CHECK_LAUNCH("attn_causal_bwd_tc_dq");
+    }
     return B200_OK;
 }
