@@ -294,8 +294,9 @@ namespace {
 constexpr int BWD_CWARPS = 16;                   // compute warps: thread = (key row, 32 of the 128 query columns)
 constexpr int BWD_THREADS = 64 + 32 * BWD_CWARPS; // warp 0 TMA, warp 1 MMA, warps 2..17 compute
 constexpr int SB_K = 0, SB_V = 16384;
-constexpr int SB_Q = 32768;                      // 2 stages x (Q 16 KB + dO 16 KB)
-constexpr int SB_P = SB_Q + 2 * 32768;           // P^T : two 64-query atoms of [128 keys x 128 B]
+constexpr int QS = 4;                            // (Q, dO) stages: TMA latency (~2-3 us under load) must span QS-1 iterations
+constexpr int SB_Q = 32768;                      // QS stages x (Q 16 KB + dO 16 KB)
+constexpr int SB_P = SB_Q + QS * 32768;          // P^T : two 64-query atoms of [128 keys x 128 B]
 constexpr int SB_DS = SB_P + 32768;              // dS^T: same layout
 constexpr int SB_LSE = SB_DS + 32768;            // float [2][2][128]: lse, delta per stage parity
 constexpr int SB_BAR = SB_LSE + 2048;
@@ -326,13 +327,13 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SB_BAR);
     uint64_t* kv_full = bars + 0;
-    uint64_t* q_full = bars + 1;      // [2]
-    uint64_t* q_empty = bars + 3;     // [2]
-    uint64_t* s_full = bars + 5;
-    uint64_t* pds_full = bars + 6;
-    uint64_t* dq_full = bars + 7;
-    uint64_t* dq_empty = bars + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    uint64_t* q_full = bars + 1;      // [QS]
+    uint64_t* q_empty = bars + 5;     // [QS]
+    uint64_t* s_full = bars + 9;
+    uint64_t* pds_full = bars + 10;
+    uint64_t* dq_full = bars + 11;
+    uint64_t* dq_empty = bars + 12;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
     float* lse_s = reinterpret_cast<float*>(smem + SB_LSE);          // [2][128]
     float* delta_s = lse_s + 256;                                      // [2][128]
 
@@ -350,7 +351,7 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmdO);
         mbar_init(kv_full, 1);
-        for (int s = 0; s < 2; s++) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
+        for (int s = 0; s < QS; s++) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
         mbar_init(s_full, 1); mbar_init(pds_full, BWD_CWARPS); mbar_init(dq_full, 1); mbar_init(dq_empty, BWD_CWARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -373,7 +374,7 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 mbar_expect_tx(&q_full[stage], 2 * BQ * D * 2);
                 tma_load_3d(sQ, &tmQ, &q_full[stage], h * D, (i0 + it) * BQ, b);
                 tma_load_3d(sQ + 16384, &tmdO, &q_full[stage], h * D, (i0 + it) * BQ, b);
-                if (++stage == 2) { stage = 0; phase ^= 1; }
+                if (++stage == QS) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -423,7 +424,7 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 }
                 umma_commit(dq_full);
                 umma_commit(&q_empty[stage]);
-                if (++stage == 2) { stage = 0; qphase ^= 1; }
+                if (++stage == QS) { stage = 0; qphase ^= 1; }
                 if (it + 1 < n_it) {
                     mbar_wait(&q_full[stage], qphase);
                     issue_s(stage);
@@ -588,8 +589,9 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 // dS = P o (dP - delta) is written row-wise to swizzled shared memory and dQ += dS . K_j accumulates in TMEM.
 // ---------------------------------------------------------------------------------------------
 constexpr int SQ_Q = 0, SQ_DO = 16384;
-constexpr int SQ_KV = 32768;                     // 2 stages x (K 16 KB + V 16 KB)
-constexpr int SQ_DS = SQ_KV + 2 * 32768;         // dS [128 q x 128 keys]: two 64-key atoms
+constexpr int KVS = 4;                           // (K, V) stages
+constexpr int SQ_KV = 32768;                     // KVS stages x (K 16 KB + V 16 KB)
+constexpr int SQ_DS = SQ_KV + KVS * 32768;       // dS [128 q x 128 keys]: two 64-key atoms
 constexpr int SQ_BAR = SQ_DS + 32768;
 constexpr int SMEM_DQ_BYTES = SQ_BAR + 128;
 
@@ -610,12 +612,12 @@ attn_bwd_dq_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SQ_BAR);
     uint64_t* q_full = bars + 0;
-    uint64_t* kv_full = bars + 1;     // [2]
-    uint64_t* kv_empty = bars + 3;    // [2]
-    uint64_t* s_full = bars + 5;
-    uint64_t* ds_full = bars + 6;
-    uint64_t* dq_done = bars + 7;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* kv_full = bars + 1;     // [KVS]
+    uint64_t* kv_empty = bars + 5;    // [KVS]
+    uint64_t* s_full = bars + 9;
+    uint64_t* ds_full = bars + 10;
+    uint64_t* dq_done = bars + 11;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = gridDim.x - 1 - blockIdx.x;       // long tiles first
@@ -629,7 +631,7 @@ attn_bwd_dq_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmdO);
         mbar_init(q_full, 1);
-        for (int s = 0; s < 2; s++) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int s = 0; s < KVS; s++) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
         mbar_init(s_full, 1); mbar_init(ds_full, BWD_CWARPS); mbar_init(dq_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -652,7 +654,7 @@ attn_bwd_dq_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                 mbar_expect_tx(&kv_full[stage], 2 * BK * D * 2);
                 tma_load_3d(sK, &tmK, &kv_full[stage], h * D, j * BK, b);
                 tma_load_3d(sK + 16384, &tmV, &kv_full[stage], h * D, j * BK, b);
-                if (++stage == 2) { stage = 0; phase ^= 1; }
+                if (++stage == KVS) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -684,7 +686,7 @@ attn_bwd_dq_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                     umma_f16(tdQ, make_smem_desc(sDS + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
                              make_smem_desc(sK + kk * 2048, 16384, 1024), id_dq, (j > 0 || kk > 0) ? 1u : 0u);
                 umma_commit(&kv_empty[stage]);
-                if (++stage == 2) { stage = 0; kv_phase ^= 1; }
+                if (++stage == KVS) { stage = 0; kv_phase ^= 1; }
                 if (j + 1 < n_kv) {
                     mbar_wait(&kv_full[stage], kv_phase);
                     issue_s(stage);               // in order behind the dQ MMAs: they have finished reading dS_j by then
