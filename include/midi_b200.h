@@ -112,6 +112,8 @@ int b200_attn_causal_bwd_tc(const void* q, const void* k, const void* v, const v
                             void* dq, void* dk, void* dv, const long long* strides /*8x3: q,k,v,o,do,dq,dk,dv*/, int batch,
                             int n_heads, int Sq, int Sk, int head_dim, float scale, const void* rope_cos /*may be NULL*/,
                             const void* rope_sin, void* workspace, size_t workspace_bytes, cudaStream_t s);
+/*      tuning hook: clock64 trace of CTA (0,0) of the dQ kernel into a device buffer of 128 int64 (NULL = off) */
+void b200_attn_debug_trace(long long* buf);
 /*      inner stack: L <= 8 positions per event, head_dim 256, packed qkv rows [n_events*L, ld_qkv]. */
 int b200_attn_tiny_fwd(const void* qkv, void* out, int n_events, int L, int n_heads, int head_dim, int ld_qkv, int ld_out,
                        float scale, cudaStream_t s);

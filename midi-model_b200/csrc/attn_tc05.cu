@@ -604,6 +604,7 @@ struct DqParams {
     const bf16* rope_sin;
     int n_heads, Sq, Sk;
     float scale;
+    long long* dbg;              // optional clock64 trace of CTA (0,0) (bring-up / tuning only)
 };
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
@@ -627,6 +628,8 @@ attn_bwd_dq_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const int off = p.Sk - p.Sq;
     int n_kv = min((p.Sk + BK - 1) / BK, (q0 + BQ - 1 + off) / BK + 1);
     if (n_kv < 1) n_kv = 1;
+    const bool trace = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+#define TRACE(slot, jj) do { if (trace && (jj) < 16) p.dbg[(jj) * 8 + (slot)] = clock64(); } while (0)
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmdO);
@@ -676,10 +679,12 @@ attn_bwd_dq_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                 umma_commit(s_full);
             };
             mbar_wait(&kv_full[0], 0);
+            TRACE(0, 0);
             issue_s(0);
             for (int j = 0; j < n_kv; j++) {
                 const uint32_t sK = smem_u32(smem + SQ_KV + stage * 32768);
                 mbar_wait(ds_full, ph);           // dS_j in shared memory; S / dP TMEM free again
+                TRACE(1, j);
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < BK / 16; kk++)
@@ -689,7 +694,9 @@ attn_bwd_dq_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                 if (++stage == KVS) { stage = 0; kv_phase ^= 1; }
                 if (j + 1 < n_kv) {
                     mbar_wait(&kv_full[stage], kv_phase);
+                    TRACE(2, j);
                     issue_s(stage);               // in order behind the dQ MMAs: they have finished reading dS_j by then
+                    TRACE(0, j + 1);
                 } else {
                     umma_commit(dq_done);
                 }
@@ -713,11 +720,13 @@ attn_bwd_dq_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             const int k0 = j * BK;
             const bool need_mask = (k0 + BK - 1 > q0 + off) || (k0 + BK > p.Sk) || (q0 + BQ > p.Sq);
             mbar_wait(s_full, ph);
+            if (warp == 2 && lane == 0) TRACE(3, j);
             tc_fence_after();
             uint32_t rs[32], rd[32];
             tmem_ld32(tS + lane_addr + cg * 32, rs);
             tmem_ld32(tdP + lane_addr + cg * 32, rd);
             tmem_ld_wait();
+            if (warp == 2 && lane == 0) TRACE(4, j);
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
@@ -739,10 +748,12 @@ attn_bwd_dq_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                 *reinterpret_cast<uint4*>(sDS + ((chunk ^ (row_t & 7)) << 4)) =
                     make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
             }
+            if (warp == 2 && lane == 0) TRACE(5, j);
             tc_fence_before();
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(ds_full);
+            if (warp == 2 && lane == 0) TRACE(6, j);
             ph ^= 1;
         }
         // epilogue: dQ = scale * tdQ (+ RoPE backward on the (d, d+32) pairs); warps 2..9 write, 16+16 columns each
@@ -786,6 +797,7 @@ attn_bwd_dq_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
+#undef TRACE
 }
 
 // dq[rows, heads*64] (bf16, row pitch ld) = scale * (optional RoPE^T) dq_acc (fp32)
@@ -821,6 +833,10 @@ __global__ void attn_bwd_dq_finalize_kernel(const float* __restrict__ acc, bf16*
 }
 
 }   // namespace
+
+static long long* g_attn_dbg = nullptr;
+// bring-up hook: device buffer of 128 int64 receiving a clock64 trace of CTA (0,0) of the dQ kernel (NULL = off)
+extern "C" void b200_attn_debug_trace(long long* buf) { g_attn_dbg = buf; }
 
 // defined in attn_flash.cu
 int b200_attn_bwd_delta_launch(const void* o, const void* d_o, float* delta, const long long* so, const long long* sdo,
@@ -897,6 +913,7 @@ extern "C" int b200_attn_causal_bwd_tc(const void* q, const void* k, const void*
         dp.lse = lse; dp.delta = delta; dp.dq = (bf16*)dq; dp.dq_b = strides[15]; dp.dq_r = strides[16];
         dp.rope_cos = (const bf16*)rope_cos; dp.rope_sin = (const bf16*)rope_sin;
         dp.n_heads = n_heads; dp.Sq = Sq; dp.Sk = Sk; dp.scale = scale;
+        dp.dbg = g_attn_dbg;
         dim3 gq((Sq + BQ - 1) / BQ, batch * n_heads);
         attn_bwd_dq_tc05_kernel<<<gq, BWD_THREADS, SMEM_DQ_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, dp);
         B200_CHECK_LAUNCH("attn_causal_bwd_tc_dq");
