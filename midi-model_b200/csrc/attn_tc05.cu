@@ -34,6 +34,10 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, ui
         : "memory");
 }
 
+// advance a shared-memory matrix descriptor by `bytes` (start-address field, 16-byte units); smem addresses are
+// < 256 KB so the 14-bit field never overflows
+__device__ __forceinline__ uint64_t desc_adv(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
+
 struct FwdParams {
     bf16* o;
     float* lse;
@@ -102,25 +106,25 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const uint32_t sQ = smem_u32(smem + SM_Q), sP = smem_u32(smem + SM_P);
             mbar_wait(q_full, 0);
             int stage = 0; uint32_t kv_phase = 0, ph = 0;
+            const uint64_t dQ0 = make_smem_desc(sQ, 16, 1024), dP0 = make_smem_desc(sP, 16, 1024);
             auto issue_s = [&](int st) {
-                const uint32_t sK = smem_u32(smem + SM_KV + st * 32768);
+                const uint64_t dK0 = make_smem_desc(smem_u32(smem + SM_KV + st * 32768), 16, 1024);
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < D / 16; k++)
-                    umma_f16(tS, make_smem_desc(sQ + k * 32, 16, 1024), make_smem_desc(sK + k * 32, 16, 1024), idesc_s, k > 0);
+                    umma_f16(tS, desc_adv(dQ0, k * 32), desc_adv(dK0, k * 32), idesc_s, k > 0);
                 umma_commit(s_full);
             };
             mbar_wait(&kv_full[0], 0);
             issue_s(0);
             for (int j = 0; j < n_kv; j++) {
-                const uint32_t sV = smem_u32(smem + SM_KV + stage * 32768 + 16384);
+                const uint64_t dV0 = make_smem_desc(smem_u32(smem + SM_KV + stage * 32768 + 16384), 16384, 1024);
                 mbar_wait(p_full, ph);            // softmax wrote P_j (and has finished reading S_j)
                 mbar_wait(pv_empty, ph ^ 1);      // previous PV tile drained from TMEM
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < BK / 16; kk++)
-                    umma_f16(tPV, make_smem_desc(sP + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                             make_smem_desc(sV + kk * 2048, 16384, 1024), idesc_pv, kk > 0);
+                    umma_f16(tPV, desc_adv(dP0, (kk >> 2) * 16384 + (kk & 3) * 32), desc_adv(dV0, kk * 2048), idesc_pv, kk > 0);
                 umma_commit(pv_full);
                 umma_commit(&kv_empty[stage]);
                 if (++stage == KV_STAGES) { stage = 0; kv_phase ^= 1; }
@@ -386,41 +390,40 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const uint32_t sP = smem_u32(smem + SB_P), sDS = smem_u32(smem + SB_DS);
             mbar_wait(kv_full, 0);
             int stage = 0; uint32_t qphase = 0, ph = 0;
+            const uint64_t dKk = make_smem_desc(sK, 16, 1024), dVk = make_smem_desc(sV, 16, 1024);   // K-major A operands
+            const uint64_t dKmn = make_smem_desc(sK, 16384, 1024);                                 // MN-major B of dQ
+            const uint64_t dPk = make_smem_desc(sP, 16, 1024), dDSk = make_smem_desc(sDS, 16, 1024);
+            const uint64_t dDSmn = make_smem_desc(sDS, 16384, 1024);
             auto issue_s = [&](int st) {
-                const uint32_t sQ = smem_u32(smem + SB_Q + st * 32768), sdO = sQ + 16384;
+                const uint32_t sQ = smem_u32(smem + SB_Q + st * 32768);
+                const uint64_t dQk = make_smem_desc(sQ, 16, 1024), dOk = make_smem_desc(sQ + 16384, 16, 1024);
                 tc_fence_after();
 #pragma unroll
-                for (int k = 0; k < D / 16; k++)
-                    umma_f16(tS, make_smem_desc(sK + k * 32, 16, 1024), make_smem_desc(sQ + k * 32, 16, 1024), id_s, k > 0);
+                for (int k = 0; k < D / 16; k++) umma_f16(tS, desc_adv(dKk, k * 32), desc_adv(dQk, k * 32), id_s, k > 0);
 #pragma unroll
-                for (int k = 0; k < D / 16; k++)
-                    umma_f16(tdP, make_smem_desc(sV + k * 32, 16, 1024), make_smem_desc(sdO + k * 32, 16, 1024), id_s, k > 0);
+                for (int k = 0; k < D / 16; k++) umma_f16(tdP, desc_adv(dVk, k * 32), desc_adv(dOk, k * 32), id_s, k > 0);
                 umma_commit(s_full);
             };
             mbar_wait(&q_full[0], 0);
             issue_s(0);
             for (int it = 0; it < n_it; it++) {
-                const uint32_t sQ = smem_u32(smem + SB_Q + stage * 32768), sdO = sQ + 16384;
+                const uint32_t sQ = smem_u32(smem + SB_Q + stage * 32768);
+                const uint64_t dQmn = make_smem_desc(sQ, 16384, 1024), dOmn = make_smem_desc(sQ + 16384, 16384, 1024);
                 mbar_wait(pds_full, ph);          // P^T, dS^T of this iteration are in shared memory; S^T/dP^T TMEM is free
                 if (WITH_DQ) mbar_wait(dq_empty, ph ^ 1);      // previous dQ tile drained
                 tc_fence_after();
 #pragma unroll
-                for (int kk = 0; kk < BQ / 16; kk++) {
-                    const uint32_t a_off = (kk >> 2) * 16384 + (kk & 3) * 32;
-                    umma_f16(tdV, make_smem_desc(sP + a_off, 16, 1024), make_smem_desc(sdO + kk * 2048, 16384, 1024), id_kv,
+                for (int kk = 0; kk < BQ / 16; kk++)
+                    umma_f16(tdV, desc_adv(dPk, (kk >> 2) * 16384 + (kk & 3) * 32), desc_adv(dOmn, kk * 2048), id_kv,
                              (it > 0 || kk > 0) ? 1u : 0u);
-                }
 #pragma unroll
-                for (int kk = 0; kk < BQ / 16; kk++) {
-                    const uint32_t a_off = (kk >> 2) * 16384 + (kk & 3) * 32;
-                    umma_f16(tdK, make_smem_desc(sDS + a_off, 16, 1024), make_smem_desc(sQ + kk * 2048, 16384, 1024), id_kv,
+                for (int kk = 0; kk < BQ / 16; kk++)
+                    umma_f16(tdK, desc_adv(dDSk, (kk >> 2) * 16384 + (kk & 3) * 32), desc_adv(dQmn, kk * 2048), id_kv,
                              (it > 0 || kk > 0) ? 1u : 0u);
-                }
                 if (WITH_DQ) {
 #pragma unroll
                     for (int kk = 0; kk < BK / 16; kk++)   // K dimension = keys: 16 key rows per step
-                        umma_f16(tdQ, make_smem_desc(sDS + kk * 2048, 16384, 1024), make_smem_desc(sK + kk * 2048, 16384, 1024),
-                                 id_dq, kk > 0);
+                        umma_f16(tdQ, desc_adv(dDSmn, kk * 2048), desc_adv(dKmn, kk * 2048), id_dq, kk > 0);
                 }
                 umma_commit(dq_full);
                 umma_commit(&q_empty[stage]);
@@ -667,29 +670,30 @@ attn_bwd_dq_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             const uint32_t sQ = smem_u32(smem + SQ_Q), sdO = smem_u32(smem + SQ_DO), sDS = smem_u32(smem + SQ_DS);
             mbar_wait(q_full, 0);
             int stage = 0; uint32_t kv_phase = 0, ph = 0;
+            const uint64_t dQk = make_smem_desc(sQ, 16, 1024), dOk = make_smem_desc(sdO, 16, 1024);
+            const uint64_t dDSk = make_smem_desc(sDS, 16, 1024);
             auto issue_s = [&](int st) {
-                const uint32_t sK = smem_u32(smem + SQ_KV + st * 32768), sV = sK + 16384;
+                const uint32_t sK = smem_u32(smem + SQ_KV + st * 32768);
+                const uint64_t dKk = make_smem_desc(sK, 16, 1024), dVk = make_smem_desc(sK + 16384, 16, 1024);
                 tc_fence_after();
 #pragma unroll
-                for (int k = 0; k < D / 16; k++)
-                    umma_f16(tS, make_smem_desc(sQ + k * 32, 16, 1024), make_smem_desc(sK + k * 32, 16, 1024), id_s, k > 0);
+                for (int k = 0; k < D / 16; k++) umma_f16(tS, desc_adv(dQk, k * 32), desc_adv(dKk, k * 32), id_s, k > 0);
 #pragma unroll
-                for (int k = 0; k < D / 16; k++)
-                    umma_f16(tdP, make_smem_desc(sdO + k * 32, 16, 1024), make_smem_desc(sV + k * 32, 16, 1024), id_s, k > 0);
+                for (int k = 0; k < D / 16; k++) umma_f16(tdP, desc_adv(dOk, k * 32), desc_adv(dVk, k * 32), id_s, k > 0);
                 umma_commit(s_full);
             };
             mbar_wait(&kv_full[0], 0);
             TRACE(0, 0);
             issue_s(0);
             for (int j = 0; j < n_kv; j++) {
-                const uint32_t sK = smem_u32(smem + SQ_KV + stage * 32768);
+                const uint64_t dKmn = make_smem_desc(smem_u32(smem + SQ_KV + stage * 32768), 16384, 1024);
                 mbar_wait(ds_full, ph);           // dS_j in shared memory; S / dP TMEM free again
                 TRACE(1, j);
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < BK / 16; kk++)
-                    umma_f16(tdQ, make_smem_desc(sDS + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                             make_smem_desc(sK + kk * 2048, 16384, 1024), id_dq, (j > 0 || kk > 0) ? 1u : 0u);
+                    umma_f16(tdQ, desc_adv(dDSk, (kk >> 2) * 16384 + (kk & 3) * 32), desc_adv(dKmn, kk * 2048), id_dq,
+                             (j > 0 || kk > 0) ? 1u : 0u);
                 umma_commit(&kv_empty[stage]);
                 if (++stage == KVS) { stage = 0; kv_phase ^= 1; }
                 if (j + 1 < n_kv) {
