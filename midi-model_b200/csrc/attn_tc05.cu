@@ -888,8 +888,10 @@ extern "C" int b200_attn_causal_bwd_tc(const void* q, const void* k, const void*
     p.n_heads = n_heads; p.Sq = Sq; p.Sk = Sk; p.scale = scale;
     static int use_atomics = -1;
     if (use_atomics < 0) {
+        // default: dQ accumulated with red.global.add.v4.f32 inside the dK/dV kernel (measured 0.68 ms per layer at
+        // B=8,S=2048 vs 0.73 ms for the atomic-free two-kernel variant, B200_ATTN_BWD_ATOMIC_DQ=0)
         const char* e = getenv("B200_ATTN_BWD_ATOMIC_DQ");
-        use_atomics = (e && e[0] == '1') ? 1 : 0;
+        use_atomics = (e && e[0] == '0') ? 0 : 1;
     }
     static bool configured = false;
     if (!configured) {

@@ -35,6 +35,7 @@ def _check(t: torch.Tensor, name: str):
 
 # ------------------------------------------------------------------ embeddings
 def embed_sum(ids: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+    ids = ids.contiguous()            # the kernel assumes row pitch T (a [:, p:p+1] slice reshaped to 2-D is NOT)
     M, T = ids.shape
     V, H = table.shape
     out = torch.empty((M, H), dtype=BF16, device=table.device)
@@ -44,6 +45,10 @@ def embed_sum(ids: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
 
 def inner_input(hidden: Optional[torch.Tensor], ids: Optional[torch.Tensor], table: torch.Tensor) -> torch.Tensor:
     V, H = table.shape
+    if ids is not None:
+        ids = ids.contiguous()
+    if hidden is not None:
+        hidden = hidden.contiguous()
     n_events = hidden.shape[0] if hidden is not None else ids.shape[0]
     n_ids = 0 if ids is None else ids.shape[1]
     Tin = n_ids + (1 if hidden is not None else 0)
