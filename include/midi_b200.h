@@ -139,6 +139,11 @@ int b200_adamw_step(void* params, const void* grads, float* exp_avg, float* exp_
 /* ---- generate() loop (midi_model.py:167-250) ------------------------------------------------------ */
 int b200_gemv_bf16(const void* x, const void* W, const void* res /*may be NULL*/, void* y, int B, int N, int K, int ldx,
                    int ldw, int ldr, int ldy, cudaStream_t s);
+/*      fused decode-step projection: y = [swiglu]([rmsnorm_w](x or table[ids]) . W^T) [+ res]; N_out = rows of W
+ *      (half of them when swiglu: W = [gate | up]) */
+int b200_gemv_fused(const void* x /*or NULL*/, const long long* ids /*or NULL*/, int ids_stride, const void* table, int V,
+                    const void* norm_w /*may be NULL*/, float eps, const void* W, const void* res /*may be NULL*/, void* y,
+                    int B, int N_out, int K, int ldx, int ldw, int ldr, int ldy, int swiglu, cudaStream_t s);
 /*      paged KV cache replacing DynamicCache.update's torch.cat (hf cache_utils.py:102-121):
  *      pools [n_pages][n_heads][page][head_dim], block_table [batch][max_pages] */
 int b200_kv_append(const void* qkv, void* k_pool, void* v_pool, const int* block_table, int max_pages, int page,
@@ -147,6 +152,11 @@ size_t b200_attn_decode_workspace_bytes(int rows, int n_heads, int head_dim, int
 int b200_attn_decode(const void* q, const void* k_pool, const void* v_pool, const int* block_table, int max_pages, int page,
                      void* out, int batch, int s_q, int n_heads, int head_dim, int past, const int* past_dev, int max_T,
                      int ldq, int ldo, float scale, int n_split, void* workspace, size_t workspace_bytes, cudaStream_t s);
+/*      one new token per row: RoPE(q, k) + KV append + attention over positions 0..pos0(+*pos_dev) in one launch */
+int b200_attn_decode_fused(const void* qkv, void* k_pool, void* v_pool, const int* block_table, int max_pages, int page,
+                           const void* cos_t, const void* sin_t, void* out, int batch, int n_heads, int head_dim, int pos0,
+                           const int* pos_dev, int max_T, int ldq, int ldo, float scale, int n_split, void* workspace,
+                           size_t workspace_bytes, cudaStream_t s);
 /*      sampler: MIDIModel.sample_top_p_k (midi_model.py:152-165) on given probabilities ...            */
 int b200_sample_topp_topk(const void* probs, int is_bf16, int rows, int V, int ld, float top_p, int top_k,
                           const float* uniforms, long long* out, cudaStream_t s);

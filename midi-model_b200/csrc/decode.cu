@@ -57,6 +57,96 @@ gemv_kernel(const bf16* __restrict__ x, const bf16* __restrict__ W, const bf16* 
     }
 }
 
+// Fused decode-step projection: y = [swiglu]( [rmsnorm_w](x) . W^T ) [+ res]
+//   * x rows come from `x` or are gathered from an embedding table (`ids` != NULL: row b = table[ids[b * ids_stride]],
+//     midi_model.py:128 -- the token-level stack's input at steps 1..7)
+//   * norm_w != NULL : RMSNorm (hf :62-67, two roundings) applied while staging x in shared memory
+//   * swiglu != 0    : W = [gate | up] rows, output n = bf16(bf16(silu(g_n)) * u_n) with g, u = bf16(acc)  (hf :183)
+// Same rounding points as the stand-alone kernels, so fused and unfused decode are bit-identical.
+template <int B>
+__global__ void __launch_bounds__(GV_WARPS * 32)
+gemv_fused_kernel(const bf16* __restrict__ x, const long long* __restrict__ ids, int ids_stride, const bf16* __restrict__ table,
+                  const bf16* __restrict__ norm_w, float eps, const bf16* __restrict__ W, const bf16* __restrict__ res,
+                  bf16* __restrict__ y, int N_out, int K, int ldx, int ldw, int ldr, int ldy, int swiglu, int V) {
+    extern __shared__ __align__(16) uint8_t gv_smem[];
+    bf16* xs = reinterpret_cast<bf16*>(gv_smem);   // [B][K]
+    const int nvec = K / 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int b = warp; b < B; b += GV_WARPS) {     // one warp stages (and normalises) one row
+        const bf16* src;
+        if (ids) {
+            long long id = ids[(size_t)b * ids_stride];
+            if (id < 0 || id >= V) id = 0;
+            src = table + (size_t)id * K;
+        } else {
+            src = x + (size_t)b * ldx;
+        }
+        if (norm_w) {
+            float ss = 0.f;
+            for (int v = lane; v < nvec; v += 32) {
+                float f[8];
+                unpack8(*reinterpret_cast<const uint4*>(src + v * 8), f);
+#pragma unroll
+                for (int j = 0; j < 8; j++) ss = fmaf(f[j], f[j], ss);
+            }
+            ss = warp_sum(ss);
+            const float rstd = rsqrtf(ss / (float)K + eps);
+            for (int v = lane; v < nvec; v += 32) {
+                float f[8], wv[8];
+                unpack8(*reinterpret_cast<const uint4*>(src + v * 8), f);
+                unpack8(*reinterpret_cast<const uint4*>(norm_w + v * 8), wv);
+#pragma unroll
+                for (int j = 0; j < 8; j++) f[j] = wv[j] * bf16_round(f[j] * rstd);
+                *reinterpret_cast<uint4*>(xs + b * K + v * 8) = pack8(f);
+            }
+        } else {
+            for (int v = lane; v < nvec; v += 32)
+                *reinterpret_cast<uint4*>(xs + b * K + v * 8) = *reinterpret_cast<const uint4*>(src + v * 8);
+        }
+    }
+    __syncthreads();
+    for (int n = blockIdx.x * GV_WARPS + warp; n < N_out; n += gridDim.x * GV_WARPS) {
+        float acc[B], acc2[B];
+#pragma unroll
+        for (int b = 0; b < B; b++) { acc[b] = 0.f; acc2[b] = 0.f; }
+        const bf16* wrow = W + (size_t)n * ldw;
+        const bf16* wrow2 = W + (size_t)(n + N_out) * ldw;     // "up" row when swiglu
+        for (int v = lane; v < nvec; v += 32) {
+            float wf[8], wf2[8];
+            unpack8(ld_nc16(wrow + v * 8), wf);
+            if (swiglu) unpack8(ld_nc16(wrow2 + v * 8), wf2);
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                float xf[8];
+                unpack8(*reinterpret_cast<const uint4*>(xs + b * K + v * 8), xf);
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[b] = fmaf(wf[j], xf[j], acc[b]);
+                if (swiglu) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) acc2[b] = fmaf(wf2[j], xf[j], acc2[b]);
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            acc[b] = warp_sum(acc[b]);
+            if (swiglu) acc2[b] = warp_sum(acc2[b]);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                float o = acc[b];
+                if (swiglu) {
+                    const float g = bf16_round(o), u = bf16_round(acc2[b]);
+                    o = bf16_round(g / (1.f + __expf(-g))) * u;
+                }
+                if (res) o = bf16_round(o) + __bfloat162float(res[(size_t)b * ldr + n]);
+                y[(size_t)b * ldy + n] = __float2bfloat16_rn(o);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // paged KV cache
 // ---------------------------------------------------------------------------------------------
@@ -168,6 +258,124 @@ decode_attn_kernel(const bf16* __restrict__ q, KVLayout L, float* __restrict__ p
         for (int j = 0; j < DPT; j++) pout[2 + d0 + j] = acc[j];
     }
     if (threadIdx.x == 0) { pout[0] = mx; pout[1] = sum; }
+}
+
+// Fused single-token attention step: RoPE on the new q and k (hf :146-168, same three roundings as rope_kernel), append
+// k / v to the paged cache (hf cache_utils.py:119-120) and attend over positions 0 .. pos -- one launch instead of
+// rope + kv_append + attention (+ combine when n_split == 1).  qkv: [batch, 3*H] pre-RoPE rows of the new token.
+template <int D>
+__global__ void __launch_bounds__(128)
+decode_attn_fused_kernel(const bf16* __restrict__ qkv, KVLayout L, const bf16* __restrict__ cos_t, const bf16* __restrict__ sin_t,
+                         float* __restrict__ partial, bf16* __restrict__ out, int pos0, const int* pos_dev, int ldq, int ldo,
+                         float scale, int n_split) {
+    constexpr int CHUNK_MAX = 1024;
+    __shared__ float s_sc[CHUNK_MAX];
+    __shared__ __align__(16) bf16 s_q[D];
+    __shared__ __align__(16) bf16 s_k[D];
+    __shared__ __align__(16) bf16 s_v[D];
+    __shared__ float s_red[8];
+    __shared__ float s_out[2][D];
+    const int rh = blockIdx.x;
+    const int b = rh / L.n_heads, h = rh % L.n_heads;
+    const int pos = (pos_dev ? *pos_dev : 0) + pos0;     // position of the new token
+    const int T = pos + 1;
+    const int chunk = (T + n_split - 1) / n_split;
+    const int t0 = blockIdx.y * chunk;
+    const int t1 = min(T, t0 + chunk);
+    const int H = L.n_heads * D;
+    const bf16* row = qkv + (size_t)b * ldq;
+    const bool owns_new = (t0 <= pos && pos < t1);
+    // RoPE(q) -> s_q ; the CTA whose chunk holds the new position also forms RoPE(k), v and appends them to the cache
+    for (int i = threadIdx.x; i < D / 2; i += blockDim.x) {
+        const float c = __bfloat162float(cos_t[(size_t)pos * (D / 2) + i]), sn = __bfloat162float(sin_t[(size_t)pos * (D / 2) + i]);
+        {
+            const float x1 = __bfloat162float(row[h * D + i]), x2 = __bfloat162float(row[h * D + i + D / 2]);
+            s_q[i] = __float2bfloat16_rn(bf16_round(x1 * c) + bf16_round(-x2 * sn));
+            s_q[i + D / 2] = __float2bfloat16_rn(bf16_round(x2 * c) + bf16_round(x1 * sn));
+        }
+        if (owns_new) {
+            const float x1 = __bfloat162float(row[H + h * D + i]), x2 = __bfloat162float(row[H + h * D + i + D / 2]);
+            s_k[i] = __float2bfloat16_rn(bf16_round(x1 * c) + bf16_round(-x2 * sn));
+            s_k[i + D / 2] = __float2bfloat16_rn(bf16_round(x2 * c) + bf16_round(x1 * sn));
+            s_v[i] = row[2 * H + h * D + i];
+            s_v[i + D / 2] = row[2 * H + h * D + i + D / 2];
+        }
+    }
+    __syncthreads();
+    if (owns_new) {
+        const size_t o = kv_off(L, b, h, pos);
+        for (int i = threadIdx.x; i < D / 8; i += blockDim.x) {
+            *reinterpret_cast<uint4*>(L.k_pool + o + i * 8) = *reinterpret_cast<const uint4*>(s_k + i * 8);
+            *reinterpret_cast<uint4*>(L.v_pool + o + i * 8) = *reinterpret_cast<const uint4*>(s_v + i * 8);
+        }
+    }
+    float* pout = partial + ((size_t)rh * n_split + blockIdx.y) * (D + 2);
+    if (t0 >= t1) {
+        if (threadIdx.x == 0) { pout[0] = -INFINITY; pout[1] = 0.f; }
+        for (int d = threadIdx.x; d < D; d += blockDim.x) pout[2 + d] = 0.f;
+        return;
+    }
+    float mx = -INFINITY;
+    for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
+        const bf16* kp = (t == pos) ? s_k : L.k_pool + kv_off(L, b, h, t);
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d < D / 8; d++) {
+            float kf[8], qf[8];
+            unpack8(*reinterpret_cast<const uint4*>(kp + d * 8), kf);
+            unpack8(*reinterpret_cast<const uint4*>(s_q + d * 8), qf);
+#pragma unroll
+            for (int j = 0; j < 8; j++) s = fmaf(kf[j], qf[j], s);
+        }
+        s *= scale;
+        s_sc[t - t0] = s;
+        mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+    float sum = 0.f;
+    for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
+        const float p = __expf(s_sc[t - t0] - mx);
+        sum += p;
+        s_sc[t - t0] = bf16_round(p);
+    }
+    sum = warp_sum(sum);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[4 + (threadIdx.x >> 5)] = sum;
+    __syncthreads();
+    sum = s_red[4] + s_red[5] + s_red[6] + s_red[7];
+    constexpr int GROUPS = (D >= 128) ? 1 : 128 / D;
+    constexpr int DPT = (D >= 128) ? D / 128 : 1;
+    const int grp = (D >= 128) ? 0 : threadIdx.x / D;
+    const int d0 = (D >= 128) ? threadIdx.x * DPT : threadIdx.x % D;
+    float acc[DPT];
+#pragma unroll
+    for (int j = 0; j < DPT; j++) acc[j] = 0.f;
+    for (int t = t0 + grp; t < t1; t += GROUPS) {
+        const bf16* vp = (t == pos) ? s_v : L.v_pool + kv_off(L, b, h, t);
+        const float p = s_sc[t - t0];
+#pragma unroll
+        for (int j = 0; j < DPT; j++) acc[j] = fmaf(p, __bfloat162float(vp[d0 + j]), acc[j]);
+    }
+    if (GROUPS == 2) {
+        s_out[grp][d0] = acc[0];
+        __syncthreads();
+        acc[0] = s_out[0][d0] + s_out[1][d0];
+    }
+    if (n_split == 1) {        // whole context in this CTA: normalise and write the attention output directly
+        if (grp == 0) {
+#pragma unroll
+            for (int j = 0; j < DPT; j++) out[(size_t)b * ldo + h * D + d0 + j] = __float2bfloat16_rn(acc[j] / sum);
+        }
+    } else {
+        if (grp == 0) {
+#pragma unroll
+            for (int j = 0; j < DPT; j++) pout[2 + d0 + j] = acc[j];
+        }
+        if (threadIdx.x == 0) { pout[0] = mx; pout[1] = sum; }
+    }
 }
 
 template <int D>
@@ -455,6 +663,85 @@ extern "C" int b200_gemv_bf16(const void* x, const void* W, const void* res, voi
     }
 #undef B200_GEMV
     B200_CHECK_LAUNCH("gemv");
+    return B200_OK;
+}
+
+extern "C" size_t b200_attn_decode_workspace_bytes(int rows, int n_heads, int head_dim, int n_split);
+
+extern "C" int b200_gemv_fused(const void* x, const long long* ids, int ids_stride, const void* table, int V,
+                               const void* norm_w, float eps, const void* W, const void* res, void* y, int B, int N_out, int K,
+                               int ldx, int ldw, int ldr, int ldy, int swiglu, cudaStream_t stream) {
+    B200_CHECK_ARG(B >= 1 && B <= 16, "gemv_fused: batch %d outside 1..16", B);
+    B200_CHECK_ARG(K % 8 == 0 && ldw % 8 == 0 && (ids || ldx % 8 == 0), "gemv_fused: K, ldx, ldw must be multiples of 8");
+    B200_CHECK_ARG(x != nullptr || ids != nullptr, "gemv_fused: x or ids required");
+    const size_t smem = (size_t)B * K * 2;
+    B200_CHECK_ARG(smem <= 200 * 1024, "gemv_fused: B*K too large for shared memory");
+    int grid = (N_out + GV_WARPS - 1) / GV_WARPS;
+    const int cap = b200_num_sms() * 4;
+    if (grid > cap) grid = cap;
+#define B200_GEMVF(BB)                                                                                                  \
+    do {                                                                                                                \
+        static bool configured = false;                                                                                 \
+        if (!configured) {                                                                                              \
+            B200_CUDA(cudaFuncSetAttribute(gemv_fused_kernel<BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), \
+                      "gemv_fused smem attr");                                                                          \
+            configured = true;                                                                                          \
+        }                                                                                                               \
+        gemv_fused_kernel<BB><<<grid, GV_WARPS * 32, smem, stream>>>((const bf16*)x, ids, ids_stride, (const bf16*)table, \
+            (const bf16*)norm_w, eps, (const bf16*)W, (const bf16*)res, (bf16*)y, N_out, K, ldx, ldw, ldr, ldy, swiglu, V); \
+    } while (0)
+    switch (B) {
+        case 1: B200_GEMVF(1); break;
+        case 2: B200_GEMVF(2); break;
+        case 3: B200_GEMVF(3); break;
+        case 4: B200_GEMVF(4); break;
+        case 5: B200_GEMVF(5); break;
+        case 6: B200_GEMVF(6); break;
+        case 7: B200_GEMVF(7); break;
+        case 8: B200_GEMVF(8); break;
+        case 9: B200_GEMVF(9); break;
+        case 10: B200_GEMVF(10); break;
+        case 11: B200_GEMVF(11); break;
+        case 12: B200_GEMVF(12); break;
+        case 13: B200_GEMVF(13); break;
+        case 14: B200_GEMVF(14); break;
+        case 15: B200_GEMVF(15); break;
+        default: B200_GEMVF(16); break;
+    }
+#undef B200_GEMVF
+    B200_CHECK_LAUNCH("gemv_fused");
+    return B200_OK;
+}
+
+// one new token per batch row: RoPE(q,k) + KV append + attention over the cache (+ combine pass when n_split > 1)
+extern "C" int b200_attn_decode_fused(const void* qkv, void* k_pool, void* v_pool, const int* block_table, int max_pages,
+                                      int page, const void* cos_t, const void* sin_t, void* out, int batch, int n_heads,
+                                      int head_dim, int pos0, const int* pos_dev, int max_T, int ldq, int ldo, float scale,
+                                      int n_split, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    B200_CHECK_ARG(head_dim == 64 || head_dim == 256, "attn_decode_fused: head_dim %d unsupported", head_dim);
+    if (batch == 0) return B200_OK;
+    if (n_split < 1) n_split = 1;
+    B200_CHECK_ARG((max_T + n_split - 1) / n_split <= 1024, "attn_decode_fused: chunk per split exceeds 1024 keys");
+    B200_CHECK_ARG(workspace_bytes >= b200_attn_decode_workspace_bytes(batch, n_heads, head_dim, n_split),
+                   "attn_decode_fused: workspace too small");
+    KVLayout L{(bf16*)k_pool, (bf16*)v_pool, block_table, max_pages, page, n_heads, head_dim};
+    dim3 grid(batch * n_heads, n_split);
+    if (head_dim == 64) {
+        decode_attn_fused_kernel<64><<<grid, 128, 0, stream>>>((const bf16*)qkv, L, (const bf16*)cos_t, (const bf16*)sin_t,
+            (float*)workspace, (bf16*)out, pos0, pos_dev, ldq, ldo, scale, n_split);
+        if (n_split > 1) {
+            decode_attn_combine_kernel<64><<<batch * n_heads, 64, 0, stream>>>((const float*)workspace, (bf16*)out, n_heads, n_split, ldo);
+            B200_COUNT_EXTRA(1);
+        }
+    } else {
+        decode_attn_fused_kernel<256><<<grid, 128, 0, stream>>>((const bf16*)qkv, L, (const bf16*)cos_t, (const bf16*)sin_t,
+            (float*)workspace, (bf16*)out, pos0, pos_dev, ldq, ldo, scale, n_split);
+        if (n_split > 1) {
+            decode_attn_combine_kernel<256><<<batch * n_heads, 128, 0, stream>>>((const float*)workspace, (bf16*)out, n_heads, n_split, ldo);
+            B200_COUNT_EXTRA(1);
+        }
+    }
+    B200_CHECK_LAUNCH("attn_decode_fused");
     return B200_OK;
 }
 

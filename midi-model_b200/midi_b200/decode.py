@@ -64,6 +64,21 @@ def _lm_head(x: torch.Tensor, w: torch.Tensor, pitch: int) -> torch.Tensor:
     return y
 
 
+def _gemv_fused(x, w, n_out, *, ids=None, table=None, norm_w=None, eps=0.0, residual=None, swiglu=False, ldy=None):
+    """y[B, n_out] = [swiglu]([rmsnorm](x or table[ids]) @ w.T) [+ residual]   (B <= 16 rows, one launch)."""
+    B = x.shape[0] if x is not None else ids.shape[0]
+    K = w.shape[1]
+    y = torch.empty((B, ldy or n_out), dtype=BF16, device=w.device)
+    lib.call("b200_gemv_fused", lib.ptr(x), lib.ptr(ids), ids.stride(0) if ids is not None else 0, lib.ptr(table),
+             table.shape[0] if table is not None else 0, lib.ptr(norm_w), float(eps), w.data_ptr(), lib.ptr(residual),
+             y.data_ptr(), B, n_out, K, x.stride(0) if x is not None else 0, w.stride(0),
+             residual.stride(0) if residual is not None else 0, y.stride(0), int(swiglu), lib.stream())
+    return y
+
+
+FUSED_DECODE = __import__("os").environ.get("B200_FUSED_DECODE", "1") != "0"
+
+
 class CachedStack:
     """Incremental forward of one stack over a PagedKV (inference only)."""
 
@@ -73,7 +88,7 @@ class CachedStack:
         self.max_pos = max_pos
 
     def step(self, x: torch.Tensor, kv: PagedKV, s_new: int, pos_dev: Optional[torch.Tensor] = None,
-             max_T: Optional[int] = None) -> torch.Tensor:
+             max_T: Optional[int] = None, final_norm: bool = True) -> torch.Tensor:
         """x: [batch * s_new, H] new inputs_embeds; appends to kv; returns final-normed hidden for the new rows.
         With `pos_dev` (int32[1] on the device) the number of cached positions is read by the kernels themselves
         (CUDA-graph replay); `max_T` then bounds the context for the split-T decode attention."""
@@ -118,6 +133,32 @@ class CachedStack:
             x = _linear(act, w.down, residual=h)
         if not dev_pos:
             kv.length = T
+        return ops.rmsnorm(x, self.eng.norm, c.eps)
+
+
+    def _step_fused(self, x, kv, past, pos_dev, T, n_split, ws_bytes, final_norm=True):
+        """Single-token step with 5 launches per layer: norm+QKV, RoPE+append+attention, o_proj+residual,
+        norm+gate/up+SwiGLU, down+residual.  Same rounding points as the unfused kernels (bit-identical)."""
+        c = self.eng.cfg
+        H, D, nh = c.hidden, c.head_dim, c.n_head
+        B = kv.batch
+        scale = 1.0 / math.sqrt(D)
+        pd = lib.ptr(pos_dev)
+        ws = ops._ws("attn_decode", ws_bytes, kv.block_table.device)
+        for li, w in enumerate(self.eng.layers):
+            qkv = _gemv_fused(x, w.qkv, 3 * H, norm_w=w.ln1, eps=c.eps)
+            attn = torch.empty((B, H), dtype=BF16, device=qkv.device)
+            lib.call("b200_attn_decode_fused", qkv.data_ptr(), kv.k[li].data_ptr(), kv.v[li].data_ptr(),
+                     kv.block_table.data_ptr(), kv.max_pages, kv.page, self.cos.data_ptr(), self.sin.data_ptr(),
+                     attn.data_ptr(), B, nh, D, past, pd, T, qkv.stride(0), H, scale, n_split, ws.data_ptr(), ws.numel(),
+                     lib.stream())
+            h = _gemv_fused(attn, w.o, H, residual=x)
+            act = _gemv_fused(h, w.gu, c.inner, norm_w=w.ln2, eps=c.eps, swiglu=True)
+            x = _gemv_fused(act, w.down, H, residual=h)
+        if pos_dev is None:
+            kv.length = T
+        if not final_norm:
+            return x                                  # caller fuses the final norm into the next projection (lm_head)
         return ops.rmsnorm(x, self.eng.norm, c.eps)
 
 
@@ -193,8 +234,13 @@ class GraphGenerator:
                 xin = ops.inner_input(hidden, None, emb_i)
             else:
                 xin = ops.inner_input(None, self.ev_t[i - 1].view(B, 1), emb_i)
-            hs = self.inner.step(xin, self.kv2, 1)
-            logits = _lm_head(hs, self.lm_head, self.pitch)
+            if FUSED_DECODE and B <= 16:
+                hs = self.inner.step(xin, self.kv2, 1, final_norm=False)      # final norm fused into the lm_head GEMV
+                logits = _gemv_fused(hs, self.lm_head, self.V, norm_w=self.inner.eng.norm, eps=self.inner.eng.cfg.eps,
+                                     ldy=self.pitch)
+            else:
+                hs = self.inner.step(xin, self.kv2, 1)
+                logits = _lm_head(hs, self.lm_head, self.pitch)
             lib.call("b200_uniform_fill", self.u.data_ptr(), B, 0, self.counter.data_ptr(), lib.stream())
             lib.call("b200_sample_from_logits", logits.data_ptr(), B, self.V, logits.stride(0), self.temp, self.top_p,
                      self.top_k, i, self.ev_t.data_ptr(), self.g.lut.data_ptr(), self.g.n_event_types, self.g.eos, self.g.pad,

@@ -55,6 +55,8 @@ SIGNATURES = {
     "b200_grad_clip_coef": (i32, [vp, i64, f32, vp, vp, sz, vp]),
     "b200_adamw_step": (i32, [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, vp, vp]),
     "b200_gemv_bf16": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "b200_gemv_fused": (i32, [vp, vp, i32, vp, i32, vp, f32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "b200_attn_decode_fused": (i32, [vp, vp, vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, i32, vp, i32, i32, i32, f32, i32, vp, sz, vp]),
     "b200_kv_append": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
     "b200_attn_decode_workspace_bytes": (sz, [i32, i32, i32, i32]),
     "b200_attn_decode": (i32, [vp, vp, vp, vp, i32, i32, vp, i32, i32, i32, i32, i32, vp, i32, i32, i32, f32, i32, vp, sz, vp]),

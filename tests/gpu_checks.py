@@ -608,6 +608,19 @@ def check_model_generate():
         for t in range(23, 40):
             parts.append(model.forward(batch[:, t:t + 1], cache=c))
     out["cached_vs_full_hidden"] = rel(torch.cat(parts, 1).float(), full.float())
+    # fused single-token decode step (norm+QKV, RoPE+append+attention, ..., 5 launches/layer) == unfused kernels, bit for bit
+    from midi_b200 import decode as dec
+    outs = {}
+    for fused in (True, False):
+        dec.FUSED_DECODE = fused
+        with torch.no_grad():
+            c = DynamicCache()
+            hs = [model.forward(batch[:, :17], cache=c)]
+            for t in range(17, 30):
+                hs.append(model.forward(batch[:, t:t + 1], cache=c))
+        outs[fused] = torch.cat(hs, 1)
+    dec.FUSED_DECODE = True
+    out["fused_decode_mismatch"] = float((outs[True] != outs[False]).sum())
     # inner cached path vs uncached logits
     with torch.no_grad():
         hid = full[:, -1]
@@ -765,7 +778,7 @@ THRESH = [
     ("cached_vs_full_hidden", 3e-2), ("inner_cached_vs_full_logits", 3e-2), ("min:greedy_token_agree", 0.6),
     ("peaked_greedy_mismatch", 0.0), ("peaked_eager_vs_graph_mismatch", 0.0), ("peaked_invalid_events", 0.0), ("peaked_loss_last", 1.5),
     ("peaked_argmax_mismatch_vs_fp32", 0.0), ("peaked_logits_vs_fp32", 3e-2),
-    ("sampled_invalid_events", 0.0), ("greedy_graph_vs_nograph_mismatch", 0.0),
+    ("sampled_invalid_events", 0.0), ("greedy_graph_vs_nograph_mismatch", 0.0), ("fused_decode_mismatch", 0.0),
 ]
 
 
