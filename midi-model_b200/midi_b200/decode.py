@@ -104,6 +104,10 @@ class CachedStack:
         n_split = max(1, min(32, (T + 255) // 256)) if D == 64 else 1
         pd = lib.ptr(pos_dev)
         ws_bytes = lib.query("b200_attn_decode_workspace_bytes", B * s_new, nh, D, n_split)
+        if FUSED_DECODE and s_new == 1 and B <= 16:
+            return self._step_fused(x, kv, past, pos_dev, T, n_split, ws_bytes, final_norm)
+        if not final_norm:
+            raise lib.B200Error("final_norm=False is only available on the fused single-token path")
         for li, w in enumerate(self.eng.layers):
             n1 = ops.rmsnorm(x, w.ln1, c.eps)
             qkv = _linear(n1, w.qkv)

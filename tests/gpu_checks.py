@@ -621,6 +621,12 @@ def check_model_generate():
         outs[fused] = torch.cat(hs, 1)
     dec.FUSED_DECODE = True
     out["fused_decode_mismatch"] = float((outs[True] != outs[False]).sum())
+    # final norm fused into the lm_head GEMV == rmsnorm kernel + GEMV
+    rt = model._rt()
+    xpre = randn(4, 1024, seed=9)
+    a = dec._gemv_fused(xpre, rt.lm_head, rt.V, norm_w=rt.inner.norm, eps=1e-6, ldy=rt.pitch)[:, :rt.V]
+    bref = dec._lm_head(ops.rmsnorm(xpre, rt.inner.norm, 1e-6), rt.lm_head, rt.pitch)[:, :rt.V]
+    out["fused_lm_head_mismatch"] = float((a != bref).sum())
     # inner cached path vs uncached logits
     with torch.no_grad():
         hid = full[:, -1]
@@ -778,7 +784,7 @@ THRESH = [
     ("cached_vs_full_hidden", 3e-2), ("inner_cached_vs_full_logits", 3e-2), ("min:greedy_token_agree", 0.6),
     ("peaked_greedy_mismatch", 0.0), ("peaked_eager_vs_graph_mismatch", 0.0), ("peaked_invalid_events", 0.0), ("peaked_loss_last", 1.5),
     ("peaked_argmax_mismatch_vs_fp32", 0.0), ("peaked_logits_vs_fp32", 3e-2),
-    ("sampled_invalid_events", 0.0), ("greedy_graph_vs_nograph_mismatch", 0.0), ("fused_decode_mismatch", 0.0),
+    ("sampled_invalid_events", 0.0), ("greedy_graph_vs_nograph_mismatch", 0.0), ("fused_decode_mismatch", 0.0), ("fused_lm_head_mismatch", 0.0),
 ]
 
 
