@@ -72,6 +72,21 @@ gemv_fused_kernel(const bf16* __restrict__ x, const long long* __restrict__ ids,
     bf16* xs = reinterpret_cast<bf16*>(gv_smem);   // [B][K]
     const int nvec = K / 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // prefetch this warp's first weight row (up to 4 vectors per lane) BEFORE staging x: the DRAM latency of the weights
+    // then overlaps the x load / RMSNorm prologue instead of following it
+    constexpr int PF = 4;
+    uint4 wpre[PF] = {}, wpre2[PF] = {};
+    const int n_first = blockIdx.x * GV_WARPS + warp;
+    if (n_first < N_out) {
+#pragma unroll
+        for (int i = 0; i < PF; i++) {
+            const int v = lane + i * 32;
+            if (v < nvec) {
+                wpre[i] = ld_nc16(W + (size_t)n_first * ldw + v * 8);
+                if (swiglu) wpre2[i] = ld_nc16(W + (size_t)(n_first + N_out) * ldw + v * 8);
+            }
+        }
+    }
     for (int b = warp; b < B; b += GV_WARPS) {     // one warp stages (and normalises) one row
         const bf16* src;
         if (ids) {
@@ -111,10 +126,11 @@ gemv_fused_kernel(const bf16* __restrict__ x, const long long* __restrict__ ids,
         for (int b = 0; b < B; b++) { acc[b] = 0.f; acc2[b] = 0.f; }
         const bf16* wrow = W + (size_t)n * ldw;
         const bf16* wrow2 = W + (size_t)(n + N_out) * ldw;     // "up" row when swiglu
-        for (int v = lane; v < nvec; v += 32) {
+        const bool first = (n == n_first);
+        auto accumulate = [&](const uint4& w1, const uint4& w2, int v) {
             float wf[8], wf2[8];
-            unpack8(ld_nc16(wrow + v * 8), wf);
-            if (swiglu) unpack8(ld_nc16(wrow2 + v * 8), wf2);
+            unpack8(w1, wf);
+            if (swiglu) unpack8(w2, wf2);
 #pragma unroll
             for (int b = 0; b < B; b++) {
                 float xf[8];
@@ -126,6 +142,24 @@ gemv_fused_kernel(const bf16* __restrict__ x, const long long* __restrict__ ids,
                     for (int j = 0; j < 8; j++) acc2[b] = fmaf(wf2[j], xf[j], acc2[b]);
                 }
             }
+        };
+#pragma unroll
+        for (int i = 0; i < PF; i++) {               // vectors covered by the prefetch registers (static indexing)
+            const int v = lane + i * 32;
+            if (v < nvec) {
+                uint4 w1 = wpre[i], w2 = wpre2[i];
+                if (!first) {
+                    w1 = ld_nc16(wrow + v * 8);
+                    if (swiglu) w2 = ld_nc16(wrow2 + v * 8);
+                }
+                accumulate(w1, w2, v);
+            }
+        }
+        for (int v = lane + PF * 32; v < nvec; v += 32) {
+            const uint4 w1 = ld_nc16(wrow + v * 8);
+            uint4 w2 = w1;
+            if (swiglu) w2 = ld_nc16(wrow2 + v * 8);
+            accumulate(w1, w2, v);
         }
 #pragma unroll
         for (int b = 0; b < B; b++) {
@@ -378,6 +412,75 @@ decode_attn_fused_kernel(const bf16* __restrict__ qkv, KVLayout L, const bf16* _
     }
 }
 
+// Token-level stack variant (context <= 32 positions): one WARP per (batch row, head); each lane owns D/32 consecutive
+// elements of q / k / v, scores are warp reductions, softmax lives in registers.  Same math and rounding points as
+// decode_attn_fused_kernel (RoPE three roundings, P rounded to bf16 before P.V).
+template <int D>
+__global__ void __launch_bounds__(128)
+decode_attn_small_kernel(const bf16* __restrict__ qkv, KVLayout L, const bf16* __restrict__ cos_t, const bf16* __restrict__ sin_t,
+                         bf16* __restrict__ out, int n_rows_heads, int pos0, const int* pos_dev, int ldq, int ldo, float scale) {
+    constexpr int E = D / 32;          // elements per lane (8 for D = 256)
+    static_assert(E == 8, "one 16-byte vector per lane");
+    const int wid = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (wid >= n_rows_heads) return;
+    const int lane = threadIdx.x & 31;
+    const int b = wid / L.n_heads, h = wid % L.n_heads;
+    const int pos = (pos_dev ? *pos_dev : 0) + pos0;
+    const int H = L.n_heads * D;
+    const bf16* row = qkv + (size_t)b * ldq + h * D;
+    // RoPE pairs (d, d + D/2) live in lanes l and l ^ 16
+    float qv[8], kv_[8], cs[8], sn[8];
+    unpack8(*reinterpret_cast<const uint4*>(row + lane * 8), qv);
+    unpack8(*reinterpret_cast<const uint4*>(row + H + lane * 8), kv_);
+    unpack8(*reinterpret_cast<const uint4*>(cos_t + (size_t)pos * (D / 2) + (lane & 15) * 8), cs);
+    unpack8(*reinterpret_cast<const uint4*>(sin_t + (size_t)pos * (D / 2) + (lane & 15) * 8), sn);
+    const bool lo = lane < 16;
+    float qr[8], kr[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const float qo = __shfl_xor_sync(0xffffffffu, qv[j], 16), ko = __shfl_xor_sync(0xffffffffu, kv_[j], 16);
+        // first half: x1*c + (-x2)*s ; second half: x2*c + x1*s   (other = the partner element)
+        qr[j] = bf16_round(bf16_round(qv[j] * cs[j]) + bf16_round((lo ? -qo : qo) * sn[j]));
+        kr[j] = bf16_round(bf16_round(kv_[j] * cs[j]) + bf16_round((lo ? -ko : ko) * sn[j]));
+    }
+    const uint4 k_new = pack8(kr);
+    const uint4 v_new = *reinterpret_cast<const uint4*>(row + 2 * H + lane * 8);
+    {
+        const size_t o = kv_off(L, b, h, pos) + lane * 8;
+        *reinterpret_cast<uint4*>(L.k_pool + o) = k_new;
+        *reinterpret_cast<uint4*>(L.v_pool + o) = v_new;
+    }
+    const int T = pos + 1;             // <= 32
+    float my_s = -INFINITY;            // lane t keeps the score of key t
+    for (int t = 0; t < T; t++) {
+        float kf[8];
+        if (t == pos) unpack8(k_new, kf);
+        else unpack8(*reinterpret_cast<const uint4*>(L.k_pool + kv_off(L, b, h, t) + lane * 8), kf);
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) s = fmaf(kf[j], qr[j], s);
+        s = warp_sum(s) * scale;
+        if (lane == t) my_s = s;
+    }
+    const float mx = warp_max(my_s);
+    const float p = (lane < T) ? __expf(my_s - mx) : 0.f;
+    const float sum = warp_sum(p);
+    const float pb = bf16_round(p);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = 0; t < T; t++) {
+        const float pt = __shfl_sync(0xffffffffu, pb, t);
+        float vf[8];
+        if (t == pos) unpack8(v_new, vf);
+        else unpack8(*reinterpret_cast<const uint4*>(L.v_pool + kv_off(L, b, h, t) + lane * 8), vf);
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = fmaf(pt, vf[j], acc[j]);
+    }
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] *= inv;
+    *reinterpret_cast<uint4*>(out + (size_t)b * ldo + h * D + lane * 8) = pack8(acc);
+}
+
 template <int D>
 __global__ void decode_attn_combine_kernel(const float* __restrict__ partial, bf16* __restrict__ out, int n_heads,
                                            int n_split, int ldo) {
@@ -498,6 +601,67 @@ __device__ int compact_nonzero(float* s_p, int* s_i, int V, int* s_cnt) {
     return total;
 }
 
+
+// Top-k preselection: the sampling tail only looks at ranks < top_k, so instead of sorting all n candidates we keep the
+// ones at or above the k-th largest value (found with two shared-memory histograms over the fp32 bit pattern: exponent,
+// then the 8 mantissa bits below it -- probabilities are bf16-rounded so 8 mantissa bits separate all distinct values)
+// and sort only those.  Returns the new candidate count (n itself when the selection would not shrink the set).
+__device__ int preselect_topk(float* s_p, int* s_i, int n, int top_k, int* s_hist /*[257]*/) {
+    if (n <= 64 || top_k >= n || top_k > 64) return n;
+    __shared__ int s_sel[2];       // {exponent bin, mantissa bin} of the k-th largest value
+    __shared__ int s_count;
+    for (int i = threadIdx.x; i < 257; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&s_hist[(__float_as_uint(s_p[i]) >> 23) & 0xFF], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int cum = 0, e = 255;
+        for (; e > 0; e--) { cum += s_hist[e]; if (cum >= top_k) break; }
+        s_sel[0] = e;
+        s_hist[256] = cum - s_hist[e];      // candidates strictly above the boundary exponent
+    }
+    __syncthreads();
+    const int e_star = s_sel[0];
+    const int above = s_hist[256];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned u = __float_as_uint(s_p[i]);
+        if (((u >> 23) & 0xFF) == (unsigned)e_star) atomicAdd(&s_hist[(u >> 15) & 0xFF], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int cum = above, m = 255;
+        for (; m > 0; m--) { cum += s_hist[m]; if (cum >= top_k) break; }
+        s_sel[1] = m;
+        s_count = 0;
+    }
+    __syncthreads();
+    const unsigned thr = ((unsigned)e_star << 23) | ((unsigned)s_sel[1] << 15);     // keep p with bit pattern >= thr
+    // count first: if the selection is not small, keep everything
+    int mine = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) mine += (__float_as_uint(s_p[i]) >= thr) ? 1 : 0;
+    atomicAdd(&s_count, mine);
+    __syncthreads();
+    const int m_sel = s_count;
+    __syncthreads();
+    if (m_sel > 256 || m_sel >= n) return n;
+    // compact the selected entries to the front (their order is fixed later by the (prob desc, id asc) sort)
+    float keep_p[SMP_MAXV / SMP_THREADS];
+    int keep_i[SMP_MAXV / SMP_THREADS];
+    int c = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if (__float_as_uint(s_p[i]) >= thr) { keep_p[c] = s_p[i]; keep_i[c] = s_i[i]; c++; }
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    const int base = atomicAdd(&s_count, c);
+    __syncthreads();       // all reads of s_p / s_i are done (values are in registers) before the overwrite
+    for (int j = 0; j < c; j++) { s_p[base + j] = keep_p[j]; s_i[base + j] = keep_i[j]; }
+    __syncthreads();
+    return m_sel;
+}
+
 // probs: [rows, V] (bf16 or fp32) already softmaxed and masked (public sample_top_p_k API)
 template <typename T>
 __global__ void __launch_bounds__(SMP_THREADS)
@@ -579,6 +743,7 @@ sample_logits_kernel(const bf16* __restrict__ logits, int V, int ld, float temp,
         // fall back to the lowest allowed id instead of crashing.
         id = lo;
     } else {
+        n = preselect_topk(s_p, s_i, n, top_k, s_cnt);      // s_cnt (257 ints) is free again after the compaction
         id = sample_tail(s_p, s_i, n, top_p, top_k, uniforms[r], true);
     }
     if (threadIdx.x == 0) out[(size_t)r * out_stride] = id;
@@ -725,6 +890,13 @@ extern "C" int b200_attn_decode_fused(const void* qkv, void* k_pool, void* v_poo
     B200_CHECK_ARG(workspace_bytes >= b200_attn_decode_workspace_bytes(batch, n_heads, head_dim, n_split),
                    "attn_decode_fused: workspace too small");
     KVLayout L{(bf16*)k_pool, (bf16*)v_pool, block_table, max_pages, page, n_heads, head_dim};
+    if (head_dim == 256 && max_T <= 32) {      // token-level stack: warp-per-head kernel
+        const int n = batch * n_heads;
+        decode_attn_small_kernel<256><<<(n + 3) / 4, 128, 0, stream>>>((const bf16*)qkv, L, (const bf16*)cos_t, (const bf16*)sin_t,
+                                                                      (bf16*)out, n, pos0, pos_dev, ldq, ldo, scale);
+        B200_CHECK_LAUNCH("attn_decode_small");
+        return B200_OK;
+    }
     dim3 grid(batch * n_heads, n_split);
     if (head_dim == 64) {
         decode_attn_fused_kernel<64><<<grid, 128, 0, stream>>>((const bf16*)qkv, L, (const bf16*)cos_t, (const bf16*)sin_t,

@@ -428,6 +428,30 @@ def check_decode():
     lib.call("b200_sample_topp_topk", probs.data_ptr(), 0, 64, V, V, 0.98, 20, u.data_ptr(), o1.data_ptr(), lib.stream())
     top20 = probs.topk(20, -1).indices
     out["sampler_topk_outside"] = float((~(top20 == o1[:, None]).any(-1)).sum())
+    # fused logits sampler (temperature softmax + grammar range + top-p/top-k) incl. the histogram top-k preselection:
+    # greedy == argmax inside the allowed range, top-20 draws stay inside the 20 largest, for narrow and 2048-wide ranges
+    from midi_b200.tokenizer_tables import TokenizerTables
+    tokz = TokenizerTables("v2")
+    glut = dec.GrammarLUT(tokz, DEV)
+    logits = torch.zeros(64, 3408, device=DEV, dtype=BF)
+    logits[:, :V] = (torch.randn(64, V, generator=g, device=DEV) * 2.5).to(BF)
+    uu = torch.rand(64, generator=g, device=DEV)
+    ev = torch.full((64,), tokz.event_ids["note"], dtype=torch.long, device=DEV)
+    for step, pname in ((1, "time1"), (7, "duration"), (5, "pitch")):
+        lo, hi = tokz.parameter_ids[pname][0], tokz.parameter_ids[pname][-1] + 1
+        outb = torch.zeros(64, 8, dtype=torch.long, device=DEV)
+        dec.sample_from_logits(logits, V, 1.0, 0.98, 1, step, ev, glut, uu, outb)
+        ref_arg = logits[:, lo:hi].float().argmax(-1) + lo
+        pr = torch.softmax(logits[:, :V].float(), -1).to(BF)
+        # ties in bf16 probabilities are broken towards the lowest id: compare probabilities, not ids
+        got = outb[:, step]
+        out[f"logits_sampler_greedy_{pname}"] = float((pr.gather(1, got[:, None]) != pr.gather(1, ref_arg[:, None])).sum()
+                                                       + ((got < lo) | (got >= hi)).sum())
+        dec.sample_from_logits(logits, V, 1.0, 1.0, 20, step, ev, glut, uu, outb)
+        got = outb[:, step]
+        kth = pr[:, lo:hi].float().topk(20, -1).values[:, -1]
+        out[f"logits_sampler_top20_{pname}"] = float((pr.gather(1, got[:, None])[:, 0].float() < kth).sum()
+                                                      + ((got < lo) | (got >= hi)).sum())
     # empirical distribution of one row vs the reference algorithm's renormalised top-p/top-k weights
     row = probs[:1].repeat(4096, 1).contiguous()
     u = torch.rand(4096, generator=g, device=DEV)
@@ -774,7 +798,7 @@ THRESH = [
     ("flash_fwd", 6e-3), ("flash_lse", 1e-4), ("flash_bwd", 1.2e-2), ("tiny_fwd", 6e-3), ("tiny_bwd", 1.2e-2),
     ("ce_loss_abs", 2e-3), ("ce_count_abs", 0.0), ("ce_bwd_padcols_absmax", 0.0), ("ce_bwd", 6e-3),
     ("ce_all_ignored_loss", 0.0), ("gradnorm_rel", 1e-4), ("adamw_maxabs", 2e-3),
-    ("gemv_", 4e-3), ("decode_attn", 6e-3), ("sampler_greedy_mismatch", 0.0), ("sampler_topk_outside", 0.0),
+    ("gemv_", 4e-3), ("decode_attn", 6e-3), ("sampler_greedy_mismatch", 0.0), ("logits_sampler_", 0.0), ("sampler_topk_outside", 0.0),
     ("sampler_dist_l1", 0.12),
     ("min:inv_freq_is_bf16", 1.0), ("margin_filtered_argmax_mismatch", 0.0),
     ("hidden_new_vs_oracle16", 3e-2), ("logits_new_vs_oracle16", 4e-2), ("logits_teacher_forced_vs_oracle16", 2e-2),
