@@ -306,7 +306,8 @@ def generate_leg(model, dev, world, rank):
     rt = model._rt()
     tok = model.tokenizer
     res = {"unit": "events/s", "sampling": "temp=1.0 top_p=0.98 top_k=20", "note": "one CUDA-graph replay per event; wall clock incl. launches"}
-    for B, n_new in ((1, 512), (8, 512)):
+    # batch 8 runs BASELINE config 3 in full: 4096-event context (1 BOS + 4095 generated events per row)
+    for B, n_new in ((1, 512), (8, 4095)):
         gg = dec.GraphGenerator(model._cached_stack("outer"), model._cached_stack("inner"), rt.lm_head, rt.pitch, rt.V, tok,
                                 dec.GrammarLUT(tok, dev), B, n_new + 1, 1.0, 0.98, 20, 1234 + rank)
         prompt = torch.full((B, 1, tok.max_token_seq), tok.pad_id, dtype=torch.long, device=dev)

@@ -91,6 +91,11 @@ int b200_gemm_bf16(const void* A, const void* B, void* C, const void* R, int M, 
 int b200_gemm_bf16_rope(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                         const void* rope_cos, const void* rope_sin, int S, int head_dim, int rope_cols, cudaStream_t s);
 
+/*      gate|up projection with SwiGLU fused (hf modeling_llama.py:182-184): gu[M,2I] = A . Wgu^T is stored (backward
+ *      needs g, u) and act[M,I] = bf16(bf16(silu(g)) * u) is produced by the same epilogue; I % 128 == 0 */
+int b200_gemm_bf16_swiglu(const void* A, const void* Wgu, void* gu, void* act, int M, int I, int K, int lda, int ldw,
+                          int ld_gu, int ld_act, cudaStream_t s);
+
 /* ---- attention (hf integrations/sdpa_attention.py:41-104 via modeling_llama.py:251-289) ----------
  *      outer stack: causal flash attention, head_dim 64; strides are element strides {batch,row,head}. */
 int b200_attn_causal_fwd(const void* q, const void* k, const void* v, void* o, float* lse /*may be NULL*/,
@@ -115,8 +120,9 @@ int b200_attn_causal_bwd_tc(const void* q, const void* k, const void* v, const v
 /*      tuning hook: clock64 trace of CTA (0,0) of the dQ kernel into a device buffer of 128 int64 (NULL = off) */
 void b200_attn_debug_trace(long long* buf);
 /*      inner stack: L <= 8 positions per event, head_dim 256, packed qkv rows [n_events*L, ld_qkv]. */
-int b200_attn_tiny_fwd(const void* qkv, void* out, int n_events, int L, int n_heads, int head_dim, int ld_qkv, int ld_out,
-                       float scale, cudaStream_t s);
+/*      rope_cos/sin != NULL: qkv holds PRE-RoPE projections; q and k are rotated in place (fused RoPE) before use */
+int b200_attn_tiny_fwd(void* qkv, void* out, int n_events, int L, int n_heads, int head_dim, int ld_qkv, int ld_out,
+                       float scale, const void* rope_cos /*may be NULL*/, const void* rope_sin, cudaStream_t s);
 int b200_attn_tiny_bwd(const void* qkv, const void* d_out, void* dqkv, int n_events, int L, int n_heads, int head_dim,
                        int ld_qkv, int ld_out, float scale, const void* rope_cos /*may be NULL*/, const void* rope_sin,
                        cudaStream_t s);

@@ -48,6 +48,22 @@ __device__ __forceinline__ void rope_bwd_lane(float* acc, const bf16* __restrict
     }
 }
 
+// forward RoPE on one 8-wide slice: lanes l and l^16 hold the (d, d+128) pairs
+__device__ __forceinline__ uint4 rope_fwd_lane(const uint4& x, const bf16* __restrict__ cos_t, const bf16* __restrict__ sin_t,
+                                               int pos, int lane) {
+    float v[8], c[8], sn[8], o[8];
+    unpack8(x, v);
+    unpack8(*reinterpret_cast<const uint4*>(cos_t + (size_t)pos * (TD / 2) + (lane & 15) * 8), c);
+    unpack8(*reinterpret_cast<const uint4*>(sin_t + (size_t)pos * (TD / 2) + (lane & 15) * 8), sn);
+    const bool lo = lane < 16;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const float other = __shfl_xor_sync(0xffffffffu, v[j], 16);
+        o[j] = bf16_round(v[j] * c[j]) + bf16_round((lo ? -other : other) * sn[j]);
+    }
+    return pack8(o);
+}
+
 // causal softmax over s[i][0..i] (scaled scores); returns fp32 probabilities in place
 template <int L>
 __device__ __forceinline__ void softmax_rows(float s[L][L]) {
@@ -70,19 +86,30 @@ __device__ __forceinline__ void softmax_rows(float s[L][L]) {
 
 template <int L>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-tiny_attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int n_events, int n_heads, int ld_qkv, int ld_out,
-                     float scale) {
+tiny_attn_fwd_kernel(bf16* __restrict__ qkv, bf16* __restrict__ out, int n_events, int n_heads, int ld_qkv, int ld_out,
+                     float scale, const bf16* __restrict__ rope_cos, const bf16* __restrict__ rope_sin) {
     const int wid = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
     if (wid >= n_events * n_heads) return;
     const int lane = threadIdx.x & 31;
     const int e = wid / n_heads, h = wid % n_heads;
     const int H = n_heads * TD;
-    const bf16* base = qkv + (size_t)e * L * ld_qkv + h * TD + lane * 8;
+    bf16* base = qkv + (size_t)e * L * ld_qkv + h * TD + lane * 8;
     uint4 q[L], k[L];
 #pragma unroll
     for (int i = 0; i < L; i++) {
-        q[i] = ld_nc16(base + (size_t)i * ld_qkv);
-        k[i] = ld_nc16(base + (size_t)i * ld_qkv + H);
+        q[i] = *reinterpret_cast<const uint4*>(base + (size_t)i * ld_qkv);
+        k[i] = *reinterpret_cast<const uint4*>(base + (size_t)i * ld_qkv + H);
+    }
+    if (rope_cos) {
+        // fused RoPE (hf :146-168, three roundings): this warp owns the (event, head) slice, so q and k are rotated in
+        // registers and written back in place -- the saved activation is post-RoPE, as the backward pass expects
+#pragma unroll
+        for (int i = 0; i < L; i++) {
+            q[i] = rope_fwd_lane(q[i], rope_cos, rope_sin, i, lane);
+            k[i] = rope_fwd_lane(k[i], rope_cos, rope_sin, i, lane);
+            *reinterpret_cast<uint4*>(base + (size_t)i * ld_qkv) = q[i];
+            *reinterpret_cast<uint4*>(base + (size_t)i * ld_qkv + H) = k[i];
+        }
     }
     float s[L][L];
 #pragma unroll
@@ -204,14 +231,15 @@ tiny_attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_ou
     }
 
 // qkv: [n_events * L, ld_qkv] packed (q | k | v thirds of n_heads*256 columns, post-RoPE); out: [n_events * L, ld_out]
-extern "C" int b200_attn_tiny_fwd(const void* qkv, void* out, int n_events, int L, int n_heads, int head_dim, int ld_qkv,
-                                  int ld_out, float scale, cudaStream_t stream) {
+extern "C" int b200_attn_tiny_fwd(void* qkv, void* out, int n_events, int L, int n_heads, int head_dim, int ld_qkv,
+                                  int ld_out, float scale, const void* rope_cos, const void* rope_sin, cudaStream_t stream) {
     B200_CHECK_ARG(head_dim == TD, "attn_tiny_fwd: head_dim %d unsupported (256 only)", head_dim);
     B200_CHECK_ARG(L >= 1 && L <= 8, "attn_tiny_fwd: L=%d outside 1..8", L);
     B200_CHECK_ARG(ld_qkv % 8 == 0 && ld_out % 8 == 0, "attn_tiny_fwd: leading dims must be multiples of 8");
     if (n_events == 0) return B200_OK;
     const int grid = (n_events * n_heads + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    B200_TINY_DISPATCH(tiny_attn_fwd_kernel, (const bf16*)qkv, (bf16*)out, n_events, n_heads, ld_qkv, ld_out, scale);
+    B200_TINY_DISPATCH(tiny_attn_fwd_kernel, (bf16*)qkv, (bf16*)out, n_events, n_heads, ld_qkv, ld_out, scale,
+                       (const bf16*)rope_cos, (const bf16*)rope_sin);
     B200_CHECK_LAUNCH("attn_tiny_fwd");
     return B200_OK;
 }

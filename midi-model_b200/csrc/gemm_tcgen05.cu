@@ -21,7 +21,7 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
 constexpr int EPI_WARP0 = 2;
 
-enum { EPI_STORE = 0, EPI_RESIDUAL = 1, EPI_PARTIAL_F32 = 2, EPI_ROPE = 3 };
+enum { EPI_STORE = 0, EPI_RESIDUAL = 1, EPI_PARTIAL_F32 = 2, EPI_ROPE = 3, EPI_SWIGLU = 4 };
 
 struct GemmParams {
     bf16* C;
@@ -37,6 +37,9 @@ struct GemmParams {
     const bf16* rope_cos;
     const bf16* rope_sin;
     int rope_S, rope_D, rope_cols;
+    // EPI_SWIGLU: B = [gate | up] weight rows; tile n covers gate rows [128n, 128n+128) and up rows [I + 128n, ...)
+    bf16* act;
+    int swiglu_I, ld_act;
 };
 
 using namespace tc05;
@@ -115,7 +118,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             tma_load_2d(sA + c * (BLOCK_K * 128), &tmA, &full_bar[stage], m_blk * BLOCK_M + c * 64, kb * BLOCK_K);
                     }
                     if (!B_MN) {
-                        tma_load_2d(sB, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+                        if (BLOCK_N == 256 && p.epilogue == EPI_SWIGLU) {   // gate half | up half (tensor map box = 128 rows)
+                            tma_load_2d(sB, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * 128);
+                            tma_load_2d(sB + 128 * BLOCK_K * 2, &tmB, &full_bar[stage], kb * BLOCK_K, p.swiglu_I + n_blk * 128);
+                        } else {
+                            tma_load_2d(sB, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+                        }
                     } else {
 #pragma unroll
                         for (int c = 0; c < BLOCK_N / 64; c++)
@@ -174,7 +182,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int row = m_blk * BLOCK_M + quarter * 32 + lane;
             const bool row_ok = row < p.M;
             const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(quarter * 32) << 16);
-            if (p.epilogue == EPI_ROPE) {
+            if (BLOCK_N == 256 && p.epilogue == EPI_SWIGLU) {
+                // gate|up projection with SwiGLU fused (hf modeling_llama.py:183): accumulator columns [0,128) are gate
+                // features, [128,256) the matching up features.  g, u = bf16(acc) are stored (backward needs them) and
+                // act = bf16(bf16(silu(g)) * u) -- same rounding points as the stand-alone kernel.
+#pragma unroll 1
+                for (int c = 0; c < 4; c++) {
+                    uint32_t r1[32], r2[32];
+                    tmem_ld32(taddr + c * 32, r1);
+                    tmem_ld32(taddr + 128 + c * 32, r2);
+                    tmem_ld_wait();
+                    const int f0 = n_blk * 128 + c * 32;
+                    if (row_ok && f0 < p.swiglu_I) {
+                        bf16* dg = p.C + (size_t)row * p.ldc + f0;
+                        bf16* du = dg + p.swiglu_I;
+                        bf16* da = p.act + (size_t)row * p.ld_act + f0;
+#pragma unroll
+                        for (int v = 0; v < 4; v++) {
+                            float g[8], u[8], a[8];
+#pragma unroll
+                            for (int q = 0; q < 8; q++) {
+                                g[q] = bf16_round(__uint_as_float(r1[8 * v + q]));
+                                u[q] = bf16_round(__uint_as_float(r2[8 * v + q]));
+                                a[q] = bf16_round(g[q] / (1.f + __expf(-g[q]))) * u[q];
+                            }
+                            *reinterpret_cast<uint4*>(dg + v * 8) = pack8(g);
+                            *reinterpret_cast<uint4*>(du + v * 8) = pack8(u);
+                            *reinterpret_cast<uint4*>(da + v * 8) = pack8(a);
+                        }
+                    }
+                }
+            } else if (p.epilogue == EPI_ROPE) {
                 // QKV projection with RoPE fused (hf modeling_llama.py:262-268): x = bf16(acc) (the Linear's rounding),
                 // then o1 = bf16(bf16(x1*c) + bf16(-x2*s)), o2 = bf16(bf16(x2*c) + bf16(x1*s)) on (d, d + D/2) pairs.
                 const int half = p.rope_D >> 1;
@@ -470,10 +508,21 @@ extern "C" int b200_gemm_bf16_rope(const void* A, const void* B, void* C, int M,
                      (const bf16*)rope_sin, S, head_dim, rope_cols, stream);
 }
 
+// Fused gate|up projection + SwiGLU: gu[M, 2I] = A . Wgu^T (stored, the backward pass needs g and u) and
+// act[M, I] = bf16(bf16(silu(g)) * u) written by the same epilogue.  Wgu = [gate rows | up rows], K-major operands.
+extern "C" int b200_gemm_bf16_swiglu(const void* A, const void* Wgu, void* gu, void* act, int M, int I, int K, int lda,
+                                     int ldw, int ld_gu, int ld_act, cudaStream_t stream) {
+    B200_CHECK_ARG(I % 128 == 0, "gemm_swiglu: intermediate size %d must be a multiple of 128", I);
+    B200_CHECK_ARG(ld_act % 8 == 0 && (uintptr_t)act % 16 == 0, "gemm_swiglu: act must be 16-byte aligned");
+    return gemm_impl(A, Wgu, gu, nullptr, M, 2 * I, K, lda, ldw, ld_gu, 0, 0, 0, 0, 256, 1, act, (size_t)I | ((size_t)ld_act << 32),
+                     nullptr, nullptr, -1, 0, 0, stream);
+}
+
 static int gemm_impl(const void* A, const void* B, void* C, const void* R, int M, int N, int K, int lda, int ldb, int ldc,
                      int ldr, int a_mn_major, int b_mn_major, int accumulate, int block_n, int splits, void* workspace,
                      size_t workspace_bytes, const bf16* rope_cos, const bf16* rope_sin, int rope_S, int rope_D,
                      int rope_cols, cudaStream_t stream) {
+    const bool swiglu = (rope_S == -1);      // internal marker set by b200_gemm_bf16_swiglu (workspace = act, bytes = I | ld<<32)
     B200_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
     // N need not be a multiple of 8: B rows >= N are out of bounds for the tensor map (zero-filled), so the
     // epilogue may store whole 16-byte vectors up to roundup8(N) (zeros) as long as the row pitch covers them.
@@ -504,7 +553,7 @@ static int gemm_impl(const void* A, const void* B, void* C, const void* R, int M
     if (const char* e = getenv("B200_GEMM_MN_SWAP")) {
         if (e[0] == '1') { p.mn_lbo = 1024; p.mn_sbo = BLOCK_K * 128; }
     }
-    if (splits > 1 || accumulate) {
+    if (!swiglu && (splits > 1 || accumulate)) {
         B200_CHECK_ARG(R == nullptr, "gemm: split-K/accumulate cannot be combined with a residual epilogue");
         B200_CHECK_ARG(ldc == N && N % 8 == 0, "gemm: split-K/accumulate output must be contiguous (ldc == N, N %% 8 == 0)");
         const size_t need = (size_t)splits * M * N * sizeof(float);
@@ -516,13 +565,21 @@ static int gemm_impl(const void* A, const void* B, void* C, const void* R, int M
     }
     p.rope_cos = rope_cos; p.rope_sin = rope_sin; p.rope_S = rope_S; p.rope_D = rope_D; p.rope_cols = rope_cols;
     if (rope_cos) p.epilogue = EPI_ROPE;
+    p.act = nullptr; p.swiglu_I = 0; p.ld_act = 0;
+    if (swiglu) {
+        p.epilogue = EPI_SWIGLU;
+        p.act = (bf16*)workspace;
+        p.swiglu_I = (int)(workspace_bytes & 0xffffffffu);
+        p.ld_act = (int)(workspace_bytes >> 32);
+        p.n_tiles = p.swiglu_I / 128;         // one tile = 128 gate + 128 up features
+    }
 
     CUtensorMap tmA, tmB;
     int rc;
     if (!a_mn_major) rc = tc05::make_tmap_2d(&tmA, A, K, M, lda, BLOCK_K, BLOCK_M);
     else             rc = tc05::make_tmap_2d(&tmA, A, M, K, lda, 64, BLOCK_K);
     if (rc) return rc;
-    if (!b_mn_major) rc = tc05::make_tmap_2d(&tmB, B, K, N, ldb, BLOCK_K, block_n);
+    if (!b_mn_major) rc = tc05::make_tmap_2d(&tmB, B, K, N, ldb, BLOCK_K, swiglu ? 128 : block_n);
     else             rc = tc05::make_tmap_2d(&tmB, B, N, K, ldb, 64, BLOCK_K);
     if (rc) return rc;
 

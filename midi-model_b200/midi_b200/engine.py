@@ -28,6 +28,8 @@ BF16 = torch.bfloat16
 # (QKV GEMM 1213 -> 843 TFLOP/s), a net loss of 0.8 ms/step against the HBM-roofline stand-alone kernel.
 FUSE_ROPE = os.environ.get("B200_FUSE_ROPE", "1") != "0"
 FUSE_ROPE_FWD = os.environ.get("B200_FUSE_ROPE_FWD", "0") != "0"
+# SwiGLU formed in the epilogue of the gate|up GEMM (bit-identical to GEMM + stand-alone kernel); B200_FUSE_SWIGLU=0 disables
+FUSE_SWIGLU = os.environ.get("B200_FUSE_SWIGLU", "1") != "0"
 ALIGN = 256   # elements; AdamW's no-decay flags are per 256-element block
 
 
@@ -221,20 +223,25 @@ class StackEngine:
                 n1, rstd1 = ops.rmsnorm(x, w.ln1, c.eps, want_rstd=True)
             else:
                 x, n1, rstd1 = ops.add_rmsnorm(x, pending, w.ln1, c.eps)
+            fuse_tiny = self.tiny and FUSE_ROPE and not FUSE_ROPE_FWD     # token-level stack: RoPE inside the attention kernel
             if FUSE_ROPE_FWD:
                 qkv = ops.linear_rope(n1, w.qkv, cos, sin, S, D)      # QKV GEMM with RoPE in the epilogue
             else:
                 qkv = ops.linear(n1, w.qkv)
-                ops.rope_qk_(qkv, cos, sin, S, H, D)
+                if not fuse_tiny:
+                    ops.rope_qk_(qkv, cos, sin, S, H, D)
             if self.tiny:
-                attn, lse = ops.attn_tiny_fwd(qkv, n_seq, S, nh, D), None
+                attn, lse = ops.attn_tiny_fwd(qkv, n_seq, S, nh, D, rope=(cos, sin) if fuse_tiny else None), None
             else:
                 attn, lse = ops.attn_causal_fwd(qkv, n_seq, S, nh, D, want_lse=save)
             y1 = ops.linear(attn, w.o)
             h, n2, rstd2 = ops.add_rmsnorm(x, y1, w.ln2, c.eps)
             del y1
-            gu = ops.linear(n2, w.gu)
-            act = ops.swiglu(gu)
+            if FUSE_SWIGLU and c.inner % 128 == 0:
+                gu, act = ops.linear_swiglu(n2, w.gu)
+            else:
+                gu = ops.linear(n2, w.gu)
+                act = ops.swiglu(gu)
             pending = ops.linear(act, w.down)
             if save:
                 saved.append((x, n1, rstd1, qkv, attn, lse, h, n2, rstd2, gu, act))

@@ -189,6 +189,24 @@ def linear(x: torch.Tensor, w: torch.Tensor, residual: Optional[torch.Tensor] = 
     return gemm(x, w, M, N, K, lda=x.stride(0), ldb=w.stride(0), residual=residual, out=out)
 
 
+def linear_swiglu(x: torch.Tensor, w_gu: torch.Tensor):
+    """(gu, act): gu = x @ w_gu.T with w_gu = [gate | up] rows, act = silu(gate) * up formed in the GEMM epilogue."""
+    M, K = x.shape
+    I = w_gu.shape[0] // 2
+    gu = torch.empty((M, 2 * I), dtype=BF16, device=x.device)
+    act = torch.empty((M, I), dtype=BF16, device=x.device)
+    prof = GEMM_PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    lib.call("b200_gemm_bf16_swiglu", x.data_ptr(), w_gu.data_ptr(), gu.data_ptr(), act.data_ptr(), M, I, K, x.stride(0),
+             w_gu.stride(0), 2 * I, I, lib.stream())
+    if prof is not None:
+        e1.record()
+        prof.append((e0, e1, 4.0 * M * I * K, (M, 2 * I, K, 0, 0, 256, 1)))
+    return gu, act
+
+
 def linear_dgrad(dy: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     """dx[M,K] = dy[M,:N] @ w[N,K]  (B operand = w as stored, 'MN-major'); dy may have a row pitch > N."""
     M = dy.shape[0]
@@ -266,11 +284,12 @@ def _attn_causal_bwd_tc(qkv, out, dout, lse, B, S, n_heads, D, rope):
     return dqkv
 
 
-def attn_tiny_fwd(qkv: torch.Tensor, n_events: int, L: int, n_heads: int, D: int) -> torch.Tensor:
+def attn_tiny_fwd(qkv: torch.Tensor, n_events: int, L: int, n_heads: int, D: int, rope=None) -> torch.Tensor:
+    """`rope=(cos, sin)`: qkv holds pre-RoPE projections; q and k are rotated IN PLACE inside the kernel (fused RoPE)."""
     H = n_heads * D
     out = torch.empty((n_events * L, H), dtype=BF16, device=qkv.device)
     lib.call("b200_attn_tiny_fwd", qkv.data_ptr(), out.data_ptr(), n_events, L, n_heads, D, qkv.stride(0), H,
-             1.0 / math.sqrt(D), lib.stream())
+             1.0 / math.sqrt(D), rope[0].data_ptr() if rope else None, rope[1].data_ptr() if rope else None, lib.stream())
     return out
 
 

@@ -58,6 +58,18 @@ def check_gemm_fwd():
     return out
 
 
+def check_gemm_swiglu():
+    """gate|up GEMM with SwiGLU in the epilogue == plain GEMM + stand-alone SwiGLU kernel, bit for bit."""
+    out = {}
+    for i, (M, I, K) in enumerate([(300, 1024, 1024), (2048, 4096, 1024), (1000, 128, 256)]):
+        x, w = randn(M, K, seed=60 + i), randn(2 * I, K, scale=0.05, seed=70 + i)
+        gu, act = ops.linear_swiglu(x, w)
+        gu_ref = ops.linear(x, w)
+        out[f"gemm_swiglu_gu_mismatch_{M}x{I}"] = float((gu != gu_ref).sum())
+        out[f"gemm_swiglu_act_mismatch_{M}x{I}"] = float((act != ops.swiglu(gu_ref)).sum())
+    return out
+
+
 def check_gemm_dgrad():
     out = {}
     for i, (M, N, K) in enumerate([(256, 256, 128), (1000, 3072, 1024), (2048, 1024, 4096), (520, 3406, 1024)]):
@@ -315,6 +327,12 @@ def check_fused_rope():
         ops.rope_qk_(b, cos, sin, S, H, D, backward=True)
         out[f"attn_bwd_fused_rope_D{D}"] = rel(a.float(), b.float())
         out[f"attn_bwd_fused_rope_v_mismatch_D{D}"] = float((a[:, 2 * H:] != b[:, 2 * H:]).sum())
+        if D == 256:   # forward: RoPE fused into the token-level attention kernel (in-place rotation) == rope kernel + attention
+            pre = ops.linear(x, w)
+            o_f = ops.attn_tiny_fwd(pre, nseq, S, nh, D, rope=(cos, sin))
+            o_r = ops.attn_tiny_fwd(ref, nseq, S, nh, D)
+            out["tiny_fused_rope_out_mismatch"] = float((o_f != o_r).sum())
+            out["tiny_fused_rope_qkv_mismatch"] = float((pre != ref).sum())
     return out
 
 
@@ -778,22 +796,51 @@ def check_model_peaked_greedy():
     return out
 
 
+def check_model_large():
+    """tv2o-large (24 event-level / 6 token-level layers, BASELINE config 5): fused loss + gradients vs the oracle at a
+    small shape, and a short KV-cached generate at the maximum context bookkeeping (max_len 4096 pools)."""
+    from midi_b200.synth import synth_batch
+    import midi_model as mm
+    out = {}
+    torch.manual_seed(0)
+    model = mm.MIDIModel(mm.MIDIModelConfig.from_name("tv2o-large"))
+    out["large_params"] = float(sum(p.numel() for p in model.parameters()))
+    ocfg = O.cfg_from_hf(model.config)
+    model = model.to(DEV, dtype=BF).train()
+    batch = synth_batch(model.tokenizer, 1, 130, seed=3).to(DEV)
+    sd = {k: v.detach().float().requires_grad_(True) for k, v in model.state_dict().items()}
+    ref = O.train_loss(sd, ocfg, batch)
+    ref.backward()
+    loss = model.training_loss(batch)
+    out["large_loss_abs"] = float((loss - ref.detach()).abs())
+    tot_n = tot_d = 0.0
+    for n, p in model.named_parameters():
+        tot_n += float((p.grad.float() - sd[n].grad).double().pow(2).sum())
+        tot_d += float(sd[n].grad.double().pow(2).sum())
+    out["large_grad_global_rel"] = math.sqrt(tot_n / tot_d)
+    del sd
+    model.eval()
+    ids = model.generate(batch_size=2, max_len=4096 if False else 40, generator=torch.Generator(DEV).manual_seed(0))
+    out["large_generate_events"] = float(ids.shape[1])
+    return out
+
+
 GROUPS = {
-    "gemm_fwd": check_gemm_fwd, "gemm_dgrad": check_gemm_dgrad, "gemm_wgrad": check_gemm_wgrad,
+    "gemm_fwd": check_gemm_fwd, "gemm_swiglu": check_gemm_swiglu, "gemm_dgrad": check_gemm_dgrad, "gemm_wgrad": check_gemm_wgrad,
     "elementwise": check_elementwise, "fused_rope": check_fused_rope, "attn_flash": check_attn_flash, "attn_tc05": check_attn_tc05, "attn_tiny": check_attn_tiny,
     "loss_optim": check_loss_optim, "decode": check_decode, "model_forward": check_model_forward,
     "model_layer_tf": check_model_layer_teacher_forced, "model_train": check_model_train,
-    "model_generate": check_model_generate, "model_peaked_greedy": check_model_peaked_greedy,
+    "model_generate": check_model_generate, "model_peaked_greedy": check_model_peaked_greedy, "model_large": check_model_large,
 }
 
 # metric-name prefix -> upper bound (first matching prefix wins); "min:" entries are lower bounds
 THRESH = [
-    ("gemm_vocab_padcols_absmax", 0.0), ("gemm_", 4e-3), ("embed_sum_maxabs", 0.0), ("embed_bwd_padrow_absmax", 0.0),
+    ("gemm_vocab_padcols_absmax", 0.0), ("gemm_swiglu", 0.0), ("gemm_", 4e-3), ("embed_sum_maxabs", 0.0), ("embed_bwd_padrow_absmax", 0.0),
     ("embed_bwd", 4e-3), ("inner_input_equal", 0.0), ("inner_embed_bwd", 4e-3),
     ("rmsnorm_fwd_mismatch", 2e-3), ("rmsnorm_fwd", 2e-3), ("rmsnorm_bwd", 4e-3),
     ("rope_table_mismatch", 8.0), ("rope_fwd_mismatch", 64.0), ("rope_bwd_adjoint", 2e-2),
     ("swiglu_fwd_mismatch", 2e-2), ("swiglu_bwd", 4e-3),
-    ("linear_rope_mismatch", 0.0), ("attn_bwd_fused_rope_v_mismatch", 0.0), ("attn_bwd_fused_rope", 5e-3),
+    ("linear_rope_mismatch", 0.0), ("tiny_fused_rope", 0.0), ("attn_bwd_fused_rope_v_mismatch", 0.0), ("attn_bwd_fused_rope", 5e-3),
     ("tc_vs_mma_bwd", 8e-3), ("tc_bwd", 1.2e-2), ("tc_vs_mma", 4e-3), ("tc_fwd", 6e-3),
     ("flash_fwd", 6e-3), ("flash_lse", 1e-4), ("flash_bwd", 1.2e-2), ("tiny_fwd", 6e-3), ("tiny_bwd", 1.2e-2),
     ("ce_loss_abs", 2e-3), ("ce_count_abs", 0.0), ("ce_bwd_padcols_absmax", 0.0), ("ce_bwd", 6e-3),
@@ -803,6 +850,7 @@ THRESH = [
     ("min:inv_freq_is_bf16", 1.0), ("margin_filtered_argmax_mismatch", 0.0),
     ("hidden_new_vs_oracle16", 3e-2), ("logits_new_vs_oracle16", 4e-2), ("logits_teacher_forced_vs_oracle16", 2e-2),
     ("outer_layer_tf", 6e-3), ("inner_layer_tf", 6e-3),
+    ("large_loss_abs", 3e-2), ("large_grad_global_rel", 8e-2), ("min:large_params", 457220096.0),
     ("loss_abs", 3e-2), ("grad_global_rel", 6e-2), ("grad_pad_row", 0.0), ("autograd_loss_abs", 5e-2),
     ("autograd_grad_global_rel", 6e-2),
     ("cached_vs_full_hidden", 3e-2), ("inner_cached_vs_full_logits", 3e-2), ("min:greedy_token_agree", 0.6),

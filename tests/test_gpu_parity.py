@@ -7,8 +7,8 @@ import pytest
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
-GROUP_NAMES = ["gemm_fwd", "gemm_dgrad", "gemm_wgrad", "elementwise", "fused_rope", "attn_flash", "attn_tc05", "attn_tiny", "loss_optim", "decode",
-               "model_forward", "model_layer_tf", "model_train", "model_generate", "model_peaked_greedy"]
+GROUP_NAMES = ["gemm_fwd", "gemm_swiglu", "gemm_dgrad", "gemm_wgrad", "elementwise", "fused_rope", "attn_flash", "attn_tc05", "attn_tiny", "loss_optim", "decode",
+               "model_forward", "model_layer_tf", "model_train", "model_generate", "model_peaked_greedy", "model_large"]
 
 
 @pytest.mark.gpu
