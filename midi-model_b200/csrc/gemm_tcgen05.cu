@@ -2,8 +2,7 @@
 // staged by TMA into 128B-swizzled shared memory), persistent, warp-specialised:
 //   warp 0     : TMA producer (one elected lane)
 //   warp 1     : TMEM allocator + MMA issuer (one elected lane)
-//   warps 2..9 : epilogue (TMEM -> registers -> fused epilogue -> global); the two warps that share a TMEM lane
-//                quarter split the accumulator columns between them
+//   warps 2..5 : epilogue (TMEM -> registers -> fused epilogue -> global)
 // D[M,N] = A . B^T with fp32 accumulation.  Each operand is either "K-major"
 // (row-major [rows, K], what nn.Linear's forward needs: hf modeling_llama.py:177-184,
 // 238-264) or "MN-major" (stored [K, rows]); the latter serves dgrad (B = W as stored)
@@ -19,7 +18,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quarter)
+constexpr int NUM_THREADS = 192;
 constexpr int EPI_WARP0 = 2;
 
 enum { EPI_STORE = 0, EPI_RESIDUAL = 1, EPI_PARTIAL_F32 = 2, EPI_ROPE = 3, EPI_SWIGLU = 4 };
@@ -83,7 +82,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         for (int s = 0; s < 2; s++) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 8);
+            mbar_init(&tempty_bar[s], 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -172,7 +171,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     } else {
         // ===================== epilogue warps =====================
         const int quarter = warp & 3;               // TMEM lane quarter this warp may access
-        const int chalf = (warp - 2) >> 2;          // which half of the accumulator columns this warp handles
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -189,7 +187,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 // features, [128,256) the matching up features.  g, u = bf16(acc) are stored (backward needs them) and
                 // act = bf16(bf16(silu(g)) * u) -- same rounding points as the stand-alone kernel.
 #pragma unroll 1
-                for (int c = chalf * 2; c < chalf * 2 + 2; c++) {
+                for (int c = 0; c < 4; c++) {
                     uint32_t r1[32], r2[32];
                     tmem_ld32(taddr + c * 32, r1);
                     tmem_ld32(taddr + 128 + c * 32, r2);
@@ -224,7 +222,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int c0 = 0; c0 < BLOCK_N / 32; c0 += 2 * cph) {
 #pragma unroll 1
                     for (int j = 0; j < cph; j++) {
-                        if ((((c0 / (2 * cph)) * cph + j) & 1) != chalf) continue;   // pairs alternate between the two warps
                         uint32_t r1[32], r2[32];
                         tmem_ld32(taddr + (c0 + j) * 32, r1);
                         tmem_ld32(taddr + (c0 + j + cph) * 32, r2);
@@ -266,7 +263,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
             } else
 #pragma unroll 1
-            for (int c = chalf; c < BLOCK_N / 32; c += 2) {
+            for (int c = 0; c < BLOCK_N / 32; c++) {
                 uint32_t r[32];
                 tmem_ld32(taddr + c * 32, r);
                 tmem_ld_wait();
