@@ -28,8 +28,11 @@ BF16 = torch.bfloat16
 # (QKV GEMM 1213 -> 843 TFLOP/s), a net loss of 0.8 ms/step against the HBM-roofline stand-alone kernel.
 FUSE_ROPE = os.environ.get("B200_FUSE_ROPE", "1") != "0"
 FUSE_ROPE_FWD = os.environ.get("B200_FUSE_ROPE_FWD", "0") != "0"
-# SwiGLU formed in the epilogue of the gate|up GEMM (bit-identical to GEMM + stand-alone kernel); B200_FUSE_SWIGLU=0 disables
-FUSE_SWIGLU = os.environ.get("B200_FUSE_SWIGLU", "1") != "0"
+# SwiGLU formed in the epilogue of the gate|up GEMM (ops.linear_swiglu, bit-identical to GEMM + stand-alone kernel) exists
+# but is OFF by default: measured on B200 the heavier epilogue (2 MUFU ops + 3 stores per element pair on 4 epilogue
+# warps) outlasts the K=1024 main loop (gate|up GEMM 1122 -> 686 TFLOP/s), a net loss of 1.3 ms/step; 8 epilogue warps
+# did not help (plain GEMMs got 6 % slower).  B200_FUSE_SWIGLU=1 enables it.
+FUSE_SWIGLU = os.environ.get("B200_FUSE_SWIGLU", "0") != "0"
 ALIGN = 256   # elements; AdamW's no-decay flags are per 256-element block
 
 
