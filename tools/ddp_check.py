@@ -53,5 +53,5 @@ all_l = [torch.zeros_like(lt) for _ in range(dist.get_world_size())]
 dist.all_gather(all_l, lt)
 if rank == 0:
     print("DDP_CHECK params_identical_across_ranks=%s losses=%s" % (same, [[round(float(v), 4) for v in l] for l in all_l]))
-    assert same and all(torch.isfinite(l).all() for l in all_l) and float(all_l[0][0]) != float(all_l[1][0])
+    assert same and all(torch.isfinite(l).all() for l in all_l) and float(all_l[0][1]) != float(all_l[1][1])
 dist.destroy_process_group()
