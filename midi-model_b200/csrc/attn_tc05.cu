@@ -8,6 +8,7 @@
 // an SM (113 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
 // Semantics = hf sdpa_attention.py:92-101 (causal, scale d^-1/2): online softmax in fp32, P rounded to bf16
 // before P.V, output rounded to bf16, LSE saved for the backward pass.
+#include <cstring>
 #include "tc05.cuh"
 
 namespace {
@@ -118,21 +119,21 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             mbar_wait(&kv_full[0], 0);
             issue_s(0);
             for (int j = 0; j < n_kv; j++) {
-                const uint64_t dV0 = make_smem_desc(smem_u32(smem + SM_KV + stage * 32768 + 16384), 16384, 1024);
+                const int st_j = stage;
+                const uint64_t dV0 = make_smem_desc(smem_u32(smem + SM_KV + st_j * 32768 + 16384), 16384, 1024);
                 mbar_wait(p_full, ph);            // softmax wrote P_j (and has finished reading S_j)
+                if (++stage == KV_STAGES) { stage = 0; kv_phase ^= 1; }
+                if (j + 1 < n_kv) {               // S_{j+1} goes first so the softmax warps never wait for the tensor pipe
+                    mbar_wait(&kv_full[stage], kv_phase);
+                    issue_s(stage);
+                }
                 mbar_wait(pv_empty, ph ^ 1);      // previous PV tile drained from TMEM
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < BK / 16; kk++)
                     umma_f16(tPV, desc_adv(dP0, (kk >> 2) * 16384 + (kk & 3) * 32), desc_adv(dV0, kk * 2048), idesc_pv, kk > 0);
                 umma_commit(pv_full);
-                umma_commit(&kv_empty[stage]);
-                if (++stage == KV_STAGES) { stage = 0; kv_phase ^= 1; }
-                if (j + 1 < n_kv) {
-                    mbar_wait(&kv_full[stage], kv_phase);
-                    mbar_wait(s_empty, ph);       // softmax finished reading S_j
-                    issue_s(stage);
-                }
+                umma_commit(&kv_empty[st_j]);
                 ph ^= 1;
             }
         }
@@ -249,6 +250,8 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 // 3-D bf16 tensor map {cols, rows per sequence, batch} with 128B swizzle: rows outside a sequence are zero-filled
 int tc05_make_tmap_3d(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t row_pitch,
                       uint64_t batch_pitch, uint32_t box_cols, uint32_t box_rows);
+int tc05_make_tmap_3d_f32(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t row_pitch,
+                          uint64_t batch_pitch, uint32_t box_cols, uint32_t box_rows);
 
 // q, k, v: [batch, S, heads*64] views (row pitch / batch pitch in elements) of e.g. the packed QKV activation
 extern "C" int b200_attn_causal_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse,
@@ -298,11 +301,12 @@ namespace {
 constexpr int BWD_CWARPS = 16;                   // compute warps: thread = (key row, 32 of the 128 query columns)
 constexpr int BWD_THREADS = 64 + 32 * BWD_CWARPS; // warp 0 TMA, warp 1 MMA, warps 2..17 compute
 constexpr int SB_K = 0, SB_V = 16384;
-constexpr int QS = 4;                            // (Q, dO) stages: TMA latency (~2-3 us under load) must span QS-1 iterations
+constexpr int QS = 3;                            // (Q, dO) stages (4 measured no faster than 3; the 4th stage's 32 KB now stages dQ)
 constexpr int SB_Q = 32768;                      // QS stages x (Q 16 KB + dO 16 KB)
 constexpr int SB_P = SB_Q + QS * 32768;          // P^T : two 64-query atoms of [128 keys x 128 B]
 constexpr int SB_DS = SB_P + 32768;              // dS^T: same layout
-constexpr int SB_LSE = SB_DS + 32768;            // float [2][2][128]: lse, delta per stage parity
+constexpr int SB_DQ = SB_DS + 32768;             // fp32 dQ tile for the TMA reduce: two 32-column boxes of [128 q x 128 B], 128B-swizzled
+constexpr int SB_LSE = SB_DQ + 32768;            // float [2][2][128]: lse, delta per stage parity
 constexpr int SB_BAR = SB_LSE + 2048;
 constexpr int SMEM_BWD_BYTES = SB_BAR + 128;
 
@@ -324,10 +328,21 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <bool WITH_DQ>
+// fp32 tile in shared memory += into global memory through the TMA unit (one instruction per 16 KB box instead of
+// 1024 per-lane red.global instructions)
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* tm, uint32_t smem_addr, int c0, int c1, int c2) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(tm), "r"(smem_addr), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// DQ_MODE: 0 = dK/dV only (dQ by the separate kernel below), 1 = dQ through red.global.add.v4.f32,
+//          2 = dQ tile staged in shared memory and added with cp.reduce.async.bulk.tensor
+template <int DQ_MODE>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const BwdParams p) {
+                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                     const __grid_constant__ CUtensorMap tmDQ, const BwdParams p) {
+    constexpr bool WITH_DQ = DQ_MODE != 0;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SB_BAR);
     uint64_t* kv_full = bars + 0;
@@ -407,9 +422,15 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             mbar_wait(&q_full[0], 0);
             issue_s(0);
             for (int it = 0; it < n_it; it++) {
-                const uint32_t sQ = smem_u32(smem + SB_Q + stage * 32768);
+                const int st_cur = stage;
+                const uint32_t sQ = smem_u32(smem + SB_Q + st_cur * 32768);
                 const uint64_t dQmn = make_smem_desc(sQ, 16384, 1024), dOmn = make_smem_desc(sQ + 16384, 16384, 1024);
                 mbar_wait(pds_full, ph);          // P^T, dS^T of this iteration are in shared memory; S^T/dP^T TMEM is free
+                if (++stage == QS) { stage = 0; qphase ^= 1; }
+                if (it + 1 < n_it) {              // next tile's S^T / dP^T first: the math warps start on it while the
+                    mbar_wait(&q_full[stage], qphase);   // tensor pipe is still busy with this tile's dV / dK / dQ
+                    issue_s(stage);
+                }
                 if (WITH_DQ) mbar_wait(dq_empty, ph ^ 1);      // previous dQ tile drained
                 tc_fence_after();
 #pragma unroll
@@ -426,12 +447,7 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                         umma_f16(tdQ, desc_adv(dDSmn, kk * 2048), desc_adv(dKmn, kk * 2048), id_dq, kk > 0);
                 }
                 umma_commit(dq_full);
-                umma_commit(&q_empty[stage]);
-                if (++stage == QS) { stage = 0; qphase ^= 1; }
-                if (it + 1 < n_it) {
-                    mbar_wait(&q_full[stage], qphase);
-                    issue_s(stage);
-                }
+                umma_commit(&q_empty[st_cur]);
                 ph ^= 1;
             }
         }
@@ -456,23 +472,58 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (ctid >= 256 || it_ >= n_it || qi >= p.Sq) return 0.f;
             return ctid < 128 ? lse_g[qi] * LOG2E : delta_g[qi];
         };
+        // dQ tile of a finished iteration: TMEM lane = query row, this thread owns columns cg*16 .. +15
+        auto drain_dq = [&](int q0_tile) {
+            uint32_t r[16];
+            tmem_ld16(tdQ + lane_addr + cg * 16, r);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dq_empty);                  // TMEM tile is free for the next dQ MMAs
+            if (DQ_MODE == 1) {
+                const int qrow = q0_tile + key_t;                   // (lane index means query row here)
+                if (qrow < p.Sq) {
+                    float* dst = p.dq_acc + b * p.dqa_b + (long long)qrow * p.dqa_r + h * D + cg * 16;
+#pragma unroll
+                    for (int v = 0; v < 4; v++)
+                        red_add_v4(dst + v * 4, __uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
+                                   __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+                }
+            } else {
+                // the staging tile was released by thread 0's wait_group.read ahead of this iteration's bar.sync 1
+                uint8_t* dst = smem + SB_DQ + (cg >> 1) * 16384 + key_t * 128;
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    const int chunk = (cg & 1) * 4 + v;
+                    *reinterpret_cast<uint4*>(dst + ((chunk ^ (key_t & 7)) << 4)) = make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+                }
+                fence_proxy_async_smem();
+                asm volatile("bar.sync 2, 512;" ::: "memory");
+                if (ctid == 0) {
+                    tma_reduce_add_3d(&tmDQ, smem_u32(smem + SB_DQ), h * D, q0_tile, b);
+                    tma_reduce_add_3d(&tmDQ, smem_u32(smem + SB_DQ + 16384), h * D + 32, q0_tile, b);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+        };
         float ld_next = fetch_ld(0);
         for (int it = 0; it < n_it; it++) {
             const int q0 = (i0 + it) * BQ;
             if (ctid < 256) (ctid < 128 ? lse_s : delta_s)[(it & 1) * 128 + (ctid & 127)] = ld_next;
             ld_next = fetch_ld(it + 1);
+            if (DQ_MODE == 2 && ctid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             asm volatile("bar.sync 1, 512;" ::: "memory");
             const float* lse_t = lse_s + (it & 1) * 128 + cg * 32;
             const float* delta_t = delta_s + (it & 1) * 128 + cg * 32;
             const bool need_mask = (k0 + BK - 1 > q0 + off) || (k0 + BK > p.Sk) || (q0 + BQ > p.Sq);
             mbar_wait(s_full, ph);
             tc_fence_after();
+            uint32_t pk[16], dk_[16];
             {
                 uint32_t rs[32], rd[32];
                 tmem_ld32(tS + lane_addr + cg * 32, rs);
                 tmem_ld32(tdP + lane_addr + cg * 32, rd);
                 tmem_ld_wait();
-                uint32_t pk[16], dk_[16];
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
                     float pv[2], dsv[2];
@@ -490,40 +541,37 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     pk[i >> 1] = pack2(pv[0], pv[1]);
                     dk_[i >> 1] = pack2(dsv[0], dsv[1]);
                 }
+            }
+            if (it > 0) {
+                // previous iteration's dV / dK / dQ MMAs must have retired before P^T / dS^T are overwritten
+                mbar_wait(dq_full, ph ^ 1);
+                tc_fence_after();
+            }
 #pragma unroll
-                for (int v = 0; v < 4; v++) {
-                    const int chunk = (cg & 1) * 4 + v;
-                    const int sw = (chunk ^ (key_t & 7)) << 4;
-                    *reinterpret_cast<uint4*>(sP + sw) = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
-                    *reinterpret_cast<uint4*>(sDS + sw) = make_uint4(dk_[4 * v], dk_[4 * v + 1], dk_[4 * v + 2], dk_[4 * v + 3]);
-                }
+            for (int v = 0; v < 4; v++) {
+                const int chunk = (cg & 1) * 4 + v;
+                const int sw = (chunk ^ (key_t & 7)) << 4;
+                *reinterpret_cast<uint4*>(sP + sw) = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+                *reinterpret_cast<uint4*>(sDS + sw) = make_uint4(dk_[4 * v], dk_[4 * v + 1], dk_[4 * v + 2], dk_[4 * v + 3]);
             }
             tc_fence_before();
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(pds_full);
-            // dQ_i tile: TMEM lane = query row, this thread owns columns cg*16 .. +15
-            mbar_wait(dq_full, ph);           // dV / dK (/ dQ) MMAs of this iteration retired: P^T, dS^T smem reusable
+            if (WITH_DQ && it > 0) drain_dq(q0 - BQ);   // off the critical path: the MMA warp is issuing S^T/dP^T of it+1
+            ph ^= 1;
+        }
+        if (n_it > 0) {
+            mbar_wait(dq_full, ph ^ 1);           // last iteration's MMAs
             tc_fence_after();
             if (WITH_DQ) {
-                uint32_t r[16];
-                tmem_ld16(tdQ + lane_addr + cg * 16, r);
-                tmem_ld_wait();
-                const int qrow = q0 + key_t;                           // (lane index now means query row)
-                if (qrow < p.Sq) {
-                    float* dst = p.dq_acc + b * p.dqa_b + (long long)qrow * p.dqa_r + h * D + cg * 16;
-#pragma unroll
-                    for (int v = 0; v < 4; v++)
-                        red_add_v4(dst + v * 4, __uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
-                                   __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+                if (DQ_MODE == 2) {
+                    if (ctid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    asm volatile("bar.sync 1, 512;" ::: "memory");
                 }
+                drain_dq((i0 + n_it - 1) * BQ);
+                if (DQ_MODE == 2 && ctid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             }
-            if (WITH_DQ) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(dq_empty);
-            }
-            ph ^= 1;
         }
         // epilogue: warps 2..9 write dK (two 16-column groups that form RoPE pairs d, d+32), warps 10..17 write dV
         // (32 columns each).  TMEM loads are warp-collective: every lane executes them, only the stores are predicated.
@@ -886,24 +934,29 @@ extern "C" int b200_attn_causal_bwd_tc(const void* q, const void* k, const void*
     p.dqa_b = (long long)Sq * W; p.dqa_r = W;
     p.rope_cos = (const bf16*)rope_cos; p.rope_sin = (const bf16*)rope_sin;
     p.n_heads = n_heads; p.Sq = Sq; p.Sk = Sk; p.scale = scale;
-    static int use_atomics = -1;
-    if (use_atomics < 0) {
-        // default: dQ accumulated with red.global.add.v4.f32 inside the dK/dV kernel (measured 0.68 ms per layer at
-        // B=8,S=2048 vs 0.73 ms for the atomic-free two-kernel variant, B200_ATTN_BWD_ATOMIC_DQ=0)
-        const char* e = getenv("B200_ATTN_BWD_ATOMIC_DQ");
-        use_atomics = (e && e[0] == '0') ? 0 : 1;
+    static int dq_mode = -1;
+    if (dq_mode < 0) {
+        // B200_ATTN_BWD_DQ = tma (default): dQ tiles added into the fp32 accumulator by the TMA unit
+        //                    red          : per-lane red.global.add.v4.f32
+        //                    split        : atomic-free, dQ recomputed by a second kernel
+        const char* e = getenv("B200_ATTN_BWD_DQ");
+        dq_mode = (e && !strcmp(e, "red")) ? 1 : (e && !strcmp(e, "split")) ? 0 : 2;
     }
     static bool configured = false;
     if (!configured) {
-        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
-        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
+        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
+        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
+        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
         B200_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ_BYTES), "attn_bwd_dq smem");
         configured = true;
     }
     dim3 grid((Sk + BK - 1) / BK, batch * n_heads);
-    if (use_atomics) {
+    if (dq_mode) {
+        CUtensorMap tmDQ;
+        if ((rc = tc05_make_tmap_3d_f32(&tmDQ, dq_acc, W, Sq, batch, W, (long long)Sq * W, 32, BQ))) return rc;
         B200_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)batch * Sq * W * sizeof(float), stream), "attn_bwd_tc memset");
-        attn_bwd_tc05_kernel<true><<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, p);
+        if (dq_mode == 2) attn_bwd_tc05_kernel<2><<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
+        else attn_bwd_tc05_kernel<1><<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
         B200_CHECK_LAUNCH("attn_causal_bwd_tc");
         const long long rows = (long long)batch * Sq;
         long long nthr = rows * (W / 16);
@@ -913,7 +966,7 @@ extern "C" int b200_attn_causal_bwd_tc(const void* q, const void* k, const void*
                                                                 (const bf16*)rope_cos, (const bf16*)rope_sin);
         B200_CHECK_LAUNCH("attn_bwd_dq_finalize");
     } else {
-        attn_bwd_tc05_kernel<false><<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, p);
+        attn_bwd_tc05_kernel<0><<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmQ, p);
         B200_CHECK_LAUNCH("attn_causal_bwd_tc_dkv");
         DqParams dp;
         dp.lse = lse; dp.delta = delta; dp.dq = (bf16*)dq; dp.dq_b = strides[15]; dp.dq_r = strides[16];

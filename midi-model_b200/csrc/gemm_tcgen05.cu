@@ -399,20 +399,19 @@ int tc05::make_tmap_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_
 }
 
 // 3-D variant {cols, rows-per-sequence, batch}: rows outside a sequence are zero-filled (attention tiles)
-int tc05_make_tmap_3d(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t row_pitch,
-                      uint64_t batch_pitch, uint32_t box_cols, uint32_t box_rows) {
+static int make_tmap_3d_any(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const void* ptr, uint64_t cols, uint64_t rows,
+                            uint64_t batch, uint64_t row_pitch, uint64_t batch_pitch, uint32_t box_cols, uint32_t box_rows) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         b200_set_error("tmap3d: cuTensorMapEncodeTiled entry point unavailable");
         return B200_ERR_CUDA;
     }
     cuuint64_t gdim[3] = {cols, rows, batch};
-    cuuint64_t gstride[2] = {row_pitch * 2, batch_pitch * 2};
+    cuuint64_t gstride[2] = {row_pitch * esize, batch_pitch * esize};
     cuuint32_t box[3] = {box_cols, box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(tm, dt, 3, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         b200_set_error("tmap3d: cuTensorMapEncodeTiled failed (%d) ptr=%p cols=%llu rows=%llu batch=%llu pitch=%llu/%llu",
                        (int)r, ptr, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)batch,
@@ -422,7 +421,17 @@ int tc05_make_tmap_3d(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t 
     return B200_OK;
 }
 
+// bf16 [batch][rows][cols] with element pitches; box = box_cols x box_rows x 1, 128B swizzle (box_cols * 2 == 128)
+int tc05_make_tmap_3d(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t row_pitch,
+                      uint64_t batch_pitch, uint32_t box_cols, uint32_t box_rows) {
+    return make_tmap_3d_any(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, cols, rows, batch, row_pitch, batch_pitch, box_cols, box_rows);
+}
 
+// fp32 variant (box_cols * 4 == 128): target of the attention backward's dQ reduce-add
+int tc05_make_tmap_3d_f32(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t row_pitch,
+                          uint64_t batch_pitch, uint32_t box_cols, uint32_t box_rows) {
+    return make_tmap_3d_any(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ptr, cols, rows, batch, row_pitch, batch_pitch, box_cols, box_rows);
+}
 
 // ---------------------------------------------------------------------------
 // C ABI (declared in include/midi_b200.h)
