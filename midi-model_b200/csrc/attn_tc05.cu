@@ -348,11 +348,11 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     uint64_t* kv_full = bars + 0;
     uint64_t* q_full = bars + 1;      // [QS]
     uint64_t* q_empty = bars + 5;     // [QS]
-    uint64_t* s_full = bars + 9;
-    uint64_t* pds_full = bars + 10;
-    uint64_t* dq_full = bars + 11;
-    uint64_t* dq_empty = bars + 12;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    uint64_t* s_full = bars + 9;      // [2]  one per half-tile buffer (64 query columns)
+    uint64_t* pds_full = bars + 11;   // [2]
+    uint64_t* dq_full = bars + 13;
+    uint64_t* dq_empty = bars + 14;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
     float* lse_s = reinterpret_cast<float*>(smem + SB_LSE);          // [2][128]
     float* delta_s = lse_s + 256;                                      // [2][128]
 
@@ -371,7 +371,8 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmdO);
         mbar_init(kv_full, 1);
         for (int s = 0; s < QS; s++) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
-        mbar_init(s_full, 1); mbar_init(pds_full, BWD_CWARPS); mbar_init(dq_full, 1); mbar_init(dq_empty, BWD_CWARPS);
+        for (int s = 0; s < 2; s++) { mbar_init(&s_full[s], 1); mbar_init(&pds_full[s], BWD_CWARPS); }
+        mbar_init(dq_full, 1); mbar_init(dq_empty, BWD_CWARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -379,7 +380,8 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320, tdQ = tmem_base + 384;
+    // columns 0..255: two half-tile buffers, each S^T [128 keys x 64 q] | dP^T [128 x 64]
+    const uint32_t tSB = tmem_base, tdV = tmem_base + 256, tdK = tmem_base + 320, tdQ = tmem_base + 384;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -398,63 +400,69 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
     } else if (warp == 1) {
         if (lane == 0 && n_it > 0) {
-            constexpr uint32_t id_s = make_idesc(128, 128, false, false);     // S^T, dP^T
+            constexpr uint32_t id_s = make_idesc(128, 64, false, false);      // S^T, dP^T of one half tile (64 queries)
             constexpr uint32_t id_kv = make_idesc(128, 64, false, true);      // dV, dK : A K-major (smem P^T/dS^T), B MN-major
             constexpr uint32_t id_dq = make_idesc(128, 64, true, true);       // dQ     : A = dS (MN-major view of dS^T), B = K MN-major
             const uint32_t sK = smem_u32(smem + SB_K), sV = smem_u32(smem + SB_V);
             const uint32_t sP = smem_u32(smem + SB_P), sDS = smem_u32(smem + SB_DS);
             mbar_wait(kv_full, 0);
-            int stage = 0; uint32_t qphase = 0, ph = 0;
             const uint64_t dKk = make_smem_desc(sK, 16, 1024), dVk = make_smem_desc(sV, 16, 1024);   // K-major A operands
             const uint64_t dKmn = make_smem_desc(sK, 16384, 1024);                                 // MN-major B of dQ
             const uint64_t dPk = make_smem_desc(sP, 16, 1024), dDSk = make_smem_desc(sDS, 16, 1024);
             const uint64_t dDSmn = make_smem_desc(sDS, 16384, 1024);
-            auto issue_s = [&](int st) {
-                const uint32_t sQ = smem_u32(smem + SB_Q + st * 32768);
+            // The pipeline unit is a half tile: 64 queries x 128 keys.  Unit u = (tile u/2, half u&1) owns TMEM buffer
+            // u&1 and P^T/dS^T atom u&1, so S^T/dP^T of unit u+2 are produced while the math warps work on unit u+1
+            // and the tensor pipe never sits on the critical path.
+            const int n_units = 2 * n_it;
+            auto issue_s = [&](int u) {
+                const int it_ = u >> 1, hb = u & 1, st = it_ % QS;
+                if (hb == 0) mbar_wait(&q_full[st], (uint32_t)((it_ / QS) & 1));
+                const uint32_t sQ = smem_u32(smem + SB_Q + st * 32768) + hb * 8192;     // 64 query rows x 128 B
                 const uint64_t dQk = make_smem_desc(sQ, 16, 1024), dOk = make_smem_desc(sQ + 16384, 16, 1024);
+                const uint32_t tS = tSB + hb * 128, tdP = tS + 64;
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < D / 16; k++) umma_f16(tS, desc_adv(dKk, k * 32), desc_adv(dQk, k * 32), id_s, k > 0);
 #pragma unroll
                 for (int k = 0; k < D / 16; k++) umma_f16(tdP, desc_adv(dVk, k * 32), desc_adv(dOk, k * 32), id_s, k > 0);
-                umma_commit(s_full);
+                umma_commit(&s_full[hb]);
             };
-            mbar_wait(&q_full[0], 0);
             issue_s(0);
-            for (int it = 0; it < n_it; it++) {
-                const int st_cur = stage;
+            issue_s(1);
+            for (int u = 0; u < n_units; u++) {
+                const int it = u >> 1, hb = u & 1, st_cur = it % QS;
                 const uint32_t sQ = smem_u32(smem + SB_Q + st_cur * 32768);
                 const uint64_t dQmn = make_smem_desc(sQ, 16384, 1024), dOmn = make_smem_desc(sQ + 16384, 16384, 1024);
-                mbar_wait(pds_full, ph);          // P^T, dS^T of this iteration are in shared memory; S^T/dP^T TMEM is free
-                if (++stage == QS) { stage = 0; qphase ^= 1; }
-                if (it + 1 < n_it) {              // next tile's S^T / dP^T first: the math warps start on it while the
-                    mbar_wait(&q_full[stage], qphase);   // tensor pipe is still busy with this tile's dV / dK / dQ
-                    issue_s(stage);
-                }
-                if (WITH_DQ) mbar_wait(dq_empty, ph ^ 1);      // previous dQ tile drained
+                mbar_wait(&pds_full[hb], (uint32_t)(it & 1));   // P^T / dS^T atom hb written; TMEM buffer hb is free
                 tc_fence_after();
 #pragma unroll
-                for (int kk = 0; kk < BQ / 16; kk++)
-                    umma_f16(tdV, desc_adv(dPk, (kk >> 2) * 16384 + (kk & 3) * 32), desc_adv(dOmn, kk * 2048), id_kv,
-                             (it > 0 || kk > 0) ? 1u : 0u);
-#pragma unroll
-                for (int kk = 0; kk < BQ / 16; kk++)
-                    umma_f16(tdK, desc_adv(dDSk, (kk >> 2) * 16384 + (kk & 3) * 32), desc_adv(dQmn, kk * 2048), id_kv,
-                             (it > 0 || kk > 0) ? 1u : 0u);
-                if (WITH_DQ) {
-#pragma unroll
-                    for (int kk = 0; kk < BK / 16; kk++)   // K dimension = keys: 16 key rows per step
-                        umma_f16(tdQ, desc_adv(dDSmn, kk * 2048), desc_adv(dKmn, kk * 2048), id_dq, kk > 0);
+                for (int k4 = 0; k4 < 4; k4++) {
+                    const int kk = hb * 4 + k4;                // 16 query rows per step, this half = steps 4*hb .. +3
+                    umma_f16(tdV, desc_adv(dPk, hb * 16384 + k4 * 32), desc_adv(dOmn, kk * 2048), id_kv, (u > 0 || k4 > 0) ? 1u : 0u);
                 }
-                umma_commit(dq_full);
-                umma_commit(&q_empty[st_cur]);
-                ph ^= 1;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; k4++) {
+                    const int kk = hb * 4 + k4;
+                    umma_f16(tdK, desc_adv(dDSk, hb * 16384 + k4 * 32), desc_adv(dQmn, kk * 2048), id_kv, (u > 0 || k4 > 0) ? 1u : 0u);
+                }
+                if (hb == 1) {
+                    if (WITH_DQ) {
+                        mbar_wait(dq_empty, (uint32_t)((it & 1) ^ 1));      // previous dQ tile drained
+                        tc_fence_after();
+#pragma unroll
+                        for (int kk = 0; kk < BK / 16; kk++)   // K dimension = keys: 16 key rows per step
+                            umma_f16(tdQ, desc_adv(dDSmn, kk * 2048), desc_adv(dKmn, kk * 2048), id_dq, kk > 0);
+                    }
+                    umma_commit(dq_full);
+                    umma_commit(&q_empty[st_cur]);
+                }
+                if (u + 2 < n_units) issue_s(u + 2);           // two units ahead: not urgent, goes after this unit's dV/dK/dQ
             }
         }
     } else {
         const int cw = warp - 2;                       // 0..15
         const int quarter = warp & 3;
-        const int cg = cw >> 2;                        // which 32 query columns of the tile this thread handles
+        const int cg = cw >> 2;                        // which 16 query columns of the half tile this thread handles
         const int key_t = quarter * 32 + lane;         // key row inside the tile == TMEM lane
         const int key = k0 + key_t;
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
@@ -462,9 +470,8 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int ctid = threadIdx.x - 64;             // 0..511
         const float* lse_g = p.lse + ((long long)b * p.n_heads + h) * p.Sq;
         const float* delta_g = p.delta + ((long long)b * p.n_heads + h) * p.Sq;
-        uint8_t* sP = smem + SB_P + (cg >> 1) * 16384 + key_t * 128;
-        uint8_t* sDS = smem + SB_DS + (cg >> 1) * 16384 + key_t * 128;
-        uint32_t ph = 0;
+        uint8_t* sP = smem + SB_P + key_t * 128;
+        uint8_t* sDS = smem + SB_DS + key_t * 128;
         // lse / delta of the query tile: one value per thread of the first 8 compute warps, fetched one iteration
         // ahead so the global load latency hides behind the previous iteration
         auto fetch_ld = [&](int it_) -> float {
@@ -513,56 +520,58 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             ld_next = fetch_ld(it + 1);
             if (DQ_MODE == 2 && ctid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             asm volatile("bar.sync 1, 512;" ::: "memory");
-            const float* lse_t = lse_s + (it & 1) * 128 + cg * 32;
-            const float* delta_t = delta_s + (it & 1) * 128 + cg * 32;
             const bool need_mask = (k0 + BK - 1 > q0 + off) || (k0 + BK > p.Sk) || (q0 + BQ > p.Sq);
-            mbar_wait(s_full, ph);
-            tc_fence_after();
-            uint32_t pk[16], dk_[16];
-            {
-                uint32_t rs[32], rd[32];
-                tmem_ld32(tS + lane_addr + cg * 32, rs);
-                tmem_ld32(tdP + lane_addr + cg * 32, rd);
-                tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float pv[2], dsv[2];
-#pragma unroll
-                    for (int e = 0; e < 2; e++) {
-                        const int qq = i + e;
-                        float pr = ex2_approx(fmaf(__uint_as_float(rs[qq]), sl2, -lse_t[qq]));
-                        if (need_mask) {
-                            const int qrow = q0 + cg * 32 + qq;
-                            if (key > qrow + off || key >= p.Sk || qrow >= p.Sq) pr = 0.f;
-                        }
-                        pv[e] = pr;
-                        dsv[e] = pr * (__uint_as_float(rd[qq]) - delta_t[qq]);
-                    }
-                    pk[i >> 1] = pack2(pv[0], pv[1]);
-                    dk_[i >> 1] = pack2(dsv[0], dsv[1]);
-                }
-            }
-            if (it > 0) {
-                // previous iteration's dV / dK / dQ MMAs must have retired before P^T / dS^T are overwritten
-                mbar_wait(dq_full, ph ^ 1);
+            for (int hb = 0; hb < 2; hb++) {
+                const int qc0 = hb * 64 + cg * 16;             // first query column (inside the tile) of this thread
+                const float* lse_t = lse_s + (it & 1) * 128 + qc0;
+                const float* delta_t = delta_s + (it & 1) * 128 + qc0;
+                mbar_wait(&s_full[hb], (uint32_t)(it & 1));
                 tc_fence_after();
-            }
+                uint32_t pk[8], dk_[8];
+                {
+                    uint32_t rs[16], rd[16];
+                    tmem_ld16(tSB + hb * 128 + lane_addr + cg * 16, rs);
+                    tmem_ld16(tSB + hb * 128 + 64 + lane_addr + cg * 16, rd);
+                    tmem_ld_wait();
 #pragma unroll
-            for (int v = 0; v < 4; v++) {
-                const int chunk = (cg & 1) * 4 + v;
-                const int sw = (chunk ^ (key_t & 7)) << 4;
-                *reinterpret_cast<uint4*>(sP + sw) = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
-                *reinterpret_cast<uint4*>(sDS + sw) = make_uint4(dk_[4 * v], dk_[4 * v + 1], dk_[4 * v + 2], dk_[4 * v + 3]);
+                    for (int i = 0; i < 16; i += 2) {
+                        float pv[2], dsv[2];
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const int qq = i + e;
+                            float pr = ex2_approx(fmaf(__uint_as_float(rs[qq]), sl2, -lse_t[qq]));
+                            if (need_mask) {
+                                const int qrow = q0 + qc0 + qq;
+                                if (key > qrow + off || key >= p.Sk || qrow >= p.Sq) pr = 0.f;
+                            }
+                            pv[e] = pr;
+                            dsv[e] = pr * (__uint_as_float(rd[qq]) - delta_t[qq]);
+                        }
+                        pk[i >> 1] = pack2(pv[0], pv[1]);
+                        dk_[i >> 1] = pack2(dsv[0], dsv[1]);
+                    }
+                }
+                if (it > 0) {
+                    // the previous tile's dV / dK / dQ MMAs read both atoms: they must have retired before the overwrite
+                    mbar_wait(dq_full, (uint32_t)((it & 1) ^ 1));
+                    tc_fence_after();
+                }
+#pragma unroll
+                for (int v = 0; v < 2; v++) {
+                    const int sw = hb * 16384 + (((cg * 2 + v) ^ (key_t & 7)) << 4);
+                    *reinterpret_cast<uint4*>(sP + sw) = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+                    *reinterpret_cast<uint4*>(sDS + sw) = make_uint4(dk_[4 * v], dk_[4 * v + 1], dk_[4 * v + 2], dk_[4 * v + 3]);
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&pds_full[hb]);
+                if (WITH_DQ && hb == 0 && it > 0) drain_dq(q0 - BQ);   // off the critical path
             }
-            tc_fence_before();
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(pds_full);
-            if (WITH_DQ && it > 0) drain_dq(q0 - BQ);   // off the critical path: the MMA warp is issuing S^T/dP^T of it+1
-            ph ^= 1;
         }
         if (n_it > 0) {
-            mbar_wait(dq_full, ph ^ 1);           // last iteration's MMAs
+            mbar_wait(dq_full, (uint32_t)((n_it - 1) & 1));   // last tile's MMAs
             tc_fence_after();
             if (WITH_DQ) {
                 if (DQ_MODE == 2) {
