@@ -131,8 +131,8 @@ flash_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const b
                  float* __restrict__ lse, Strides sq, Strides sk, Strides sv, Strides so, int n_heads, int Sq, int Sk,
                  float scale) {
     __shared__ __align__(128) uint8_t smem[8192 * 5];   // Q | K0 | V0 | K1 | V1
-    const int qt = gridDim.x - 1 - blockIdx.x;           // heavy (late) tiles first
-    const int bh = blockIdx.y;
+    const int qt = gridDim.y - 1 - blockIdx.y;           // heavy (late) tiles first
+    const int bh = blockIdx.x;
     const int b = bh / n_heads, h = bh % n_heads;
     const int off = Sk - Sq;
     const int q0 = qt * BM;
@@ -307,8 +307,8 @@ flash_bwd_dkv_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, con
     extern __shared__ __align__(128) uint8_t smem[];    // K | V | Q0 | dO0 | Q1 | dO1 | lse[2][64] | delta[2][64]
     float (*s_lse)[BM] = reinterpret_cast<float (*)[BM]>(smem + 8192 * 6);
     float (*s_delta)[BM] = reinterpret_cast<float (*)[BM]>(smem + 8192 * 6 + 2 * BM * 4);
-    const int kt = blockIdx.x;
-    const int bh = blockIdx.y;
+    const int kt = blockIdx.y;       // slow grid index: all heavy (early-key) tiles are scheduled first
+    const int bh = blockIdx.x;
     const int b = bh / n_heads, h = bh % n_heads;
     const int off = Sk - Sq;
     const int k0 = kt * BN;
@@ -434,8 +434,8 @@ flash_bwd_dq_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, cons
                     bf16* __restrict__ dq, Strides sq, Strides sk, Strides sv, Strides sdo, Strides sdq, int n_heads,
                     int Sq, int Sk, float scale, const bf16* __restrict__ rope_cos, const bf16* __restrict__ rope_sin) {
     extern __shared__ __align__(128) uint8_t smem[];    // Q | dO | K0 | V0 | K1 | V1
-    const int qt = gridDim.x - 1 - blockIdx.x;
-    const int bh = blockIdx.y;
+    const int qt = gridDim.y - 1 - blockIdx.y;
+    const int bh = blockIdx.x;
     const int b = bh / n_heads, h = bh % n_heads;
     const int off = Sk - Sq;
     const int q0 = qt * BM;
@@ -556,7 +556,7 @@ extern "C" int b200_attn_causal_fwd(const void* q, const void* k, const void* v,
                                        cudaSharedmemCarveoutMaxShared), "attn carveout");
         configured = true;
     }
-    dim3 grid((Sq + BM - 1) / BM, batch * n_heads);
+    dim3 grid(batch * n_heads, (Sq + BM - 1) / BM);   // tiles on the slow index: longest first across all heads
     flash_fwd_kernel<<<grid, NT, 0, stream>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)o, lse, s[0], s[1],
                                              s[2], s[3], n_heads, Sq, Sk, scale);
     B200_CHECK_LAUNCH("attn_causal_fwd");
@@ -598,12 +598,12 @@ extern "C" int b200_attn_causal_bwd(const void* q, const void* k, const void* v,
                                        cudaSharedmemCarveoutMaxShared), "attn carveout");
         configured = true;
     }
-    dim3 gkv((Sk + BN - 1) / BN, batch * n_heads);
+    dim3 gkv(batch * n_heads, (Sk + BN - 1) / BN);   // tiles on the slow index: longest first across all heads
     flash_bwd_dkv_kernel<<<gkv, NT, SMEM_BWD, stream>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (const bf16*)d_o, lse, delta,
                                                  (bf16*)dk, (bf16*)dv, s[0], s[1], s[2], s[4], s[6], s[7], n_heads, Sq, Sk,
                                                  scale, (const bf16*)rope_cos, (const bf16*)rope_sin);
     B200_CHECK_LAUNCH("attn_causal_bwd_dkv");
-    dim3 gq((Sq + BM - 1) / BM, batch * n_heads);
+    dim3 gq(batch * n_heads, (Sq + BM - 1) / BM);   // tiles on the slow index: longest first across all heads
     flash_bwd_dq_kernel<<<gq, NT, SMEM_BWD, stream>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (const bf16*)d_o, lse, delta,
                                                (bf16*)dq, s[0], s[1], s[2], s[4], s[5], n_heads, Sq, Sk, scale,
                                                (const bf16*)rope_cos, (const bf16*)rope_sin);

@@ -64,8 +64,8 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qt = gridDim.x - 1 - blockIdx.x;     // long (late) tiles first
-    const int bh = blockIdx.y;
+    const int qt = gridDim.y - 1 - blockIdx.y;     // long (late) tiles first
+    const int bh = blockIdx.x;
     const int b = bh / p.n_heads, h = bh % p.n_heads;
     const int q0 = qt * BQ;
     const int off = p.Sk - p.Sq;
@@ -245,6 +245,219 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// forward, second generation: one CTA per SM, 16 softmax warps (thread = query row x 32 of the 128 keys of a tile),
+// S double-buffered in TMEM so the tensor pipe runs one tile ahead of the math, P double-buffered in shared memory,
+// P.V tiles double-buffered in TMEM and folded into register accumulators one tile late.  Only the row maximum is
+// exchanged between the four column slices of a row (4 KB of shared memory, one 128-thread named barrier per tile);
+// row sums stay per-slice until the end.
+// ---------------------------------------------------------------------------------------------
+constexpr int F2_CWARPS = 16;
+constexpr int F2_THREADS = 64 + 32 * F2_CWARPS;
+constexpr int F2_KVS = 4;                                 // K/V stages: S runs two tiles ahead of P.V, TMA latency needs one more
+constexpr int F2_Q = 0;                                   // 16 KB
+constexpr int F2_KV = 16384;                              // F2_KVS x (K 16 KB + V 16 KB)
+constexpr int F2_P = F2_KV + F2_KVS * 32768;              // 2 x 32 KB
+constexpr int F2_MX = F2_P + 2 * 32768;                   // float [2][4][128] row-max exchange, then [4][128] row sums
+constexpr int F2_BAR = F2_MX + 4096;
+constexpr int F2_SMEM = F2_BAR + 256;
+
+__global__ void __launch_bounds__(F2_THREADS, 1)
+attn_fwd_tc05_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F2_BAR);
+    uint64_t* q_full = bars + 0;
+    uint64_t* kv_full = bars + 1;     // [F2_KVS]
+    uint64_t* kv_empty = bars + 5;    // [F2_KVS]
+    uint64_t* s_full = bars + 9;      // [2]
+    uint64_t* p_full = bars + 11;     // [2]
+    uint64_t* pv_full = bars + 13;    // [2]
+    uint64_t* pv_empty = bars + 15;   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+    float* mx_s = reinterpret_cast<float*>(smem + F2_MX);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = gridDim.y - 1 - blockIdx.y;     // long (late) tiles first
+    const int bh = blockIdx.x;
+    const int b = bh / p.n_heads, h = bh % p.n_heads;
+    const int q0 = qt * BQ;
+    const int off = p.Sk - p.Sq;
+    int n_kv = min((p.Sk + BK - 1) / BK, (q0 + BQ - 1 + off) / BK + 1);
+    if (n_kv < 1) n_kv = 1;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < F2_KVS; s++) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&s_full[s], 1); mbar_init(&p_full[s], F2_CWARPS); mbar_init(&pv_full[s], 1); mbar_init(&pv_empty[s], F2_CWARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tS = tmem_base /* 2 x 128 columns */, tPV = tmem_base + 256 /* 2 x 64 columns */;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(q_full, BQ * D * 2);
+            tma_load_3d(smem + F2_Q, &tmQ, q_full, p.q_col0 + h * D, q0, b);
+            int stage = 0; uint32_t phase = 0;
+            for (int j = 0; j < n_kv; j++) {
+                mbar_wait(&kv_empty[stage], phase ^ 1);
+                uint8_t* sK = smem + F2_KV + stage * 32768;
+                mbar_expect_tx(&kv_full[stage], 2 * BK * D * 2);
+                tma_load_3d(sK, &tmK, &kv_full[stage], p.k_col0 + h * D, j * BK, b);
+                tma_load_3d(sK + 16384, &tmV, &kv_full[stage], p.v_col0 + h * D, j * BK, b);
+                if (++stage == F2_KVS) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc(BQ, BK, false, false);    // S[128 x 128] = Q . K^T
+            constexpr uint32_t idesc_pv = make_idesc(BQ, D, false, true);     // PV[128 x 64] = P . V (V is [keys, d]: MN-major B)
+            const uint32_t sQ = smem_u32(smem + F2_Q), sP = smem_u32(smem + F2_P);
+            mbar_wait(q_full, 0);
+            const uint64_t dQ0 = make_smem_desc(sQ, 16, 1024);
+            auto issue_s = [&](int j) {
+                const int st = j % F2_KVS;
+                mbar_wait(&kv_full[st], (uint32_t)((j / F2_KVS) & 1));
+                const uint64_t dK0 = make_smem_desc(smem_u32(smem + F2_KV + st * 32768), 16, 1024);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < D / 16; k++)
+                    umma_f16(tS + (j & 1) * 128, desc_adv(dQ0, k * 32), desc_adv(dK0, k * 32), idesc_s, k > 0);
+                umma_commit(&s_full[j & 1]);
+            };
+            issue_s(0);
+            if (n_kv > 1) issue_s(1);
+            for (int j = 0; j < n_kv; j++) {
+                const int bb = j & 1, st = j % F2_KVS;
+                const uint32_t par = (uint32_t)((j >> 1) & 1);
+                const uint64_t dP0 = make_smem_desc(sP + bb * 32768, 16, 1024);
+                const uint64_t dV0 = make_smem_desc(smem_u32(smem + F2_KV + st * 32768 + 16384), 16384, 1024);
+                mbar_wait(&p_full[bb], par);          // P_j written, S_j consumed
+                mbar_wait(&pv_empty[bb], par ^ 1);    // P.V tile j-2 folded into the register accumulators
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < BK / 16; kk++)
+                    umma_f16(tPV + bb * 64, desc_adv(dP0, (kk >> 2) * 16384 + (kk & 3) * 32), desc_adv(dV0, kk * 2048), idesc_pv, kk > 0);
+                umma_commit(&pv_full[bb]);
+                umma_commit(&kv_empty[st]);
+                if (j + 2 < n_kv) issue_s(j + 2);     // into the S buffer the math warps have just released
+            }
+        }
+    } else {
+        const int cw = warp - 2;
+        const int quarter = warp & 3;
+        const int cg = cw >> 2;                           // key slice: columns cg*32 .. +31 of the tile; d slice cg*16 .. +15 of P.V
+        const int row_t = quarter * 32 + lane;            // row inside the tile == TMEM lane
+        const int row = q0 + row_t;
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        const float sl2 = p.scale * LOG2E;
+        float m_i = -INFINITY, l_part = 0.f, alpha_prev = 0.f;
+        float o[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) o[i] = 0.f;
+        auto fold_pv = [&](int j, float alpha) {          // o = o * alpha_j + (P.V)_j for this thread's 16 columns
+            const int bb = j & 1;
+            mbar_wait(&pv_full[bb], (uint32_t)((j >> 1) & 1));
+            tc_fence_after();
+            uint32_t r[16];
+            tmem_ld16(tPV + bb * 64 + lane_addr + cg * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; i++) o[i] = fmaf(o[i], alpha, __uint_as_float(r[i]));
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&pv_empty[bb]);
+        };
+        for (int j = 0; j < n_kv; j++) {
+            const int k0 = j * BK, bb = j & 1;
+            const bool need_mask = (k0 + BK - 1 > q0 + off) || (k0 + BK > p.Sk);
+            mbar_wait(&s_full[bb], (uint32_t)((j >> 1) & 1));
+            tc_fence_after();
+            float sv[32];
+            {
+                uint32_t r[32];
+                tmem_ld32(tS + bb * 128 + lane_addr + cg * 32, r);
+                tmem_ld_wait();
+                if (need_mask) {      // diagonal / ragged tiles only: a real (warp-uniform) branch, not predication
+                    const int lim = min(row + off, p.Sk - 1) - (k0 + cg * 32);     // last visible column of this slice
+#pragma unroll
+                    for (int i = 0; i < 32; i++) sv[i] = (i > lim) ? -INFINITY : __uint_as_float(r[i]);
+                    asm volatile("" ::: "memory");
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i++) sv[i] = __uint_as_float(r[i]);
+                }
+            }
+            float mx4[4] = {sv[0], sv[1], sv[2], sv[3]};
+#pragma unroll
+            for (int i = 4; i < 32; i++) mx4[i & 3] = fmaxf(mx4[i & 3], sv[i]);
+            float* mxp = mx_s + bb * 512 + row_t;
+            mxp[cg * 128] = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");     // the four slices of this row quarter
+            const float mx = fmaxf(fmaxf(m_i, fmaxf(mxp[0], mxp[128])), fmaxf(mxp[256], mxp[384]));
+            const float msc = (mx == -INFINITY) ? 0.f : mx * sl2;
+            const float alpha = (m_i == -INFINITY) ? 0.f : exp2f(m_i * sl2 - msc);
+            m_i = mx;
+            uint32_t pk[16];
+            float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+                const float p0 = ex2_approx(fmaf(sv[i], sl2, -msc)), p1 = ex2_approx(fmaf(sv[i + 1], sl2, -msc));
+                rs4[(i >> 1) & 3] += p0 + p1;
+                pk[i >> 1] = pack2(p0, p1);
+            }
+            l_part = fmaf(l_part, alpha, (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
+            // keys cg*32 .. +31 of this row: atom (cg >> 1), 16-byte chunks (cg & 1) * 4 .. + 3.  Buffer bb was last read by
+            // the P.V MMAs of tile j-2, whose completion this thread saw in fold_pv(j-2) during tile j-1.
+            uint8_t* rowp = smem + F2_P + bb * 32768 + (cg >> 1) * 16384 + row_t * 128;
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const int chunk = (cg & 1) * 4 + v;
+                *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row_t & 7)) << 4)) =
+                    make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[bb]);
+            if (j > 0) fold_pv(j - 1, alpha_prev);
+            alpha_prev = alpha;
+        }
+        fold_pv(n_kv - 1, alpha_prev);
+        // total row sum: the four slices of a row meet in shared memory
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");         // everyone is done with mx_s
+        mx_s[cg * 128 + row_t] = l_part;
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
+        const float l_i = (mx_s[row_t] + mx_s[128 + row_t]) + (mx_s[256 + row_t] + mx_s[384 + row_t]);
+        if (row < p.Sq) {
+            const float inv = l_i > 0.f ? 1.f / l_i : 0.f;
+            bf16* dst = p.o + b * p.o_b + (long long)row * p.o_r + h * D + cg * 16;
+#pragma unroll
+            for (int v = 0; v < 2; v++) {
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) f[i] = o[v * 8 + i] * inv;
+                *reinterpret_cast<uint4*>(dst + v * 8) = pack8(f);
+            }
+            if (p.lse && cg == 0) p.lse[((long long)b * p.n_heads + h) * p.Sq + row] = m_i * p.scale + logf(l_i);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
 }   // namespace
 
 // 3-D bf16 tensor map {cols, rows per sequence, batch} with 128B swizzle: rows outside a sequence are zero-filled
@@ -273,15 +486,19 @@ extern "C" int b200_attn_causal_fwd_tc(const void* q, const void* k, const void*
     p.n_heads = n_heads; p.Sq = Sq; p.Sk = Sk; p.H = (int)W;
     p.q_col0 = p.k_col0 = p.v_col0 = 0;
     p.scale = scale;
-    static bool configured = false;
-    if (!configured) {
+    static int gen = 0;
+    if (!gen) {
+        // B200_ATTN_FWD_TC=v1 selects the first-generation kernel (4 softmax warps, 2 CTAs per SM)
+        const char* e = getenv("B200_ATTN_FWD_TC");
+        gen = (e && !strcmp(e, "v1")) ? 1 : 2;
         B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES), "attn_tc smem");
         B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc05_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                        cudaSharedmemCarveoutMaxShared), "attn_tc carveout");
-        configured = true;
+        B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc05_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM), "attn_tc v2 smem");
     }
-    dim3 grid((Sq + BQ - 1) / BQ, batch * n_heads);
-    attn_fwd_tc05_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+    dim3 grid(batch * n_heads, (Sq + BQ - 1) / BQ);   // tiles on the slow index: longest first across all heads
+    if (gen == 2) attn_fwd_tc05_v2_kernel<<<grid, F2_THREADS, F2_SMEM, stream>>>(tmQ, tmK, tmV, p);
+    else attn_fwd_tc05_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
     B200_CHECK_LAUNCH("attn_causal_fwd_tc");
     return B200_OK;
 }
@@ -357,8 +574,8 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     float* delta_s = lse_s + 256;                                      // [2][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kt = blockIdx.x;
-    const int bh = blockIdx.y;
+    const int kt = blockIdx.y;       // slow grid index: all heavy (early-key) tiles are scheduled first
+    const int bh = blockIdx.x;
     const int b = bh / p.n_heads, h = bh % p.n_heads;
     const int k0 = kt * BK;
     const int off = p.Sk - p.Sq;
@@ -534,22 +751,39 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     tmem_ld16(tSB + hb * 128 + lane_addr + cg * 16, rs);
                     tmem_ld16(tSB + hb * 128 + 64 + lane_addr + cg * 16, rd);
                     tmem_ld_wait();
+                    if (need_mask) {
+                        // column qq of this thread is visible iff key <= q0+qc0+qq+off, key < Sk and q0+qc0+qq < Sq
+                        const int lo = (key < p.Sk) ? key - off - q0 - qc0 : 1 << 20;     // first visible column
+                        const int hi = p.Sq - q0 - qc0;                                     // first column past the end
 #pragma unroll
-                    for (int i = 0; i < 16; i += 2) {
-                        float pv[2], dsv[2];
+                        for (int i = 0; i < 16; i += 2) {
+                            float pv[2], dsv[2];
 #pragma unroll
-                        for (int e = 0; e < 2; e++) {
-                            const int qq = i + e;
-                            float pr = ex2_approx(fmaf(__uint_as_float(rs[qq]), sl2, -lse_t[qq]));
-                            if (need_mask) {
-                                const int qrow = q0 + qc0 + qq;
-                                if (key > qrow + off || key >= p.Sk || qrow >= p.Sq) pr = 0.f;
+                            for (int e = 0; e < 2; e++) {
+                                const int qq = i + e;
+                                float pr = ex2_approx(fmaf(__uint_as_float(rs[qq]), sl2, -lse_t[qq]));
+                                if (qq < lo || qq >= hi) pr = 0.f;
+                                pv[e] = pr;
+                                dsv[e] = pr * (__uint_as_float(rd[qq]) - delta_t[qq]);
                             }
-                            pv[e] = pr;
-                            dsv[e] = pr * (__uint_as_float(rd[qq]) - delta_t[qq]);
+                            pk[i >> 1] = pack2(pv[0], pv[1]);
+                            dk_[i >> 1] = pack2(dsv[0], dsv[1]);
                         }
-                        pk[i >> 1] = pack2(pv[0], pv[1]);
-                        dk_[i >> 1] = pack2(dsv[0], dsv[1]);
+                        asm volatile("" ::: "memory");
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 2) {
+                            float pv[2], dsv[2];
+#pragma unroll
+                            for (int e = 0; e < 2; e++) {
+                                const int qq = i + e;
+                                const float pr = ex2_approx(fmaf(__uint_as_float(rs[qq]), sl2, -lse_t[qq]));
+                                pv[e] = pr;
+                                dsv[e] = pr * (__uint_as_float(rd[qq]) - delta_t[qq]);
+                            }
+                            pk[i >> 1] = pack2(pv[0], pv[1]);
+                            dk_[i >> 1] = pack2(dsv[0], dsv[1]);
+                        }
                     }
                 }
                 if (it > 0) {
@@ -681,8 +915,8 @@ attn_bwd_dq_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qt = gridDim.x - 1 - blockIdx.x;       // long tiles first
-    const int bh = blockIdx.y;
+    const int qt = gridDim.y - 1 - blockIdx.y;       // long tiles first
+    const int bh = blockIdx.x;
     const int b = bh / p.n_heads, h = bh % p.n_heads;
     const int q0 = qt * BQ;
     const int off = p.Sk - p.Sq;
@@ -959,7 +1193,7 @@ extern "C" int b200_attn_causal_bwd_tc(const void* q, const void* k, const void*
         B200_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ_BYTES), "attn_bwd_dq smem");
         configured = true;
     }
-    dim3 grid((Sk + BK - 1) / BK, batch * n_heads);
+    dim3 grid(batch * n_heads, (Sk + BK - 1) / BK);   // tiles on the slow index: longest first across all heads
     if (dq_mode) {
         CUtensorMap tmDQ;
         if ((rc = tc05_make_tmap_3d_f32(&tmDQ, dq_acc, W, Sq, batch, W, (long long)Sq * W, 32, BQ))) return rc;
@@ -982,7 +1216,7 @@ extern "C" int b200_attn_causal_bwd_tc(const void* q, const void* k, const void*
         dp.rope_cos = (const bf16*)rope_cos; dp.rope_sin = (const bf16*)rope_sin;
         dp.n_heads = n_heads; dp.Sq = Sq; dp.Sk = Sk; dp.scale = scale;
         dp.dbg = g_attn_dbg;
-        dim3 gq((Sq + BQ - 1) / BQ, batch * n_heads);
+        dim3 gq(batch * n_heads, (Sq + BQ - 1) / BQ);   // tiles on the slow index: longest first across all heads
         attn_bwd_dq_tc05_kernel<<<gq, BWD_THREADS, SMEM_DQ_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, dp);
         B200_CHECK_LAUNCH("attn_causal_bwd_tc_dq");
     }

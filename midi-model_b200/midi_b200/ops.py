@@ -231,7 +231,7 @@ def _strides_packed(S: int, H: int, D: int, col0: int, ld: int):
 import os as _os
 
 # "tc" = tcgen05 / TMEM / TMA kernel (csrc/attn_tc05.cu); "mma" = mma.sync kernel (csrc/attn_flash.cu)
-ATTN_FWD_IMPL = _os.environ.get("B200_ATTN_FWD", "mma")
+ATTN_FWD_IMPL = _os.environ.get("B200_ATTN_FWD", "tc")
 ATTN_BWD_IMPL = _os.environ.get("B200_ATTN_BWD", "tc")
 
 
