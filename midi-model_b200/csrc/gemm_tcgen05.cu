@@ -30,6 +30,7 @@ struct GemmParams {
     int M, N, K;
     int ldc, ldr;
     int epilogue;
+    int tma_store;             // EPI_STORE only: bf16 tile staged in shared memory and written with cp.async.bulk.tensor
     int splits, kb_per_split, num_kb;
     int m_tiles, n_tiles;
     uint32_t mn_lbo, mn_sbo;   // MN-major descriptor byte offsets (overridable for bring-up)
@@ -50,20 +51,23 @@ struct SmemLayout {
     static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;   // 16/32 KB
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+    static constexpr int OUT_BYTES = 2 * BLOCK_M * 64 * 2;  // two [128 rows x 128 B] staging boxes for the TMA-store epilogue
     static constexpr int BAR_BYTES = 1024;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024 for manual alignment
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES + 1024;   // +1024 for manual alignment
 };
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
     using L = SmemLayout<BLOCK_N>;
     constexpr int STAGES = L::STAGES;
     constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;   // double-buffered accumulator (256 or 512 columns)
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* bar_base = smem + STAGES * L::STAGE_BYTES;
+    uint8_t* out_stage = smem + STAGES * L::STAGE_BYTES;         // 1024-aligned: STAGE_BYTES is a multiple of 16 KB
+    uint8_t* bar_base = out_stage + L::OUT_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
@@ -171,7 +175,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     } else {
         // ===================== epilogue warps =====================
         const int quarter = warp & 3;               // TMEM lane quarter this warp may access
-        int acc = 0;
+        int acc = 0, out_buf = 0;
         uint32_t acc_phase = 0;
         for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
             const int split = item % p.splits;
@@ -261,6 +265,42 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         }
                     }
                 }
+            } else if (p.tma_store) {
+                // plain bf16 store: row-per-thread 16-byte global stores touch 32 different rows per instruction and
+                // made the epilogue longer than a K=1024 main loop (tensor pipe 64% busy); instead the tile goes
+                // through two 128B-swizzled [128 x 64] staging boxes and leaves with one TMA store per box.
+                const int r_t = quarter * 32 + lane;
+                const bool leader = (warp == EPI_WARP0 && lane == 0);
+#pragma unroll 1
+                for (int bx = 0; bx < BLOCK_N / 64; bx++) {
+                    const int col0 = n_blk * BLOCK_N + bx * 64;
+                    if (col0 >= p.N) break;                                   // uniform
+                    uint8_t* dst = out_stage + out_buf * (BLOCK_M * 128) + r_t * 128;
+#pragma unroll
+                    for (int hc = 0; hc < 2; hc++) {
+                        uint32_t r[32];
+                        tmem_ld32(taddr + bx * 64 + hc * 32, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int v = 0; v < 4; v++) {
+                            float f[8];
+#pragma unroll
+                            for (int j = 0; j < 8; j++) f[j] = __uint_as_float(r[8 * v + j]);
+                            *reinterpret_cast<uint4*>(dst + (((hc * 4 + v) ^ (r_t & 7)) << 4)) = pack8(f);
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    // the previous box's store has finished reading the other buffer before anyone writes it again
+                    if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (leader) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(&tmC), "r"(smem_u32(out_stage + out_buf * (BLOCK_M * 128))), "r"(col0), "r"(m_blk * BLOCK_M)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    out_buf ^= 1;
+                }
             } else
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N / 32; c++) {
@@ -304,6 +344,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (p.tma_store && warp == EPI_WARP0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 
     tc_fence_before();
@@ -336,7 +377,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, bf16* __restr
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p, cudaStream_t stream) {
     using L = SmemLayout<BLOCK_N>;
     auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN>;
     static bool configured = false;
@@ -346,7 +387,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, 
     }
     const int items = p.m_tiles * p.n_tiles * p.splits;
     const int grid = items < b200_num_sms() ? items : b200_num_sms();
-    kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, p);
+    kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, p);
     B200_CHECK_LAUNCH("gemm_tcgen05");
     return B200_OK;
 }
@@ -583,21 +624,31 @@ static int gemm_impl(const void* A, const void* B, void* C, const void* R, int M
         p.n_tiles = p.swiglu_I / 128;         // one tile = 128 gate + 128 up features
     }
 
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmC;
     int rc;
+    static int tma_store_ok = -1;
+    if (tma_store_ok < 0) {
+        const char* e = getenv("B200_GEMM_TMA_STORE");       // 0 = per-thread global stores (bring-up / A-B timing)
+        tma_store_ok = (e && e[0] == '0') ? 0 : 1;
+    }
+    p.tma_store = (p.epilogue == EPI_STORE && tma_store_ok) ? 1 : 0;
+    if (p.tma_store) {
+        if ((rc = tc05::make_tmap_2d(&tmC, C, N8, M, ldc, 64, BLOCK_M))) return rc;
+    }
     if (!a_mn_major) rc = tc05::make_tmap_2d(&tmA, A, K, M, lda, BLOCK_K, BLOCK_M);
     else             rc = tc05::make_tmap_2d(&tmA, A, M, K, lda, 64, BLOCK_K);
     if (rc) return rc;
     if (!b_mn_major) rc = tc05::make_tmap_2d(&tmB, B, K, N, ldb, BLOCK_K, swiglu ? 128 : block_n);
     else             rc = tc05::make_tmap_2d(&tmB, B, N, K, ldb, 64, BLOCK_K);
     if (rc) return rc;
+    if (!p.tma_store) tmC = tmA;      // unused by the kernel, but must be a valid map
 
 #define B200_DISPATCH(BN)                                                                   \
     do {                                                                                    \
-        if (!a_mn_major && !b_mn_major) rc = launch<BN, false, false>(tmA, tmB, p, stream);  \
-        else if (!a_mn_major && b_mn_major) rc = launch<BN, false, true>(tmA, tmB, p, stream); \
-        else if (a_mn_major && b_mn_major) rc = launch<BN, true, true>(tmA, tmB, p, stream);  \
-        else rc = launch<BN, true, false>(tmA, tmB, p, stream);                              \
+        if (!a_mn_major && !b_mn_major) rc = launch<BN, false, false>(tmA, tmB, tmC, p, stream);  \
+        else if (!a_mn_major && b_mn_major) rc = launch<BN, false, true>(tmA, tmB, tmC, p, stream); \
+        else if (a_mn_major && b_mn_major) rc = launch<BN, true, true>(tmA, tmB, tmC, p, stream);  \
+        else rc = launch<BN, true, false>(tmA, tmB, tmC, p, stream);                              \
     } while (0)
     if (block_n == 256) B200_DISPATCH(256);
     else B200_DISPATCH(128);
