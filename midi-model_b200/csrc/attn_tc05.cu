@@ -588,8 +588,8 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmdO);
         mbar_init(kv_full, 1);
         for (int s = 0; s < QS; s++) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(&s_full[s], 1); mbar_init(&pds_full[s], BWD_CWARPS); }
-        mbar_init(dq_full, 1); mbar_init(dq_empty, BWD_CWARPS);
+        for (int s = 0; s < 2; s++) { mbar_init(&s_full[s], 1); mbar_init(&pds_full[s], BWD_CWARPS / 2); }
+        mbar_init(dq_full, 1); mbar_init(dq_empty, BWD_CWARPS / 2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -677,29 +677,35 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             }
         }
     } else {
+        // Two math groups of 8 warps: group g owns half g (64 queries) of every tile, i.e. every second pipeline unit,
+        // with its own staging buffers and named barriers, so while one group waits (TMEM load, barrier, st.shared
+        // + fence) the other is in its exp2/FMA stretch.  thread = (key row, 32 of the 64 query columns).
         const int cw = warp - 2;                       // 0..15
         const int quarter = warp & 3;
-        const int cg = cw >> 2;                        // which 16 query columns of the half tile this thread handles
+        const int grp = cw >> 3;                       // math group == half tile index hb
+        const int cgi = (cw >> 2) & 1;                 // which 32 query columns of the half tile
+        const int gtid = (cw & 7) * 32 + lane;         // 0..255 inside the group
         const int key_t = quarter * 32 + lane;         // key row inside the tile == TMEM lane
         const int key = k0 + key_t;
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         const float sl2 = p.scale * LOG2E;
-        const int ctid = threadIdx.x - 64;             // 0..511
         const float* lse_g = p.lse + ((long long)b * p.n_heads + h) * p.Sq;
         const float* delta_g = p.delta + ((long long)b * p.n_heads + h) * p.Sq;
-        uint8_t* sP = smem + SB_P + key_t * 128;
-        uint8_t* sDS = smem + SB_DS + key_t * 128;
-        // lse / delta of the query tile: one value per thread of the first 8 compute warps, fetched one iteration
-        // ahead so the global load latency hides behind the previous iteration
+        const int hb = grp;
+        const int qc0 = hb * 64 + cgi * 32;            // first query column (inside the tile) of this thread
+        uint8_t* sP = smem + SB_P + hb * 16384 + key_t * 128;
+        uint8_t* sDS = smem + SB_DS + hb * 16384 + key_t * 128;
+        // lse / delta of this group's 64 queries: one value per thread of the group's first 4 warps, fetched one
+        // iteration ahead so the global load latency hides behind the previous iteration
         auto fetch_ld = [&](int it_) -> float {
-            const int qi = (i0 + it_) * BQ + (ctid & 127);
-            if (ctid >= 256 || it_ >= n_it || qi >= p.Sq) return 0.f;
-            return ctid < 128 ? lse_g[qi] * LOG2E : delta_g[qi];
+            const int qi = (i0 + it_) * BQ + hb * 64 + (gtid & 63);
+            if (gtid >= 128 || it_ >= n_it || qi >= p.Sq) return 0.f;
+            return gtid < 64 ? lse_g[qi] * LOG2E : delta_g[qi];
         };
-        // dQ tile of a finished iteration: TMEM lane = query row, this thread owns columns cg*16 .. +15
+        // dQ tile of a finished iteration, drained by group 0: TMEM lane = query row, this thread owns 32 columns
         auto drain_dq = [&](int q0_tile) {
-            uint32_t r[16];
-            tmem_ld16(tdQ + lane_addr + cg * 16, r);
+            uint32_t r[32];
+            tmem_ld32(tdQ + lane_addr + cgi * 32, r);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
@@ -707,113 +713,109 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (DQ_MODE == 1) {
                 const int qrow = q0_tile + key_t;                   // (lane index means query row here)
                 if (qrow < p.Sq) {
-                    float* dst = p.dq_acc + b * p.dqa_b + (long long)qrow * p.dqa_r + h * D + cg * 16;
+                    float* dst = p.dq_acc + b * p.dqa_b + (long long)qrow * p.dqa_r + h * D + cgi * 32;
 #pragma unroll
-                    for (int v = 0; v < 4; v++)
+                    for (int v = 0; v < 8; v++)
                         red_add_v4(dst + v * 4, __uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
                                    __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
                 }
             } else {
-                // the staging tile was released by thread 0's wait_group.read ahead of this iteration's bar.sync 1
-                uint8_t* dst = smem + SB_DQ + (cg >> 1) * 16384 + key_t * 128;
+                // the staging tile was released by the leader's wait_group.read ahead of this iteration's group barrier
+                uint8_t* dst = smem + SB_DQ + cgi * 16384 + key_t * 128;
 #pragma unroll
-                for (int v = 0; v < 4; v++) {
-                    const int chunk = (cg & 1) * 4 + v;
-                    *reinterpret_cast<uint4*>(dst + ((chunk ^ (key_t & 7)) << 4)) = make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
-                }
+                for (int v = 0; v < 8; v++)
+                    *reinterpret_cast<uint4*>(dst + ((v ^ (key_t & 7)) << 4)) = make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
                 fence_proxy_async_smem();
-                asm volatile("bar.sync 2, 512;" ::: "memory");
-                if (ctid == 0) {
+                asm volatile("bar.sync 3, 256;" ::: "memory");
+                if (gtid == 0) {
                     tma_reduce_add_3d(&tmDQ, smem_u32(smem + SB_DQ), h * D, q0_tile, b);
                     tma_reduce_add_3d(&tmDQ, smem_u32(smem + SB_DQ + 16384), h * D + 32, q0_tile, b);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
         };
+        const bool drainer = WITH_DQ && grp == 0;
         float ld_next = fetch_ld(0);
         for (int it = 0; it < n_it; it++) {
             const int q0 = (i0 + it) * BQ;
-            if (ctid < 256) (ctid < 128 ? lse_s : delta_s)[(it & 1) * 128 + (ctid & 127)] = ld_next;
+            if (gtid < 128) (gtid < 64 ? lse_s : delta_s)[(it & 1) * 128 + hb * 64 + (gtid & 63)] = ld_next;
             ld_next = fetch_ld(it + 1);
-            if (DQ_MODE == 2 && ctid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (DQ_MODE == 2 && drainer && gtid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory");
             const bool need_mask = (k0 + BK - 1 > q0 + off) || (k0 + BK > p.Sk) || (q0 + BQ > p.Sq);
+            const float* lse_t = lse_s + (it & 1) * 128 + qc0;
+            const float* delta_t = delta_s + (it & 1) * 128 + qc0;
+            mbar_wait(&s_full[hb], (uint32_t)(it & 1));
+            tc_fence_after();
+            uint32_t pk[16], dk_[16];
 #pragma unroll
-            for (int hb = 0; hb < 2; hb++) {
-                const int qc0 = hb * 64 + cg * 16;             // first query column (inside the tile) of this thread
-                const float* lse_t = lse_s + (it & 1) * 128 + qc0;
-                const float* delta_t = delta_s + (it & 1) * 128 + qc0;
-                mbar_wait(&s_full[hb], (uint32_t)(it & 1));
-                tc_fence_after();
-                uint32_t pk[8], dk_[8];
-                {
-                    uint32_t rs[16], rd[16];
-                    tmem_ld16(tSB + hb * 128 + lane_addr + cg * 16, rs);
-                    tmem_ld16(tSB + hb * 128 + 64 + lane_addr + cg * 16, rd);
-                    tmem_ld_wait();
-                    if (need_mask) {
-                        // column qq of this thread is visible iff key <= q0+qc0+qq+off, key < Sk and q0+qc0+qq < Sq
-                        const int lo = (key < p.Sk) ? key - off - q0 - qc0 : 1 << 20;     // first visible column
-                        const int hi = p.Sq - q0 - qc0;                                     // first column past the end
+            for (int hc = 0; hc < 2; hc++) {               // two chunks of 16 columns keep the register footprint flat
+                uint32_t rs[16], rd[16];
+                tmem_ld16(tSB + hb * 128 + lane_addr + cgi * 32 + hc * 16, rs);
+                tmem_ld16(tSB + hb * 128 + 64 + lane_addr + cgi * 32 + hc * 16, rd);
+                tmem_ld_wait();
+                if (need_mask) {
+                    // column c of this thread is visible iff key <= q0+qc0+c+off, key < Sk and q0+qc0+c < Sq
+                    const int lo = (key < p.Sk) ? key - off - q0 - qc0 : 1 << 20;     // first visible column
+                    const int hi = p.Sq - q0 - qc0;                                     // first column past the end
 #pragma unroll
-                        for (int i = 0; i < 16; i += 2) {
-                            float pv[2], dsv[2];
+                    for (int i = 0; i < 16; i += 2) {
+                        float pv[2], dsv[2];
 #pragma unroll
-                            for (int e = 0; e < 2; e++) {
-                                const int qq = i + e;
-                                float pr = ex2_approx(fmaf(__uint_as_float(rs[qq]), sl2, -lse_t[qq]));
-                                if (qq < lo || qq >= hi) pr = 0.f;
-                                pv[e] = pr;
-                                dsv[e] = pr * (__uint_as_float(rd[qq]) - delta_t[qq]);
-                            }
-                            pk[i >> 1] = pack2(pv[0], pv[1]);
-                            dk_[i >> 1] = pack2(dsv[0], dsv[1]);
+                        for (int e = 0; e < 2; e++) {
+                            const int qq = hc * 16 + i + e;
+                            float pr = ex2_approx(fmaf(__uint_as_float(rs[i + e]), sl2, -lse_t[qq]));
+                            if (qq < lo || qq >= hi) pr = 0.f;
+                            pv[e] = pr;
+                            dsv[e] = pr * (__uint_as_float(rd[i + e]) - delta_t[qq]);
                         }
-                        asm volatile("" ::: "memory");
-                    } else {
+                        pk[hc * 8 + (i >> 1)] = pack2(pv[0], pv[1]);
+                        dk_[hc * 8 + (i >> 1)] = pack2(dsv[0], dsv[1]);
+                    }
+                    asm volatile("" ::: "memory");
+                } else {
 #pragma unroll
-                        for (int i = 0; i < 16; i += 2) {
-                            float pv[2], dsv[2];
+                    for (int i = 0; i < 16; i += 2) {
+                        float pv[2], dsv[2];
 #pragma unroll
-                            for (int e = 0; e < 2; e++) {
-                                const int qq = i + e;
-                                const float pr = ex2_approx(fmaf(__uint_as_float(rs[qq]), sl2, -lse_t[qq]));
-                                pv[e] = pr;
-                                dsv[e] = pr * (__uint_as_float(rd[qq]) - delta_t[qq]);
-                            }
-                            pk[i >> 1] = pack2(pv[0], pv[1]);
-                            dk_[i >> 1] = pack2(dsv[0], dsv[1]);
+                        for (int e = 0; e < 2; e++) {
+                            const int qq = hc * 16 + i + e;
+                            const float pr = ex2_approx(fmaf(__uint_as_float(rs[i + e]), sl2, -lse_t[qq]));
+                            pv[e] = pr;
+                            dsv[e] = pr * (__uint_as_float(rd[i + e]) - delta_t[qq]);
                         }
+                        pk[hc * 8 + (i >> 1)] = pack2(pv[0], pv[1]);
+                        dk_[hc * 8 + (i >> 1)] = pack2(dsv[0], dsv[1]);
                     }
                 }
-                if (it > 0) {
-                    // the previous tile's dV / dK / dQ MMAs read both atoms: they must have retired before the overwrite
-                    mbar_wait(dq_full, (uint32_t)((it & 1) ^ 1));
-                    tc_fence_after();
-                }
-#pragma unroll
-                for (int v = 0; v < 2; v++) {
-                    const int sw = hb * 16384 + (((cg * 2 + v) ^ (key_t & 7)) << 4);
-                    *reinterpret_cast<uint4*>(sP + sw) = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
-                    *reinterpret_cast<uint4*>(sDS + sw) = make_uint4(dk_[4 * v], dk_[4 * v + 1], dk_[4 * v + 2], dk_[4 * v + 3]);
-                }
-                tc_fence_before();
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&pds_full[hb]);
-                if (WITH_DQ && hb == 0 && it > 0) drain_dq(q0 - BQ);   // off the critical path
             }
+            if (it > 0) {
+                // the previous tile's dV / dK / dQ MMAs read both atoms: they must have retired before the overwrite
+                mbar_wait(dq_full, (uint32_t)((it & 1) ^ 1));
+                tc_fence_after();
+            }
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const int sw = ((cgi * 4 + v) ^ (key_t & 7)) << 4;
+                *reinterpret_cast<uint4*>(sP + sw) = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+                *reinterpret_cast<uint4*>(sDS + sw) = make_uint4(dk_[4 * v], dk_[4 * v + 1], dk_[4 * v + 2], dk_[4 * v + 3]);
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&pds_full[hb]);
+            if (drainer && it > 0) drain_dq(q0 - BQ);   // off the critical path
         }
         if (n_it > 0) {
             mbar_wait(dq_full, (uint32_t)((n_it - 1) & 1));   // last tile's MMAs
             tc_fence_after();
-            if (WITH_DQ) {
+            if (drainer) {
                 if (DQ_MODE == 2) {
-                    if (ctid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    asm volatile("bar.sync 1, 512;" ::: "memory");
+                    if (gtid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
                 }
                 drain_dq((i0 + n_it - 1) * BQ);
-                if (DQ_MODE == 2 && ctid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                if (DQ_MODE == 2 && gtid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             }
         }
         // epilogue: warps 2..9 write dK (two 16-column groups that form RoPE pairs d, d+32), warps 10..17 write dV

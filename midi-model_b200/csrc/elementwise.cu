@@ -100,27 +100,51 @@ __global__ void embed_fill_kernel(const long long* __restrict__ ids, int n, int 
         }
     }
 }
-// grid (V, SLICES): block (v, y) sums entries y, y+SLICES, ... of segment v and adds the partial to acc32[v,:]
+// grid (V, SLICES): segment v (all occurrences of token id v) is cut into ceil(len / SEG_ROWS) <= SLICES slices; block
+// (v, y) sums the entries y, y+n, ... of its slice set.  Short segments (the common case) have one slice and store their
+// sum directly; only long ones (event-type ids, common values) combine partials with vector reds.  The previous version
+// always used 32 slices and 8 scalar atomics per thread: 109k blocks x 1024 atomics dominated the kernel.
+constexpr int SEG_ROWS = 48;
 __global__ void embed_segsum_kernel(const int* __restrict__ offsets, const int* __restrict__ sorted,
                                     const bf16* __restrict__ dout, float* __restrict__ acc32, int H, int per_row,
                                     int row_stride, int row_inner, int row_off, int pad_id) {
     const int v = blockIdx.x;
     if (v == pad_id) return;   // padding_idx row receives zero gradient (hf nn.Embedding(padding_idx))
     const int beg = offsets[v], end = offsets[v + 1];
-    if (beg + (int)blockIdx.y >= end) return;
+    const int len = end - beg;
+    int n_slices = (len + SEG_ROWS - 1) / SEG_ROWS;
+    if (n_slices > (int)gridDim.y) n_slices = gridDim.y;
+    if ((int)blockIdx.y >= n_slices) return;       // also covers len == 0
+    auto row_of = [&](int i) -> const bf16* {
+        return dout + ((size_t)(i / per_row) * row_stride + (size_t)(i % per_row) * row_inner + row_off) * H;
+    };
     for (int c = threadIdx.x; c < H / 8; c += blockDim.x) {
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int j = beg + blockIdx.y; j < end; j += gridDim.y) {
-            const int i = sorted[j];
-            const size_t row = (size_t)(i / per_row) * row_stride + (size_t)(i % per_row) * row_inner + row_off;
+        int j = beg + blockIdx.y;
+        // four rows in flight per thread
+        for (; j + 3 * n_slices < end; j += 4 * n_slices) {
+            const int i0 = sorted[j], i1 = sorted[j + n_slices], i2 = sorted[j + 2 * n_slices], i3 = sorted[j + 3 * n_slices];
+            const uint4 u0 = ld_nc16(row_of(i0) + c * 8), u1 = ld_nc16(row_of(i1) + c * 8);
+            const uint4 u2 = ld_nc16(row_of(i2) + c * 8), u3 = ld_nc16(row_of(i3) + c * 8);
+            float f0[8], f1[8], f2[8], f3[8];
+            unpack8(u0, f0); unpack8(u1, f1); unpack8(u2, f2); unpack8(u3, f3);
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[k] += (f0[k] + f1[k]) + (f2[k] + f3[k]);
+        }
+        for (; j < end; j += n_slices) {
             float f[8];
-            unpack8(ld_nc16(dout + row * H + c * 8), f);
+            unpack8(ld_nc16(row_of(sorted[j]) + c * 8), f);
 #pragma unroll
             for (int k = 0; k < 8; k++) acc[k] += f[k];
         }
         float* dst = acc32 + (size_t)v * H + c * 8;
-#pragma unroll
-        for (int k = 0; k < 8; k++) atomicAdd(dst + k, acc[k]);
+        if (n_slices == 1) {
+            *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        } else {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(acc[0]), "f"(acc[1]), "f"(acc[2]), "f"(acc[3]) : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(acc[4]), "f"(acc[5]), "f"(acc[6]), "f"(acc[7]) : "memory");
+        }
     }
 }
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n, int accumulate) {
