@@ -59,7 +59,7 @@ struct SmemLayout {
 template <int BLOCK_N, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
     using L = SmemLayout<BLOCK_N>;
     constexpr int STAGES = L::STAGES;
     constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;   // double-buffered accumulator (256 or 512 columns)
@@ -186,7 +186,117 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int row = m_blk * BLOCK_M + quarter * 32 + lane;
             const bool row_ok = row < p.M;
             const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(quarter * 32) << 16);
-            if (BLOCK_N == 256 && p.epilogue == EPI_SWIGLU) {
+            // ---- staged output: the thread's 64 consecutive columns (8 x 16 B) of row r_t go into a 128B-swizzled
+            // [128 x 64] staging box, one TMA store per box (see the plain-store branch below for the why)
+            const int r_t = quarter * 32 + lane;
+            const bool leader = (warp == EPI_WARP0 && lane == 0);
+            auto box_row = [&]() -> uint8_t* { return out_stage + out_buf * (BLOCK_M * 128) + r_t * 128; };
+            auto box_put = [&](uint8_t* dst, int chunk, const float* f8) {
+                *reinterpret_cast<uint4*>(dst + ((chunk ^ (r_t & 7)) << 4)) = pack8(f8);
+            };
+            auto box_send = [&](const CUtensorMap* tm, int gcol) {
+                fence_proxy_async_smem();
+                // the previous box's store has finished reading the other buffer before anyone writes it again
+                if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (leader) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(tm), "r"(smem_u32(out_stage + out_buf * (BLOCK_M * 128))), "r"(gcol), "r"(m_blk * BLOCK_M)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                out_buf ^= 1;
+            };
+            if (BLOCK_N == 256 && p.epilogue == EPI_SWIGLU && p.tma_store) {
+                // gate|up projection with SwiGLU fused (hf modeling_llama.py:183), staged: per 64 features three boxes --
+                // gate, up (both kept for the backward) and act = bf16(silu(gate)) * up.  TMEM is re-read for the act
+                // pass instead of holding 128 values per thread in registers.
+#pragma unroll 1
+                for (int fb = 0; fb < 2; fb++) {
+                    const int f0 = n_blk * 128 + fb * 64;
+                    if (f0 >= p.swiglu_I) break;
+#pragma unroll 1
+                    for (int which = 0; which < 2; which++) {          // 0: gate columns, 1: up columns
+                        uint8_t* dst = box_row();
+#pragma unroll
+                        for (int hc = 0; hc < 2; hc++) {
+                            uint32_t r[32];
+                            tmem_ld32(taddr + which * 128 + fb * 64 + hc * 32, r);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int v = 0; v < 4; v++) {
+                                float f[8];
+#pragma unroll
+                                for (int q = 0; q < 8; q++) f[q] = __uint_as_float(r[8 * v + q]);
+                                box_put(dst, hc * 4 + v, f);
+                            }
+                        }
+                        box_send(&tmC, which * p.swiglu_I + f0);
+                    }
+                    uint8_t* dst = box_row();
+#pragma unroll
+                    for (int hc = 0; hc < 2; hc++) {
+                        uint32_t r1[32], r2[32];
+                        tmem_ld32(taddr + fb * 64 + hc * 32, r1);
+                        tmem_ld32(taddr + 128 + fb * 64 + hc * 32, r2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int v = 0; v < 4; v++) {
+                            float a[8];
+#pragma unroll
+                            for (int q = 0; q < 8; q++) {
+                                const float g = bf16_round(__uint_as_float(r1[8 * v + q]));
+                                const float u = bf16_round(__uint_as_float(r2[8 * v + q]));
+                                a[q] = bf16_round(g / (1.f + __expf(-g))) * u;
+                            }
+                            box_put(dst, hc * 4 + v, a);
+                        }
+                    }
+                    box_send(&tmD, f0);
+                }
+            } else if (p.epilogue == EPI_ROPE && p.tma_store) {
+                // QKV projection with RoPE fused (hf modeling_llama.py:262-268), staged, head_dim 64: one box = one head, the
+                // (d, d+32) pairs are the two 32-column halves of the thread's 64 values.
+                const int pos = row_ok ? row % p.rope_S : 0;
+                const bf16* cp = p.rope_cos + (size_t)pos * 32;
+                const bf16* sp = p.rope_sin + (size_t)pos * 32;
+#pragma unroll 1
+                for (int bx = 0; bx < BLOCK_N / 64; bx++) {
+                    const int col0 = n_blk * BLOCK_N + bx * 64;
+                    if (col0 >= p.N) break;
+                    uint8_t* dst = box_row();
+                    uint32_t r1[32], r2[32];
+                    tmem_ld32(taddr + bx * 64, r1);
+                    tmem_ld32(taddr + bx * 64 + 32, r2);
+                    tmem_ld_wait();
+                    const bool rot = col0 < p.rope_cols;
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+                        float x1[8], x2[8], o1[8], o2[8];
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            x1[q] = bf16_round(__uint_as_float(r1[8 * v + q]));
+                            x2[q] = bf16_round(__uint_as_float(r2[8 * v + q]));
+                        }
+                        if (rot) {
+                            float cc[8], ss[8];
+                            unpack8(*reinterpret_cast<const uint4*>(cp + v * 8), cc);
+                            unpack8(*reinterpret_cast<const uint4*>(sp + v * 8), ss);
+#pragma unroll
+                            for (int q = 0; q < 8; q++) {
+                                o1[q] = bf16_round(x1[q] * cc[q]) + bf16_round(-x2[q] * ss[q]);
+                                o2[q] = bf16_round(x2[q] * cc[q]) + bf16_round(x1[q] * ss[q]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 8; q++) { o1[q] = x1[q]; o2[q] = x2[q]; }
+                        }
+                        box_put(dst, v, o1);
+                        box_put(dst, 4 + v, o2);
+                    }
+                    box_send(&tmC, col0);
+                }
+            } else if (BLOCK_N == 256 && p.epilogue == EPI_SWIGLU) {
                 // gate|up projection with SwiGLU fused (hf modeling_llama.py:183): accumulator columns [0,128) are gate
                 // features, [128,256) the matching up features.  g, u = bf16(acc) are stored (backward needs them) and
                 // act = bf16(bf16(silu(g)) * u) -- same rounding points as the stand-alone kernel.
@@ -269,13 +379,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 // plain bf16 store: row-per-thread 16-byte global stores touch 32 different rows per instruction and
                 // made the epilogue longer than a K=1024 main loop (tensor pipe 64% busy); instead the tile goes
                 // through two 128B-swizzled [128 x 64] staging boxes and leaves with one TMA store per box.
-                const int r_t = quarter * 32 + lane;
-                const bool leader = (warp == EPI_WARP0 && lane == 0);
 #pragma unroll 1
                 for (int bx = 0; bx < BLOCK_N / 64; bx++) {
                     const int col0 = n_blk * BLOCK_N + bx * 64;
                     if (col0 >= p.N) break;                                   // uniform
-                    uint8_t* dst = out_stage + out_buf * (BLOCK_M * 128) + r_t * 128;
+                    uint8_t* dst = box_row();
 #pragma unroll
                     for (int hc = 0; hc < 2; hc++) {
                         uint32_t r[32];
@@ -286,20 +394,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             float f[8];
 #pragma unroll
                             for (int j = 0; j < 8; j++) f[j] = __uint_as_float(r[8 * v + j]);
-                            *reinterpret_cast<uint4*>(dst + (((hc * 4 + v) ^ (r_t & 7)) << 4)) = pack8(f);
+                            box_put(dst, hc * 4 + v, f);
                         }
                     }
-                    fence_proxy_async_smem();
-                    // the previous box's store has finished reading the other buffer before anyone writes it again
-                    if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (leader) {
-                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                                     ::"l"(&tmC), "r"(smem_u32(out_stage + out_buf * (BLOCK_M * 128))), "r"(col0), "r"(m_blk * BLOCK_M)
-                                     : "memory");
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
-                    out_buf ^= 1;
+                    box_send(&tmC, col0);
                 }
             } else
 #pragma unroll 1
@@ -377,7 +475,8 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, bf16* __restr
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p, cudaStream_t stream) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmD, const GemmParams& p,
+           cudaStream_t stream) {
     using L = SmemLayout<BLOCK_N>;
     auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN>;
     static bool configured = false;
@@ -387,7 +486,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
     }
     const int items = p.m_tiles * p.n_tiles * p.splits;
     const int grid = items < b200_num_sms() ? items : b200_num_sms();
-    kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, p);
+    kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, tmD, p);
     B200_CHECK_LAUNCH("gemm_tcgen05");
     return B200_OK;
 }
@@ -631,9 +730,20 @@ static int gemm_impl(const void* A, const void* B, void* C, const void* R, int M
         const char* e = getenv("B200_GEMM_TMA_STORE");       // 0 = per-thread global stores (bring-up / A-B timing)
         tma_store_ok = (e && e[0] == '0') ? 0 : 1;
     }
-    p.tma_store = (p.epilogue == EPI_STORE && tma_store_ok) ? 1 : 0;
+    // staged (TMA-store) epilogues: plain store always; SwiGLU when I is a multiple of 128 and the outputs are 16-byte
+    // pitched; RoPE for head_dim 64 (one staging box = one head)
+    p.tma_store = 0;
+    if (tma_store_ok) {
+        if (p.epilogue == EPI_STORE) p.tma_store = 1;
+        else if (p.epilogue == EPI_SWIGLU && block_n == 256 && p.ld_act % 8 == 0 && ((uintptr_t)p.act % 16 == 0)) p.tma_store = 1;
+        else if (p.epilogue == EPI_ROPE && rope_D == 64 && rope_cols % 64 == 0) p.tma_store = 1;
+    }
+    CUtensorMap tmD;
     if (p.tma_store) {
         if ((rc = tc05::make_tmap_2d(&tmC, C, N8, M, ldc, 64, BLOCK_M))) return rc;
+        if (p.epilogue == EPI_SWIGLU) {
+            if ((rc = tc05::make_tmap_2d(&tmD, p.act, p.swiglu_I, M, p.ld_act, 64, BLOCK_M))) return rc;
+        } else tmD = tmC;
     }
     if (!a_mn_major) rc = tc05::make_tmap_2d(&tmA, A, K, M, lda, BLOCK_K, BLOCK_M);
     else             rc = tc05::make_tmap_2d(&tmA, A, M, K, lda, 64, BLOCK_K);
@@ -641,14 +751,14 @@ static int gemm_impl(const void* A, const void* B, void* C, const void* R, int M
     if (!b_mn_major) rc = tc05::make_tmap_2d(&tmB, B, K, N, ldb, BLOCK_K, swiglu ? 128 : block_n);
     else             rc = tc05::make_tmap_2d(&tmB, B, N, K, ldb, 64, BLOCK_K);
     if (rc) return rc;
-    if (!p.tma_store) tmC = tmA;      // unused by the kernel, but must be a valid map
+    if (!p.tma_store) { tmC = tmA; tmD = tmA; }      // unused by the kernel, but must be valid maps
 
 #define B200_DISPATCH(BN)                                                                   \
     do {                                                                                    \
-        if (!a_mn_major && !b_mn_major) rc = launch<BN, false, false>(tmA, tmB, tmC, p, stream);  \
-        else if (!a_mn_major && b_mn_major) rc = launch<BN, false, true>(tmA, tmB, tmC, p, stream); \
-        else if (a_mn_major && b_mn_major) rc = launch<BN, true, true>(tmA, tmB, tmC, p, stream);  \
-        else rc = launch<BN, true, false>(tmA, tmB, tmC, p, stream);                              \
+        if (!a_mn_major && !b_mn_major) rc = launch<BN, false, false>(tmA, tmB, tmC, tmD, p, stream);  \
+        else if (!a_mn_major && b_mn_major) rc = launch<BN, false, true>(tmA, tmB, tmC, tmD, p, stream); \
+        else if (a_mn_major && b_mn_major) rc = launch<BN, true, true>(tmA, tmB, tmC, tmD, p, stream);  \
+        else rc = launch<BN, true, false>(tmA, tmB, tmC, tmD, p, stream);                              \
     } while (0)
     if (block_n == 256) B200_DISPATCH(256);
     else B200_DISPATCH(128);
