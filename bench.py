@@ -277,7 +277,8 @@ def run_native(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": ach_tf / peak_tf if peak_tf else None, "traffic": None,
+                     "frac": ach_tf / peak_tf if peak_tf else None, "traffic": gemm_traffic(),
+                     "traffic_unit": "DRAM bytes (read+write) per GEMM launch, ncu capture in profiles/r1_gemm_traffic.json",
                      "kernel": "gemm_tcgen05_kernel (all launches of the timed steps)", "peak_kind": f"{pk_kind} sustained cuBLAS bf16",
                      "gemm_ms_per_step": gemm_ms / K, "gemm_share_of_step": gemm_ms / ms_total if ms_total else None,
                      "whole_step_model_tflops": step_tf, "whole_step_frac": step_tf / peak_tf if peak_tf else None,
@@ -294,6 +295,17 @@ def run_native(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def gemm_traffic():
+    """DRAM bytes (read + write) per GEMM launch from the committed ncu capture of this same command
+    (profiles/r1_gemm_traffic.json, derived from profiles/r1_launches_step.csv); None when the capture is absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")) as f:
+            t = json.load(f)
+        return float(t["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def generate_leg(model, dev, world, rank):

@@ -79,6 +79,8 @@ int b200_swiglu_bwd(const void* gu, const void* dact, void* dgu, long long rows,
  *      R != NULL: C = bf16(bf16(acc) + R) (residual add, hf :325 / :331).
  *      splits > 1 or accumulate: fp32 split-K partials in `workspace`, reduced (and added to C). */
 size_t b200_gemm_workspace_bytes(int M, int N, int splits);
+/* optional fp32 workspace that lets b200_gemm_bf16 cut the tiles of the last partial wave along K (0: not useful) */
+size_t b200_gemm_tail_workspace_bytes(int M, int N, int K, int block_n);
 int b200_gemm_suggest_splits(int M, int N, int K, int block_n);
 /* cheapest (block_n in {128,256}, split-K factor) for an [M,N,K] problem on this device */
 int b200_gemm_plan(int M, int N, int K, int allow_split, int* block_n_out, int* splits_out);

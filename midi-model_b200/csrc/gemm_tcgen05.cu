@@ -32,6 +32,10 @@ struct GemmParams {
     int epilogue;
     int tma_store;             // EPI_STORE only: bf16 tile staged in shared memory and written with cp.async.bulk.tensor
     int splits, kb_per_split, num_kb;
+    // tail split: the tiles of the last, partial wave (index >= tail_tile0) are cut into tail_splits K-slices whose fp32
+    // partials go to tail_ws[tile - tail_tile0][slice][128][BLOCK_N] and are summed by tail_reduce_kernel
+    int tail_tile0, tail_splits, tail_kb, total_items;
+    float* tail_ws;
     int m_tiles, n_tiles;
     uint32_t mn_lbo, mn_sbo;   // MN-major descriptor byte offsets (overridable for bring-up)
     // EPI_ROPE: rotary embedding applied to columns [0, rope_cols) (the q and k thirds of a packed QKV row)
@@ -55,6 +59,33 @@ struct SmemLayout {
     static constexpr int BAR_BYTES = 1024;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES + 1024;   // +1024 for manual alignment
 };
+
+struct WorkItem {
+    int m_blk, n_blk, kb0, kb1, split;
+    int tail;          // -1: regular item; otherwise index of the tile inside the tail region
+};
+__device__ __forceinline__ WorkItem decode_item(const GemmParams& p, int item) {
+    WorkItem w;
+    const int reg_items = p.tail_tile0 * p.splits;
+    int t;
+    if (item < reg_items) {
+        w.split = item % p.splits;
+        t = item / p.splits;
+        w.kb0 = w.split * p.kb_per_split;
+        w.kb1 = min(w.kb0 + p.kb_per_split, p.num_kb);
+        w.tail = -1;
+    } else {
+        const int idx = item - reg_items;
+        w.tail = idx / p.tail_splits;
+        w.split = idx % p.tail_splits;
+        t = p.tail_tile0 + w.tail;
+        w.kb0 = w.split * p.tail_kb;
+        w.kb1 = min(w.kb0 + p.tail_kb, p.num_kb);
+    }
+    w.n_blk = t % p.n_tiles;
+    w.m_blk = t / p.n_tiles;
+    return w;
+}
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -96,7 +127,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int total_items = p.m_tiles * p.n_tiles * p.splits;
+    const int total_items = p.total_items;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -104,11 +135,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-                const int split = item % p.splits;
-                const int t = item / p.splits;
-                const int n_blk = t % p.n_tiles, m_blk = t / p.n_tiles;
-                const int kb0 = split * p.kb_per_split;
-                const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+                const WorkItem wi = decode_item(p, item);
+                const int n_blk = wi.n_blk, m_blk = wi.m_blk, kb0 = wi.kb0, kb1 = wi.kb1;
                 for (int kb = kb0; kb < kb1; kb++) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sA = smem + stage * L::STAGE_BYTES;
@@ -146,9 +174,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-                const int split = item % p.splits;
-                const int kb0 = split * p.kb_per_split;
-                const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+                const WorkItem wi = decode_item(p, item);
+                const int kb0 = wi.kb0, kb1 = wi.kb1;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
@@ -178,9 +205,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int acc = 0, out_buf = 0;
         uint32_t acc_phase = 0;
         for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-            const int split = item % p.splits;
-            const int t = item / p.splits;
-            const int n_blk = t % p.n_tiles, m_blk = t / p.n_tiles;
+            const WorkItem wi = decode_item(p, item);
+            const int split = wi.split, n_blk = wi.n_blk, m_blk = wi.m_blk;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const int row = m_blk * BLOCK_M + quarter * 32 + lane;
@@ -207,7 +233,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 out_buf ^= 1;
             };
-            if (BLOCK_N == 256 && p.epilogue == EPI_SWIGLU && p.tma_store) {
+            if (wi.tail >= 0) {
+                // K-slice of a tail tile: fp32 partial, tile-local layout [128][BLOCK_N]
+                float* dstp = p.tail_ws + ((size_t)(wi.tail * p.tail_splits + split) * BLOCK_M + r_t) * BLOCK_N;
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 32; c++) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int v = 0; v < 8; v++)
+                        *reinterpret_cast<uint4*>(dstp + c * 32 + v * 4) = make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+                }
+            } else if (BLOCK_N == 256 && p.epilogue == EPI_SWIGLU && p.tma_store) {
                 // gate|up projection with SwiGLU fused (hf modeling_llama.py:183), staged: per 64 features three boxes --
                 // gate, up (both kept for the backward) and act = bf16(silu(gate)) * up.  TMEM is re-read for the act
                 // pass instead of holding 128 values per thread in registers.
@@ -474,6 +512,28 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, bf16* __restr
     }
 }
 
+// sums the K-slices of the tail tiles and writes bf16 into C (rows < M, columns < N, N a multiple of 8)
+__global__ void tail_reduce_kernel(const float* __restrict__ ws, bf16* __restrict__ C, int M, int N, int ldc, int n_tiles,
+                                   int tail_tile0, int n_tail, int splits, int block_n) {
+    const int per_tile = BLOCK_M * block_n / 8;                 // 8-column groups per tile
+    const long long total = (long long)n_tail * per_tile;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int tt = (int)(i / per_tile), e = (int)(i % per_tile);
+        const int r = e / (block_n / 8), c8 = e % (block_n / 8);
+        const int t = tail_tile0 + tt;
+        const int row = (t / n_tiles) * BLOCK_M + r, col = (t % n_tiles) * block_n + c8 * 8;
+        if (row >= M || col >= N) continue;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int s = 0; s < splits; s++) {
+            const float* src = ws + ((size_t)(tt * splits + s) * BLOCK_M + r) * block_n + c8 * 8;
+            const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+            acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+        }
+        *reinterpret_cast<uint4*>(C + (size_t)row * ldc + col) = pack8(acc);
+    }
+}
+
 template <int BLOCK_N, bool A_MN, bool B_MN>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmD, const GemmParams& p,
            cudaStream_t stream) {
@@ -484,7 +544,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL), "gemm smem attr");
         configured = true;
     }
-    const int items = p.m_tiles * p.n_tiles * p.splits;
+    const int items = p.total_items;
     const int grid = items < b200_num_sms() ? items : b200_num_sms();
     kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, tmD, p);
     B200_CHECK_LAUNCH("gemm_tcgen05");
@@ -578,6 +638,34 @@ int tc05_make_tmap_3d_f32(CUtensorMap* tm, const void* ptr, uint64_t cols, uint6
 // ---------------------------------------------------------------------------
 extern "C" size_t b200_gemm_workspace_bytes(int M, int N, int splits) {
     return splits > 1 ? (size_t)splits * M * N * sizeof(float) : 0;
+}
+
+// Tail split.  tiles = full * sms + r: the last wave keeps only r of the sms CTAs busy for a whole tile time.  Cutting
+// those r tiles into s K-slices makes the tail ceil(r*s/sms)/s tile times long (e.g. 512 tiles on 148 SMs: r = 68,
+// s = 2 -> 3.5 instead of 4 waves).  Returns s (1 = leave the tail alone).
+static int plan_tail(int tiles, int num_kb, int sms) {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("B200_GEMM_TAIL_SPLIT");
+        enabled = (e && e[0] == '0') ? 0 : 1;
+    }
+    const int full = tiles / sms, r = tiles % sms;
+    // measured (profiles/r1_gemm_tail_ab.txt): +3 % at K = 8192, neutral at K = 4096, a loss at K <= 3072 (the partial round
+    // trip and the extra launch cost more than the half wave saves) and for 4-way splits -> long-K, 2-way only
+    if (!enabled || r == 0 || full == 0 || full > 8 || num_kb < 96) return 1;
+    const double cost = (double)((r * 2 + sms - 1) / sms) / 2 + 0.06;
+    return cost < 0.75 ? 2 : 1;
+}
+
+// bytes of fp32 workspace b200_gemm_bf16 can use to split the tiles of the last partial wave along K (0: no tail split
+// for this shape).  Optional: without the workspace the GEMM runs unsplit.
+extern "C" size_t b200_gemm_tail_workspace_bytes(int M, int N, int K, int block_n) {
+    if (block_n != 128 && block_n != 256) return 0;
+    const int tiles = ((M + BLOCK_M - 1) / BLOCK_M) * ((N + block_n - 1) / block_n);
+    const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+    const int sms = b200_num_sms();
+    const int s = plan_tail(tiles, num_kb, sms);
+    return s > 1 ? (size_t)(tiles % sms) * s * BLOCK_M * block_n * sizeof(float) : 0;
 }
 
 // Tile / split-K planner.  Work items = tiles(block_n) x splits run persistently on `sms` CTAs, so the cost is
@@ -738,6 +826,25 @@ static int gemm_impl(const void* A, const void* B, void* C, const void* R, int M
         else if (p.epilogue == EPI_SWIGLU && block_n == 256 && p.ld_act % 8 == 0 && ((uintptr_t)p.act % 16 == 0)) p.tma_store = 1;
         else if (p.epilogue == EPI_ROPE && rope_D == 64 && rope_cols % 64 == 0) p.tma_store = 1;
     }
+    // tail split (plain bf16 store, no split-K, no accumulate) when the caller provided the optional workspace
+    p.total_items = p.m_tiles * p.n_tiles * p.splits;
+    p.tail_tile0 = p.m_tiles * p.n_tiles;
+    p.tail_splits = 1; p.tail_kb = p.num_kb; p.tail_ws = nullptr;
+    int n_tail = 0;
+    if (p.epilogue == EPI_STORE && p.splits == 1 && !accumulate && workspace != nullptr) {
+        const int tiles = p.m_tiles * p.n_tiles, sms = b200_num_sms();
+        const int ts = plan_tail(tiles, p.num_kb, sms);
+        const size_t need = (size_t)(tiles % sms) * ts * BLOCK_M * block_n * sizeof(float);
+        if (ts > 1 && workspace_bytes >= need && ((uintptr_t)workspace % 16 == 0)) {
+            n_tail = tiles % sms;
+            p.tail_tile0 = tiles - n_tail;
+            p.tail_splits = ts;
+            p.tail_kb = (p.num_kb + ts - 1) / ts;
+            p.tail_splits = (p.num_kb + p.tail_kb - 1) / p.tail_kb;      // no empty slices
+            p.tail_ws = (float*)workspace;
+            p.total_items = p.tail_tile0 + n_tail * p.tail_splits;
+        }
+    }
     CUtensorMap tmD;
     if (p.tma_store) {
         if ((rc = tc05::make_tmap_2d(&tmC, C, N8, M, ldc, 64, BLOCK_M))) return rc;
@@ -765,6 +872,13 @@ static int gemm_impl(const void* A, const void* B, void* C, const void* R, int M
 #undef B200_DISPATCH
     if (rc) return rc;
 
+    if (n_tail > 0) {
+        const long long groups = (long long)n_tail * BLOCK_M * block_n / 8;
+        int blocks = (int)((groups + 255) / 256);
+        if (blocks > b200_num_sms() * 8) blocks = b200_num_sms() * 8;
+        tail_reduce_kernel<<<blocks, 256, 0, stream>>>(p.tail_ws, p.C, M, N8, ldc, p.n_tiles, p.tail_tile0, n_tail, p.tail_splits, block_n);
+        B200_CHECK_LAUNCH("gemm_tail_reduce");
+    }
     if (p.epilogue == EPI_PARTIAL_F32) {
         const size_t n = (size_t)M * N;
         int blocks = (int)((n / 4 + 255) / 256);

@@ -148,6 +148,18 @@ def _plan(M: int, N: int, K: int, allow_split: bool):
     return p
 
 
+_tail_cache: dict = {}
+
+
+def _tail_bytes(M: int, N: int, K: int, block_n: int) -> int:
+    key = (M, N, K, block_n)
+    v = _tail_cache.get(key)
+    if v is None:
+        v = int(lib.query("b200_gemm_tail_workspace_bytes", M, N, K, block_n))
+        _tail_cache[key] = v
+    return v
+
+
 def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, lda: int, ldb: int, a_mn: bool = False,
          b_mn: bool = False, out: Optional[torch.Tensor] = None, ldc: Optional[int] = None,
          residual: Optional[torch.Tensor] = None, accumulate: bool = False, allow_split: bool = False) -> torch.Tensor:
@@ -164,6 +176,11 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, lda: int, 
             nbytes = M * N * 4
         ws = _ws("gemm", nbytes, A.device)
         ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
+    elif residual is None:
+        tb = _tail_bytes(M, N, K, block_n)          # optional: lets the library split the last partial wave along K
+        if tb:
+            ws = _ws("gemm_tail", tb, A.device)
+            ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
     ldr = residual.stride(0) if residual is not None else 0
     prof = GEMM_PROFILE
     if prof is not None:
