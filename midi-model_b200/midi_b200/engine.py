@@ -33,6 +33,32 @@ FUSE_ROPE_FWD = os.environ.get("B200_FUSE_ROPE_FWD", "0") != "0"
 # warps) outlasts the K=1024 main loop (gate|up GEMM 1122 -> 686 TFLOP/s), a net loss of 1.3 ms/step; 8 epilogue warps
 # did not help (plain GEMMs got 6 % slower).  B200_FUSE_SWIGLU=1 enables it.
 FUSE_SWIGLU = os.environ.get("B200_FUSE_SWIGLU", "0") != "0"
+# Weight-gradient GEMMs on a second (lower-priority) stream: dW = dY^T X is off the backward's critical path, so it can run
+# under the HBM-bound kernels that follow on the main stream (SwiGLU / RMSNorm backward leave the tensor pipe idle, and an
+# elementwise CTA fits next to a GEMM CTA on an SM).  B200_WGRAD_STREAM=0 keeps everything on one stream.
+WGRAD_STREAM = os.environ.get("B200_WGRAD_STREAM", "1") != "0"
+_side_streams: dict = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    s = _side_streams.get(device.index)
+    if s is None:
+        s = torch.cuda.Stream(device=device, priority=0)     # main work keeps the default (same) priority class
+        _side_streams[device.index] = s
+    return s
+
+
+def _wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, accumulate: bool, side) -> None:
+    """dW (+)= dY^T X, on `side` when given: ordered after everything queued so far on the current stream; the caller
+    joins `side` back before the gradients are consumed."""
+    if side is None:
+        ops.linear_wgrad(dy, x, dw, accumulate)
+        return
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ops.linear_wgrad(dy, x, dw, accumulate)
+    dy.record_stream(side)           # the caching allocator must not hand these blocks out before the side GEMM ran
+    x.record_stream(side)
 ALIGN = 256   # elements; AdamW's no-decay flags are per 256-element block
 
 
@@ -273,6 +299,7 @@ class StackEngine:
         if sv is None or sv["layers"] is None:
             raise lib.B200Error("backward called without a saved forward")
         n_seq, S, cos, sin = sv["n_seq"], sv["S"], sv["cos"], sv["sin"]
+        side = _side_stream(dy.device) if WGRAD_STREAM else None
         dx = ops.rmsnorm_bwd(dy, sv["x_last"], self.norm, sv["rstd_f"], None, grads.norm, accumulate)
         for li in range(len(self.layers) - 1, -1, -1):
             w = self.layers[li]
@@ -281,18 +308,18 @@ class StackEngine:
             sv["layers"][li] = None   # free as we go
             # ---- MLP block: x_out = h + down(act)
             dact = ops.linear_dgrad(dx, w.down)
-            ops.linear_wgrad(dx, act, g.down, accumulate)
+            _wgrad(dx, act, g.down, accumulate, side)
             del act
             dgu = ops.swiglu_bwd(gu, dact)
             del dact, gu
             dn2 = ops.linear_dgrad(dgu, w.gu)
-            ops.linear_wgrad(dgu, n2, g.gu, accumulate)
+            _wgrad(dgu, n2, g.gu, accumulate, side)
             del dgu, n2
             dh = ops.rmsnorm_bwd(dn2, h, w.ln2, rstd2, dx, g.ln2, accumulate)
             del dn2, h, dx
             # ---- attention block: h = x + o(attn)
             dattn = ops.linear_dgrad(dh, w.o)
-            ops.linear_wgrad(dh, attn, g.o, accumulate)
+            _wgrad(dh, attn, g.o, accumulate, side)
             rope = (cos, sin) if FUSE_ROPE else None
             if self.tiny:
                 dqkv = ops.attn_tiny_bwd(qkv, dattn, n_seq, S, nh, D, rope=rope)
@@ -302,11 +329,15 @@ class StackEngine:
             if not FUSE_ROPE:
                 ops.rope_qk_(dqkv, cos, sin, S, H, D, backward=True)
             dn1 = ops.linear_dgrad(dqkv, w.qkv)
-            ops.linear_wgrad(dqkv, n1, g.qkv, accumulate)
+            _wgrad(dqkv, n1, g.qkv, accumulate, side)
             del dqkv, n1
             dx = ops.rmsnorm_bwd(dn1, x, w.ln1, rstd1, dh, g.ln1, accumulate)
             del dn1, dh, x
             if layer_done is not None:
+                if side is not None:
+                    torch.cuda.current_stream().wait_stream(side)     # this layer's weight gradients are complete
                 layer_done(li)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
         sv["layers"] = None
         return dx

@@ -27,6 +27,7 @@ import tqdm
 from transformers import DynamicCache, LlamaConfig, LlamaModel, PretrainedConfig, PreTrainedModel
 
 from midi_b200 import decode as _dec
+from midi_b200 import engine as _engine
 from midi_b200 import lib as _lib
 from midi_b200 import ops as _ops
 from midi_b200.engine import ParamStore, StackCfg, StackEngine
@@ -189,7 +190,9 @@ class _InnerFn(torch.autograd.Function):
 
 def _inner_backward(rt, model, sv, hs, dlogits, ids, N, L, n_ids, has_hidden, g, g_head, accumulate):
     """dlogits [N*L, pitch] -> grads of lm_head, the token-level stack, its embedding; returns (dhidden,)."""
-    _ops.linear_wgrad(dlogits, hs, g_head, accumulate)
+    # lm_head weight gradient on the engine's side stream (joined at the end of rt.inner.backward)
+    side = _engine._side_stream(dlogits.device) if _engine.WGRAD_STREAM else None
+    _engine._wgrad(dlogits, hs, g_head, accumulate, side)
     dhs = _ops.linear_dgrad(dlogits, rt.lm_head)
     dx = rt.inner.backward(sv, dhs, g, accumulate=accumulate)
     if n_ids > 0:
