@@ -224,8 +224,18 @@ class GraphGenerator:
         self.seq = torch.full((batch, max_len, self.T), tok.pad_id, dtype=torch.long, device=dev)
         self.u = torch.zeros(batch, dtype=torch.float32, device=dev)
         self.counter = torch.zeros(2, dtype=torch.int64, device=dev)   # {call counter, seed} read by the RNG kernel
+        # extra sampling mask ANDed with the grammar ranges (app.py:27-34,73-87: disable_patch_change /
+        # disable_control_change / disable_channels); its address is baked into the graph, its contents are not
+        self.mask = torch.ones((batch, V), dtype=torch.uint8, device=dev)
         self.graph = None
         self.stream = torch.cuda.Stream(device=dev)
+
+    def set_deny(self, ids) -> None:
+        """Token ids that may never be sampled (empty = plain grammar)."""
+        self.mask.fill_(1)
+        ids = sorted(set(int(i) for i in ids))
+        if ids:
+            self.mask[:, torch.tensor(ids, dtype=torch.long, device=self.mask.device)] = 0
 
     def _event(self):
         B, T = self.B, self.T
@@ -248,7 +258,7 @@ class GraphGenerator:
             lib.call("b200_uniform_fill", self.u.data_ptr(), B, 0, self.counter.data_ptr(), lib.stream())
             lib.call("b200_sample_from_logits", logits.data_ptr(), B, self.V, logits.stride(0), self.temp, self.top_p,
                      self.top_k, i, self.ev_t.data_ptr(), self.g.lut.data_ptr(), self.g.n_event_types, self.g.eos, self.g.pad,
-                     None, self.u.data_ptr(), self.ev_t.data_ptr() + 8 * B * i, 1, lib.stream())
+                     self.mask.data_ptr(), self.u.data_ptr(), self.ev_t.data_ptr() + 8 * B * i, 1, lib.stream())
         lib.call("b200_event_commit", self.ev_t.data_ptr(), self.seq.data_ptr(), self.ev_in.data_ptr(), self.pos.data_ptr(),
                  B, T, self.max_len, lib.stream())
 
@@ -265,6 +275,39 @@ class GraphGenerator:
         self.ev_in.copy_(prompt[:, P - 1])
         self.counter.copy_(torch.tensor([0, self.seed], dtype=torch.int64))
 
+    def _prepare(self, prompt: torch.Tensor, use_graph: bool) -> None:
+        """Load the prompt into the device state; capture the per-event graph on first use (current stream = self.stream)."""
+        self._set_state(prompt)
+        if use_graph and self.graph is None:
+            self._event()                       # warm-up (allocations, function attributes) outside capture
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.stream):
+                self._event()
+            self.graph = g
+            self._set_state(prompt)             # undo the warm-up's state changes
+
+    def events(self, prompt: torch.Tensor, use_graph: bool = True):
+        """Generator form (app.py:27-120): yields each new event as an int64 [B, T] CPU tensor right after its graph
+        replay -- one device->host copy per EVENT, none per token -- and stops after the event in which every row
+        emitted EOS (app.py:119) or at max_len."""
+        P = prompt.shape[1]
+        cur = torch.cuda.current_stream()
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            self._prepare(prompt, use_graph)
+        for i in range(self.max_len - P):
+            with torch.cuda.stream(self.stream):          # not held across the yield
+                if use_graph:
+                    self.graph.replay()
+                else:
+                    self._event()
+                ev = self.seq[:, P + i].cpu()              # synchronises on this event only
+            yield ev
+            if bool((ev[:, 0] == self.tok.eos_id).all()):
+                break
+        cur.wait_stream(self.stream)
+
     def run(self, prompt: torch.Tensor, use_graph: bool = True, check_every: int = 32, progress=None,
             stop_on_eos: bool = True) -> torch.Tensor:
         P = prompt.shape[1]
@@ -274,15 +317,7 @@ class GraphGenerator:
         cur = torch.cuda.current_stream()
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
-            self._set_state(prompt)
-            if use_graph and self.graph is None:
-                self._event()                       # warm-up (allocations, function attributes) outside capture
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=self.stream):
-                    self._event()
-                self.graph = g
-                self._set_state(prompt)             # undo the warm-up's state changes
+            self._prepare(prompt, use_graph)
             done = 0
             stop_at = None
             while done < n_new:

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import json
 import os
+import threading
 from typing import Any, Dict, Optional, Union
 
 import numpy as np
@@ -118,6 +119,7 @@ class _Runtime:
         self.cached_inner = None
         self.grammar = None
         self.graph_gen = {}
+        self.gen_lock = threading.RLock()      # gradio serves generate from several threads (app.py:496)
 
 
 def _flat_ids(x: torch.Tensor) -> torch.Tensor:
@@ -335,27 +337,81 @@ class MIDIModel(PreTrainedModel):
         return out.reshape(*shape[:-1])
 
     @torch.inference_mode()
+    def _prompt_tensor(self, prompt, batch_size: int, dev) -> torch.Tensor:
+        """Prompt normalisation of midi_model.py:173-190 / app.py:36-54 -> int64 [B, P, T] on the device."""
+        tok = self.tokenizer
+        T = tok.max_token_seq
+        if prompt is None:
+            inp = torch.full((batch_size, 1, T), tok.pad_id, dtype=torch.long, device=dev)
+            inp[:, 0, 0] = tok.bos_id
+            return inp
+        if len(prompt.shape) == 2:
+            prompt = np.repeat(prompt[None, :], repeats=batch_size, axis=0)
+        elif prompt.shape[0] == 1:
+            prompt = np.repeat(prompt, repeats=batch_size, axis=0)
+        elif len(prompt.shape) != 3 or prompt.shape[0] != batch_size:
+            raise ValueError(f"invalid shape for prompt, {prompt.shape}")
+        prompt = prompt[..., :T]
+        if prompt.shape[-1] < T:
+            prompt = np.pad(prompt, ((0, 0), (0, 0), (0, T - prompt.shape[-1])), mode="constant",
+                            constant_values=tok.pad_id)
+        return torch.from_numpy(np.ascontiguousarray(prompt)).to(dtype=torch.long, device=dev)
+
+    def _graph_generator(self, batch_size, max_len, temp, top_p, top_k, generator):
+        """The (cached) device-resident generate loop for these settings, reseeded from `generator`."""
+        rt = self._rt()
+        gen_dev = generator.device if generator is not None else torch.device("cpu")
+        seed = int(torch.randint(0, 2 ** 62, (1,), generator=generator, device=gen_dev).item())
+        key = (batch_size, max_len, float(temp), float(top_p), int(top_k))
+        gg = rt.graph_gen.get(key)
+        if gg is None:
+            if rt.grammar is None:
+                rt.grammar = _dec.GrammarLUT(self.tokenizer, rt.store.device)
+            gg = _dec.GraphGenerator(self._cached_stack("outer"), self._cached_stack("inner"), rt.lm_head, rt.pitch,
+                                     rt.V, self.tokenizer, rt.grammar, batch_size, max_len, temp, top_p, top_k, seed)
+            rt.graph_gen.clear()               # keep one (KV pools are large)
+            rt.graph_gen[key] = gg
+        gg.seed = seed & ((1 << 63) - 1)
+        return gg
+
+    @torch.inference_mode()
+    def generate_stream(self, prompt=None, batch_size=1, max_len=512, temp=1.0, top_p=0.98, top_k=20,
+                        disable_patch_change=False, disable_control_change=False, disable_channels=None, generator=None):
+        """app.py:27-120 (the gradio app's own generate loop) on the device-resident loop: a Python generator that
+        yields every new event as an int64 numpy array [batch, max_token_seq], with the app's extra grammar options
+        (`disable_patch_change`, `disable_control_change`, `disable_channels` = channel numbers) applied as a device-side
+        mask, the app's 4096-event context window (app.py:55) and its stop rule (all rows EOS in the same event).
+        One device->host copy per event, no sync per token."""
+        tok = self.tokenizer
+        rt = self._rt()
+        dev = rt.store.device
+        deny = []
+        if disable_patch_change:
+            deny.append(tok.event_ids["patch_change"])
+        if disable_control_change:
+            deny.append(tok.event_ids["control_change"])
+        for c in (disable_channels or []):
+            deny.append(tok.parameter_ids["channel"][c])
+        inp = self._prompt_tensor(prompt, batch_size, dev)[:, -4096:]
+        if inp.shape[1] >= max_len:
+            return
+        mode = os.environ.get("B200_GENERATE", "graph")
+        with rt.gen_lock:                      # one generation at a time per model: the loop's state lives on the device
+            gg = self._graph_generator(batch_size, max_len, temp, top_p, top_k, generator)
+            gg.set_deny(deny)
+            try:
+                for ev in gg.events(inp, use_graph=(mode not in ("nograph", "eager"))):
+                    yield ev.numpy()
+            finally:
+                gg.set_deny(())
+
     def generate(self, prompt=None, batch_size=1, max_len=512, temp=1.0, top_p=0.98, top_k=20, generator=None):
         """midi_model.py:167-250 with the per-token work on the device (see midi_b200/decode.py)."""
         tok = self.tokenizer
         T = tok.max_token_seq
         rt = self._rt()
         dev = rt.store.device
-        if prompt is None:
-            inp = torch.full((batch_size, 1, T), tok.pad_id, dtype=torch.long, device=dev)
-            inp[:, 0, 0] = tok.bos_id
-        else:
-            if len(prompt.shape) == 2:
-                prompt = np.repeat(prompt[None, :], repeats=batch_size, axis=0)
-            elif prompt.shape[0] == 1:
-                prompt = np.repeat(prompt, repeats=batch_size, axis=0)
-            elif len(prompt.shape) != 3 or prompt.shape[0] != batch_size:
-                raise ValueError(f"invalid shape for prompt, {prompt.shape}")
-            prompt = prompt[..., :T]
-            if prompt.shape[-1] < T:
-                prompt = np.pad(prompt, ((0, 0), (0, 0), (0, T - prompt.shape[-1])), mode="constant",
-                                constant_values=tok.pad_id)
-            inp = torch.from_numpy(np.ascontiguousarray(prompt)).to(dtype=torch.long, device=dev)
+        inp = self._prompt_tensor(prompt, batch_size, dev)
         cur_len = inp.shape[1]
         if cur_len >= max_len:
             return inp.cpu().numpy()
@@ -364,19 +420,12 @@ class MIDIModel(PreTrainedModel):
         mode = os.environ.get("B200_GENERATE", "graph")
         if mode != "eager" and max_len - cur_len >= 4:
             # device-resident loop: one CUDA graph replay per event (midi_b200/decode.py::GraphGenerator)
-            gen_dev = generator.device if generator is not None else torch.device("cpu")
-            seed = int(torch.randint(0, 2 ** 62, (1,), generator=generator, device=gen_dev).item())
-            key = (batch_size, max_len, float(temp), float(top_p), int(top_k))
-            gg = rt.graph_gen.get(key)
-            if gg is None:
-                gg = _dec.GraphGenerator(self._cached_stack("outer"), self._cached_stack("inner"), rt.lm_head, rt.pitch,
-                                         rt.V, tok, rt.grammar, batch_size, max_len, temp, top_p, top_k, seed)
-                rt.graph_gen.clear()               # keep one (KV pools are large)
-                rt.graph_gen[key] = gg
-            gg.seed = seed & ((1 << 63) - 1)
-            bar = tqdm.tqdm(desc="generating", total=max_len - cur_len)
-            with bar:
-                out = gg.run(inp, use_graph=(mode != "nograph"), progress=bar.update)
+            with rt.gen_lock:
+                gg = self._graph_generator(batch_size, max_len, temp, top_p, top_k, generator)
+                gg.set_deny(())
+                bar = tqdm.tqdm(desc="generating", total=max_len - cur_len)
+                with bar:
+                    out = gg.run(inp, use_graph=(mode != "nograph"), progress=bar.update)
             return out.cpu().numpy()
         seq = torch.full((batch_size, max_len, T), tok.pad_id, dtype=torch.long, device=dev)
         seq[:, :cur_len] = inp

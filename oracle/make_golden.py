@@ -10,6 +10,8 @@ imported read-only through oracle/ref_loader.py.
               checksums, greedy generate ids, sample_top_p_k cases.
   medium.npz  tv2o-medium seed-0 init checksums + fp32 hidden/logits slices and
               loss on a (1,17,8) synthetic batch (weights regenerated from seed).
+  app_stream.npz  events yielded by the reference's app.py generate() (app.py:27-120, executed from the reference
+              file at run time, nothing copied) on the tiny model with the disable_* options, greedy and sampled.
 """
 from __future__ import annotations
 
@@ -142,8 +144,55 @@ def medium():
     print("medium.npz: loss", float(loss))
 
 
+def ref_app_generate(model, tokenizer):
+    """The reference's `generate` generator function of app.py:27-120, compiled from the reference file itself (the module
+    cannot be imported: gradio / synthesizer dependencies) into a namespace holding its two globals."""
+    import ast
+    import tqdm
+    from transformers import DynamicCache
+    path = os.path.join(ref_loader.REF_DIR, "app.py")
+    tree = ast.parse(open(path).read(), filename=path)
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "generate"]
+    assert len(fn) == 1
+    ns = {"torch": torch, "np": np, "tqdm": tqdm, "F": F, "DynamicCache": DynamicCache, "model": model, "tokenizer": tokenizer}
+    exec(compile(ast.Module(body=fn, type_ignores=[]), path, "exec"), ns)
+    return ns["generate"]
+
+
+APP_CASES = {
+    "greedy": dict(prompt=None, batch_size=2, max_len=14, top_k=1, disable_patch_change=True, disable_control_change=True,
+                   disable_channels=list(range(9))),
+    "sampled": dict(prompt="batch4", batch_size=2, max_len=12, temp=1.0, top_p=0.98, top_k=20, disable_patch_change=False,
+                    disable_control_change=True, disable_channels=[9], seed=3),
+    "plain": dict(prompt="batch4", batch_size=2, max_len=10, top_k=1),
+}
+
+
+def app_stream():
+    mm, _ = ref_loader.load()
+    torch.manual_seed(0)
+    cfg = mm.MIDIModelConfig.get_config("v2", True, n_layer=4, n_head=4, n_embd=32, n_inner=64)
+    model = mm.MIDIModel(cfg).eval()                    # same seed-0 weights as tiny.npz
+    gen = ref_app_generate(model, model.tokenizer)
+    batch = synth_batch(model.tokenizer, 2, 13, seed=7, pad_tail=2)
+    out = {"prompt": batch[:, :4].numpy()}
+    for name, kw in APP_CASES.items():
+        kw = dict(kw)
+        if kw.get("prompt") == "batch4":
+            kw["prompt"] = batch[:, :4].numpy()
+        seed = kw.pop("seed", 0)
+        evs = list(gen(generator=torch.Generator().manual_seed(seed), **kw))
+        out[name] = np.stack(evs, axis=1)
+        print("app_stream", name, out[name].shape)
+    np.savez_compressed(os.path.join(OUT, "app_stream.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    tiny()
-    medium()
+    if len(sys.argv) > 1 and sys.argv[1] == "app_stream":
+        app_stream()
+    else:
+        tiny()
+        medium()
+        app_stream()

@@ -250,28 +250,51 @@ def grammar_tables(tok) -> dict:
 
 
 @torch.no_grad()
-def generate(sd, cfg: ModelCfg, tok, prompt=None, batch_size=1, max_len=512, temp=1.0, top_p=0.98, top_k=20,
-             generator=None, inv_freq_net=None, inv_freq_tok=None):
-    """midi_model.py:167-250 restated (same quirks: `end` reset per event,
-    early exit only when all rows end on the same event)."""
+def _prompt_tensor(tok, prompt, batch_size, dev):
+    """Prompt normalisation shared by midi_model.py:173-190 and app.py:36-54."""
     import numpy as np
     T = tok.max_token_seq
-    dev = sd["lm_head.weight"].device
     if prompt is None:
         inp = torch.full((1, T), tok.pad_id, dtype=torch.long, device=dev)
         inp[0, 0] = tok.bos_id
-        inp = inp.unsqueeze(0).repeat(batch_size, 1, 1)
-    else:
-        if prompt.ndim == 2:
-            prompt = np.repeat(prompt[None, :], batch_size, axis=0)
-        elif prompt.shape[0] == 1:
-            prompt = np.repeat(prompt, batch_size, axis=0)
-        elif prompt.ndim != 3 or prompt.shape[0] != batch_size:
-            raise ValueError(f"invalid shape for prompt, {prompt.shape}")
-        prompt = prompt[..., :T]
-        if prompt.shape[-1] < T:
-            prompt = np.pad(prompt, ((0, 0), (0, 0), (0, T - prompt.shape[-1])), constant_values=tok.pad_id)
-        inp = torch.from_numpy(prompt).to(dtype=torch.long, device=dev)
+        return inp.unsqueeze(0).repeat(batch_size, 1, 1)
+    if prompt.ndim == 2:
+        prompt = np.repeat(prompt[None, :], batch_size, axis=0)
+    elif prompt.shape[0] == 1:
+        prompt = np.repeat(prompt, batch_size, axis=0)
+    elif prompt.ndim != 3 or prompt.shape[0] != batch_size:
+        raise ValueError(f"invalid shape for prompt, {prompt.shape}")
+    prompt = prompt[..., :T]
+    if prompt.shape[-1] < T:
+        prompt = np.pad(prompt, ((0, 0), (0, 0), (0, T - prompt.shape[-1])), constant_values=tok.pad_id)
+    return torch.from_numpy(prompt).to(dtype=torch.long, device=dev)
+
+
+def deny_ids(tok, disable_patch_change=False, disable_control_change=False, disable_channels=None):
+    """Token ids app.py:31-34,73-76,86-87 removes from the grammar masks (event-type ids at step 0, channel ids)."""
+    deny = set()
+    if disable_patch_change:
+        deny.add(tok.event_ids["patch_change"])
+    if disable_control_change:
+        deny.add(tok.event_ids["control_change"])
+    for c in (disable_channels or []):
+        deny.add(tok.parameter_ids["channel"][c])
+    return deny
+
+
+def generate_stream(sd, cfg: ModelCfg, tok, prompt=None, batch_size=1, max_len=512, temp=1.0, top_p=0.98, top_k=20,
+                    generator=None, inv_freq_net=None, inv_freq_tok=None, deny=(), max_context=None):
+    """The generate loop of midi_model.py:167-250 / app.py:27-120 restated as a Python generator: yields the first
+    (prompt) block [B, P, T] and then one int64 [B, T] event per iteration.  Same quirks: `end` is reset per event and
+    the loop exits only when all rows end on the same event.  `deny` = ids removed from every grammar mask
+    (app.py's disable_* options, see deny_ids); `max_context` = app.py:55's `input_tensor[:, -4096:]`."""
+    T = tok.max_token_seq
+    dev = sd["lm_head.weight"].device
+    inp = _prompt_tensor(tok, prompt, batch_size, dev)
+    if max_context is not None:
+        inp = inp[:, -max_context:]
+    deny = set(deny)
+    yield inp
     cur_len = inp.shape[1]
     cache1 = KV()
     past_len = 0
@@ -289,13 +312,14 @@ def generate(sd, cfg: ModelCfg, tok, prompt=None, batch_size=1, max_len=512, tem
                     mask[b, tok.pad_id] = 1
                     continue
                 if i == 0:
-                    mask[b, list(tok.event_ids.values()) + [tok.eos_id]] = 1
+                    ids = list(tok.event_ids.values()) + [tok.eos_id]
                 else:
                     pn = tok.events[names[b]]
                     if i > len(pn):
                         mask[b, tok.pad_id] = 1
                         continue
-                    mask[b, tok.parameter_ids[pn[i - 1]]] = 1
+                    ids = tok.parameter_ids[pn[i - 1]]
+                mask[b, [t for t in ids if t not in deny]] = 1
             mask = mask.unsqueeze(1)
             if i == 0:
                 logits = forward_token(sd, cfg, hidden, None, cache2, inv_freq_tok)[:, -1:]
@@ -322,9 +346,19 @@ def generate(sd, cfg: ModelCfg, tok, prompt=None, batch_size=1, max_len=512, tem
         inp = torch.cat([inp, seq.unsqueeze(1)], dim=1)
         past_len = cur_len
         cur_len += 1
+        yield seq
         if all(end):
             break
-    return inp.cpu().numpy()
+
+
+def generate(sd, cfg: ModelCfg, tok, prompt=None, batch_size=1, max_len=512, temp=1.0, top_p=0.98, top_k=20,
+             generator=None, inv_freq_net=None, inv_freq_tok=None, deny=(), max_context=None):
+    """midi_model.py:167-250: the whole [B, L, T] result as numpy (prompt + generated events)."""
+    blocks = []
+    for blk in generate_stream(sd, cfg, tok, prompt, batch_size, max_len, temp, top_p, top_k, generator, inv_freq_net,
+                               inv_freq_tok, deny, max_context):
+        blocks.append(blk if blk.dim() == 3 else blk.unsqueeze(1))
+    return torch.cat(blocks, dim=1).cpu().numpy()
 
 
 # --------------------------------------------------------------------------

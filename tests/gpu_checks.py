@@ -778,6 +778,29 @@ def check_model_peaked_greedy():
         print("first divergence at event", first_e, "row", b0, "token", t0, "ref", ids_ref[b0, first_e], "new", ids_new[b0, first_e])
     top2 = l32a[:, 8:].topk(2, -1).values
     out["peaked_min_top1_margin_fp32"] = float((top2[..., 0] - top2[..., 1])[ref_t[:, 9:] != 0].min())
+    # app.py's streaming loop: same events as generate() when no option is set, and with the
+    # disable_* options the oracle's restatement of app.py:27-120 event for event (greedy), no denied id emitted
+    P0 = prompt.shape[1]
+    evs = list(model.generate_stream(prompt=prompt, batch_size=4, max_len=40, top_k=1))
+    ids_stream = np.stack(evs, axis=1)
+    out["stream_vs_generate_mismatch"] = (float((ids_stream != ids_new[:, P0:]).sum())
+                                          if ids_stream.shape == ids_new[:, P0:].shape else 1e9)
+    chans = [int(c) for c in np.unique([tok.tokens2event(r.tolist())[1 + tok.events["note"].index("channel")]
+                                        for r in ids_new[:, P0:].reshape(-1, 8) if r[0] == tok.event_ids["note"]])][:2]
+    deny = O.deny_ids(tok, True, True, chans)
+    evs = list(model.generate_stream(prompt=prompt, batch_size=4, max_len=40, top_k=1, disable_patch_change=True,
+                                     disable_control_change=True, disable_channels=chans))
+    ids_masked = np.stack(evs, axis=1)
+    ref_masked = O.generate(sd16, ocfg, tok, prompt, batch_size=4, max_len=40, top_k=1, deny=deny, max_context=4096,
+                            inv_freq_net=model.net.rotary_emb.inv_freq, inv_freq_tok=model.net_token.rotary_emb.inv_freq)[:, P0:]
+    out["stream_masked_mismatch"] = (float((ids_masked != ref_masked).sum()) if ids_masked.shape == ref_masked.shape
+                                     else 1e9)
+    out["stream_denied_ids_emitted"] = float(np.isin(ids_masked, sorted(deny)).sum())
+    out["stream_masked_differs_from_plain"] = float((ids_masked[:, :min(ids_masked.shape[1], ids_stream.shape[1])]
+                                                     != ids_stream[:, :min(ids_masked.shape[1], ids_stream.shape[1])]).sum())
+    print("stream: disabled channels", chans, "masked events", ids_masked.shape[1], "plain events", ids_stream.shape[1])
+    ids_after = model.generate(prompt=prompt, batch_size=4, max_len=40, top_k=1)      # the mask must not leak into generate()
+    out["stream_mask_leak_mismatch"] = float((ids_after != ids_new).sum()) if ids_after.shape == ids_new.shape else 1e9
     # the generated continuation is itself grammar-valid
     bad = sum(1 for row in ids_new[:, 1:].reshape(-1, 8) if row[0] not in (tok.eos_id, tok.pad_id) and tok.tokens2event(row.tolist()) == [])
     out["peaked_invalid_events"] = float(bad)
@@ -854,7 +877,8 @@ THRESH = [
     ("loss_abs", 3e-2), ("grad_global_rel", 6e-2), ("grad_pad_row", 0.0), ("autograd_loss_abs", 5e-2),
     ("autograd_grad_global_rel", 6e-2),
     ("cached_vs_full_hidden", 3e-2), ("inner_cached_vs_full_logits", 3e-2), ("min:greedy_token_agree", 0.6),
-    ("peaked_greedy_mismatch", 0.0), ("peaked_eager_vs_graph_mismatch", 0.0), ("peaked_invalid_events", 0.0), ("peaked_loss_last", 1.5),
+    ("stream_vs_generate_mismatch", 0.0), ("stream_masked_mismatch", 0.0), ("stream_denied_ids_emitted", 0.0),
+    ("stream_mask_leak_mismatch", 0.0), ("peaked_greedy_mismatch", 0.0), ("peaked_eager_vs_graph_mismatch", 0.0), ("peaked_invalid_events", 0.0), ("peaked_loss_last", 1.5),
     ("peaked_argmax_mismatch_vs_fp32", 0.0), ("peaked_logits_vs_fp32", 3e-2),
     ("sampled_invalid_events", 0.0), ("greedy_graph_vs_nograph_mismatch", 0.0), ("fused_decode_mismatch", 0.0), ("fused_lm_head_mismatch", 0.0),
 ]

@@ -93,6 +93,20 @@ def test_medium_seeded_init_and_oracle_golden(golden_medium):
     assert abs(loss.item() - float(g["fp32/loss"])) < 1e-4
 
 
+def test_generate_signatures_follow_the_reference():
+    """MIDIModel.generate = midi_model.py:167-168; MIDIModel.generate_stream = app.py:28-29 (the app's own loop)."""
+    import inspect
+    import midi_model as mm
+    gen = list(inspect.signature(mm.MIDIModel.generate).parameters)[1:]
+    assert gen == ["prompt", "batch_size", "max_len", "temp", "top_p", "top_k", "generator"]
+    st = inspect.signature(mm.MIDIModel.generate_stream).parameters
+    assert list(st)[1:] == ["prompt", "batch_size", "max_len", "temp", "top_p", "top_k", "disable_patch_change",
+                            "disable_control_change", "disable_channels", "generator"]
+    assert [st[k].default for k in list(st)[1:]] == [None, 1, 512, 1.0, 0.98, 20, False, False, None, None]
+    assert inspect.isgeneratorfunction(inspect.unwrap(mm.MIDIModel.generate_stream)) or \
+        inspect.isgeneratorfunction(mm.MIDIModel.generate_stream)
+
+
 def test_no_cpu_fallback():
     import midi_model as mm
     from midi_b200.lib import B200Error

@@ -114,6 +114,56 @@ def test_generate_greedy_golden(golden_tiny):
     np.testing.assert_array_equal(ids2, g["gen/greedy_prompt_ids"])
 
 
+def _app_stream_kwargs(name, g):
+    from oracle.make_golden import APP_CASES
+    kw = dict(APP_CASES[name])
+    prompt = g["prompt"] if kw.pop("prompt", None) == "batch4" else None
+    seed = kw.pop("seed", 0)
+    tok = TokenizerTables("v2")
+    deny = O.deny_ids(tok, kw.pop("disable_patch_change", False), kw.pop("disable_control_change", False),
+                      kw.pop("disable_channels", None))
+    return tok, prompt, seed, deny, kw
+
+
+@pytest.mark.parametrize("case", ["greedy", "sampled", "plain"])
+def test_app_stream_golden(golden_tiny, case):
+    """oracle.generate_stream (+ deny masks, 4096-event window) == the events the reference's app.py generate() yields
+    (tests/golden/app_stream.npz, produced by oracle/make_golden.py from the reference file itself)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "app_stream.npz"))
+    tok, prompt, seed, deny, kw = _app_stream_kwargs(case, g)
+    sd = tiny_sd(golden_tiny)
+    blocks = list(O.generate_stream(sd, TINY, tok, prompt, generator=torch.Generator().manual_seed(seed), deny=deny,
+                                    max_context=4096, **kw))
+    P = blocks[0].shape[1]
+    assert P == (1 if prompt is None else prompt.shape[1])
+    evs = np.stack([b.numpy() for b in blocks[1:]], axis=1)
+    np.testing.assert_array_equal(evs, g[case])
+    assert not np.isin(evs, sorted(deny)).any()
+    if case == "plain":      # no options: identical to MIDIModel.generate's continuation (midi_model.py:167-250)
+        np.testing.assert_array_equal(evs, golden_tiny["gen/greedy_prompt_ids"][:, P:])
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference not present")
+def test_app_stream_vs_live_reference(golden_tiny):
+    """Same comparison against app.py's generate() executed live from /root/reference (build container only)."""
+    from oracle.make_golden import ref_app_generate, APP_CASES
+    mm, _ = ref_loader.load()
+    torch.manual_seed(0)
+    cfg = mm.MIDIModelConfig.get_config("v2", True, n_layer=4, n_head=4, n_embd=32, n_inner=64)
+    model = mm.MIDIModel(cfg).eval()
+    gen = ref_app_generate(model, model.tokenizer)
+    tok = TokenizerTables("v2")
+    kw = dict(batch_size=3, max_len=9, temp=0.9, top_p=0.95, top_k=10, disable_patch_change=True,
+              disable_control_change=False, disable_channels=[0, 3])
+    ref = np.stack(list(gen(prompt=None, generator=torch.Generator().manual_seed(21), **kw)), axis=1)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    deny = O.deny_ids(tok, True, False, [0, 3])
+    blocks = list(O.generate_stream(sd, TINY, tok, None, batch_size=3, max_len=9, temp=0.9, top_p=0.95, top_k=10,
+                                    generator=torch.Generator().manual_seed(21), deny=deny, max_context=4096))
+    np.testing.assert_array_equal(np.stack([b.numpy() for b in blocks[1:]], axis=1), ref)
+
+
 def test_sampler_golden(golden_tiny):
     g = golden_tiny
     probs = torch.from_numpy(g["samp/probs"])
