@@ -255,10 +255,15 @@ def run_native(args):
             print(*r, file=sys.stderr)
 
     losses = []
+    # end to end through the public API: int16 token batches in pinned host memory (the dataset's own dtype,
+    # train.py:71) -> midi_b200.data.Prefetcher (H2D of batch i+1 on a copy stream while step i runs, inside the timed
+    # region) -> MIDIModel.training_loss (widening + x/y split on the device) -> D2H read of the loss every step
+    from midi_b200 import data as _data
+    host16 = [_data.collate(list(h.numpy()), pad_id=0) for h in host]
+    feed = iter(_data.Prefetcher((host16[i % n_batches] for i in range(K)), dev))
 
     def e2e_step(i):
-        b = host[i % n_batches].to(dev, non_blocking=True)  # H2D of this step's batch (pinned host memory)
-        losses.append(float(step(b)))                       # D2H read of the loss
+        losses.append(float(step(next(feed))))              # D2H read of the loss
 
     ms_e2e, _, _, _ = timed(e2e_step, K)
 
@@ -279,7 +284,7 @@ def run_native(args):
                    "parallelism": f"dp{world}", "weights": "seeded-init (torch.manual_seed(0))",
                    "l2": "per-step working set ~20 GB >> 126 MB L2 (no explicit flush needed); 4 distinct batches cycled"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
-                "h2d_bytes_per_step": int(host[0].numel() * host[0].element_size()), "d2h_bytes_per_step": 4,
+                "h2d_bytes_per_step": int(host16[0].numel() * host16[0].element_size()), "d2h_bytes_per_step": 4,
                 "last_loss": losses[-1] if losses else None},
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -44,6 +44,9 @@ int b200_embed_sum_fwd(const long long* ids, const void* table, void* out, int M
 int b200_inner_input_fwd(const void* hidden /*may be NULL*/, const long long* ids, const void* table, void* out,
                          int n_events, int n_ids, int H, int V, cudaStream_t s);
 int b200_inner_input_bwd_hidden(const void* dx, void* dhidden, int n_events, int Tin, int H, cudaStream_t s);
+/* host data path (train.py:71 int16 token matrices; train.py:169-176 x = batch[:, :-1], y = batch[:, 1:]):
+   batch int16 [B, S1, T] -> x, y int64 [B*(S1-1), T] in one pass */
+int b200_batch_to_xy_i16(const void* batch, int B, int S1, int T, long long* x, long long* y, cudaStream_t s);
 size_t b200_embed_bwd_workspace_bytes(int n_ids, int V, int H);
 /* id i reads gradient row (i / per_row) * row_stride + (i % per_row) * row_inner + row_off; pad row gets 0 */
 int b200_embed_bwd(const long long* ids, int n_ids, const void* dout, void* dtable, int V, int H, int per_row,

@@ -534,6 +534,30 @@ extern "C" int b200_inner_input_bwd_hidden(const void* dx, void* dhidden, int n_
     return B200_OK;
 }
 
+// Host data path (train.py:71,168-176): the dataset keeps token matrices as int16; one launch widens a [B, S+1, T] int16
+// batch and cuts it into the two contiguous int64 views the step needs, x = batch[:, :-1] and y = batch[:, 1:].
+namespace {
+__global__ void batch_to_xy_kernel(const short* __restrict__ b, long long* __restrict__ x, long long* __restrict__ y,
+                                   long long n, int S, int T) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long per = (long long)S * T;
+        const long long bi = i / per, rem = i - bi * per;
+        const short* src = b + bi * (per + T) + rem;
+        x[i] = src[0];
+        y[i] = src[T];
+    }
+}
+}   // namespace
+
+extern "C" int b200_batch_to_xy_i16(const void* batch, int B, int S1, int T, long long* x, long long* y, cudaStream_t stream) {
+    B200_CHECK_ARG(B >= 0 && S1 >= 1 && T >= 1, "batch_to_xy: bad shape (%d, %d, %d)", B, S1, T);
+    const long long n = (long long)B * (S1 - 1) * T;
+    if (n == 0) return B200_OK;
+    batch_to_xy_kernel<<<grid_for((size_t)n, 256), 256, 0, stream>>>((const short*)batch, x, y, n, S1 - 1, T);
+    B200_CHECK_LAUNCH("batch_to_xy");
+    return B200_OK;
+}
+
 extern "C" size_t b200_embed_bwd_workspace_bytes(int n_ids, int V, int H) {
     return (size_t)(3 * (V + 1) + n_ids) * sizeof(int) + 256 + (size_t)V * H * sizeof(float);
 }

@@ -26,6 +26,7 @@ SIGNATURES = {
     "b200_embed_sum_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
     "b200_inner_input_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "b200_inner_input_bwd_hidden": (i32, [vp, vp, i32, i32, i32, vp]),
+    "b200_batch_to_xy_i16": (i32, [vp, i32, i32, i32, vp, vp, vp]),
     "b200_embed_bwd_workspace_bytes": (sz, [i32, i32, i32]),
     "b200_embed_bwd": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, sz, vp]),
     "b200_rmsnorm_fwd": (i32, [vp, vp, vp, vp, i32, i32, f32, vp]),

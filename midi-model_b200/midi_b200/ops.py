@@ -58,6 +58,17 @@ def inner_input(hidden: Optional[torch.Tensor], ids: Optional[torch.Tensor], tab
     return out
 
 
+def batch_to_xy(batch: torch.Tensor):
+    """int16 [B, S+1, T] token batch (train.py:71) -> (x, y) int64 [B*S, T]: x = batch[:, :-1], y = batch[:, 1:]."""
+    if not batch.is_cuda or batch.dtype != torch.int16 or not batch.is_contiguous():
+        raise lib.B200Error(f"batch_to_xy: expected a contiguous CUDA int16 batch, got {batch.dtype} on {batch.device}")
+    B, S1, T = batch.shape
+    x = torch.empty((B * (S1 - 1), T), dtype=torch.long, device=batch.device)
+    y = torch.empty_like(x)
+    lib.call("b200_batch_to_xy_i16", batch.data_ptr(), B, S1, T, x.data_ptr(), y.data_ptr(), lib.stream())
+    return x, y
+
+
 def embed_bwd(ids: torch.Tensor, dout: torch.Tensor, dtable: torch.Tensor, per_row: int, row_stride: int, row_inner: int,
               row_off: int, pad_id: int, accumulate: bool):
     V, H = dtable.shape

@@ -491,9 +491,12 @@ class MIDIModel(PreTrainedModel):
         tok = self.tokenizer
         B, S1, T = batch.shape
         S = S1 - 1
-        batch = batch.to(torch.long)
-        x = batch[:, :-1].contiguous().view(B * S, T)
-        y = batch[:, 1:].contiguous().view(B * S, T)
+        if batch.dtype == torch.int16:
+            x, y = _ops.batch_to_xy(batch.contiguous())        # int16 host data path (midi_b200/data.py): one widening pass
+        else:
+            batch = batch.to(torch.long)
+            x = batch[:, :-1].contiguous().view(B * S, T)
+            y = batch[:, 1:].contiguous().view(B * S, T)
         e = _ops.embed_sum(x, rt.outer.embed)
         hidden, sv_o = rt.outer.forward(e, B, S, self.net.rotary_emb.inv_freq, save=backward)
         ids_in = y[:, :-1].contiguous()

@@ -627,7 +627,21 @@ def check_model_train():
         tot_n += float((p.grad.float() - sd[n].grad).double().pow(2).sum())
         tot_d += float(sd[n].grad.double().pow(2).sum())
     out["autograd_grad_global_rel"] = math.sqrt(tot_n / tot_d)
-    # 5 fused steps: loss curve vs torch AdamW on the oracle (tier 3)
+    # int16 host data path (midi_b200/data.py): device-side widening + x/y split, prefetcher, same loss bit for bit
+    from midi_b200 import data as hostdata
+    b16 = hostdata.collate(list(batch.cpu().numpy()), pad_id=model.tokenizer.pad_id)
+    xs, ys = ops.batch_to_xy(b16.to(DEV))
+    out["xy_split_mismatch"] = float((xs.view(2, -1, 8) != batch[:, :-1]).sum() + (ys.view(2, -1, 8) != batch[:, 1:]).sum())
+    fed = list(hostdata.Prefetcher([b16, b16, b16], DEV))
+    out["prefetch_mismatch"] = float(sum((f.to(torch.long) != batch).sum() for f in fed)) + abs(len(fed) - 3)
+    for p in model.parameters():
+        p.grad = None
+    loss16 = model.training_loss(fed[0])
+    out["int16_path_loss_mismatch"] = float((loss16 - loss).abs())
+    # (gradients: the backward accumulates dQ / embedding rows with fp32 reductions whose order is not fixed -> rel. error)
+    num = sum(float((p.grad.float() - fused[n].float()).double().pow(2).sum()) for n, p in model.named_parameters())
+    den = sum(float(fused[n].float().double().pow(2).sum()) for n, p in model.named_parameters())
+    out["int16_path_grad_rel"] = math.sqrt(num / den)
     return out
 
 
@@ -877,7 +891,7 @@ THRESH = [
     ("loss_abs", 3e-2), ("grad_global_rel", 6e-2), ("grad_pad_row", 0.0), ("autograd_loss_abs", 5e-2),
     ("autograd_grad_global_rel", 6e-2),
     ("cached_vs_full_hidden", 3e-2), ("inner_cached_vs_full_logits", 3e-2), ("min:greedy_token_agree", 0.6),
-    ("stream_vs_generate_mismatch", 0.0), ("stream_masked_mismatch", 0.0), ("stream_denied_ids_emitted", 0.0),
+    ("xy_split_mismatch", 0.0), ("prefetch_mismatch", 0.0), ("int16_path_loss_mismatch", 0.0), ("int16_path_grad_rel", 1e-3), ("stream_vs_generate_mismatch", 0.0), ("stream_masked_mismatch", 0.0), ("stream_denied_ids_emitted", 0.0),
     ("stream_mask_leak_mismatch", 0.0), ("peaked_greedy_mismatch", 0.0), ("peaked_eager_vs_graph_mismatch", 0.0), ("peaked_invalid_events", 0.0), ("peaked_loss_last", 1.5),
     ("peaked_argmax_mismatch_vs_fp32", 0.0), ("peaked_logits_vs_fp32", 3e-2),
     ("sampled_invalid_events", 0.0), ("greedy_graph_vs_nograph_mismatch", 0.0), ("fused_decode_mismatch", 0.0), ("fused_lm_head_mismatch", 0.0),

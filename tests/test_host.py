@@ -107,6 +107,24 @@ def test_generate_signatures_follow_the_reference():
         inspect.isgeneratorfunction(mm.MIDIModel.generate_stream)
 
 
+def test_collate_int16_matches_reference_collate_fn():
+    """midi_b200.data.collate == train.py:82-86 (F.pad to the longest sample with pad_id, stack), kept in int16."""
+    import torch.nn.functional as F
+    from midi_b200 import data
+    rng = np.random.default_rng(0)
+    samples = [rng.integers(0, 3406, size=(n, 8)).astype(np.int16) for n in (5, 1, 9, 3)]
+    got = data.collate(samples, pad_id=0, pin=False)
+    ref = [torch.from_numpy(s.astype(np.int64)) for s in samples]                    # train.py:79-80
+    mx = max(len(m) for m in ref)
+    ref = torch.stack([F.pad(m, (0, 0, 0, mx - m.shape[0]), mode="constant", value=0) for m in ref])
+    assert got.dtype == torch.int16 and got.shape == ref.shape
+    assert torch.equal(got.to(torch.int64), ref)
+    with pytest.raises(ValueError):
+        data.collate([np.full((2, 8), 40000, dtype=np.int64)], pin=False)
+    with pytest.raises(ValueError):
+        data.collate([], pin=False)
+
+
 def test_no_cpu_fallback():
     import midi_model as mm
     from midi_b200.lib import B200Error
