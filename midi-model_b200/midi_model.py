@@ -17,6 +17,7 @@ Extra (non-reference) entry points used by the fused trainer and the benchmark:
 from __future__ import annotations
 
 import json
+import math
 import os
 import threading
 from typing import Any, Dict, Optional, Union
@@ -242,8 +243,14 @@ class MIDIModel(PreTrainedModel):
         return rt
 
     def load_merge_lora(self, model_id):
-        """midi_model.py:109-114 (peft imported lazily: it is only needed here)."""
-        from peft import LoraModel, PeftConfig, load_peft_weights, set_peft_model_state_dict
+        """midi_model.py:109-114: merge a LoRA adapter into the base weights and return the merged model.
+        With `peft` installed this is the reference's own sequence; without it (this image) the adapter directory
+        (`adapter_config.json` + `adapter_model.safetensors`/`.bin`, as written by train.py:234-244 or by peft) is merged
+        natively: W += (B @ A) * scaling, in place on the packed parameter buffer."""
+        try:
+            from peft import LoraModel, PeftConfig, load_peft_weights, set_peft_model_state_dict
+        except ImportError:
+            return self._merge_lora_native(model_id)
         peft_config = PeftConfig.from_pretrained(model_id)
         model = LoraModel(self, peft_config, adapter_name="default")
         adapter_state_dict = load_peft_weights(model_id, device=str(self.device))
@@ -251,6 +258,71 @@ class MIDIModel(PreTrainedModel):
         merged = model.merge_and_unload()
         self.__dict__["_b200_rt"] = None
         return merged
+
+    def _merge_lora_native(self, adapter_dir: str):
+        """LoRA merge without peft (what LoraModel.merge_and_unload computes for nn.Linear targets): for every target
+        module, delta = lora_B @ lora_A scaled by lora_alpha / r (lora_alpha / sqrt(r) with use_rslora; per-module
+        rank_pattern / alpha_pattern honoured), accumulated in fp32 and rounded once into the weight's dtype."""
+        import json
+        import re
+        cfg_path = os.path.join(adapter_dir, "adapter_config.json")
+        if not os.path.isfile(cfg_path):
+            raise FileNotFoundError(f"load_merge_lora: {cfg_path} not found (a local adapter directory is required without peft)")
+        with open(cfg_path) as f:
+            cfg = json.load(f)
+        if str(cfg.get("peft_type", "LORA")).upper() != "LORA":
+            raise ValueError(f"load_merge_lora: unsupported peft_type {cfg.get('peft_type')}")
+        st_path = os.path.join(adapter_dir, "adapter_model.safetensors")
+        if os.path.isfile(st_path):
+            from safetensors.torch import load_file
+            weights = load_file(st_path)
+        else:
+            weights = torch.load(os.path.join(adapter_dir, "adapter_model.bin"), map_location="cpu", weights_only=True)
+        r0, alpha0 = int(cfg["r"]), float(cfg.get("lora_alpha", cfg["r"]))
+        rank_pattern, alpha_pattern = cfg.get("rank_pattern") or {}, cfg.get("alpha_pattern") or {}
+        rslora, fan_in_fan_out = bool(cfg.get("use_rslora", False)), bool(cfg.get("fan_in_fan_out", False))
+
+        def pattern(table, name, default):
+            for k, v in table.items():
+                if re.fullmatch(rf"(.*\.)?{k}", name):
+                    return v
+            return default
+
+        # key = [base_model.model.]<module path>.lora_{A,B}[.<adapter name>].weight
+        pairs = {}
+        for k, v in weights.items():
+            mobj = re.fullmatch(r"(?:base_model\.model\.)?(.+)\.lora_(A|B)(?:\.[^.]+)?\.weight", k)
+            if mobj is None:
+                if "lora_embedding" in k:
+                    raise NotImplementedError("load_merge_lora: LoRA on embeddings is not supported by the native merge")
+                continue
+            pairs.setdefault(mobj.group(1), {})[mobj.group(2)] = v
+        if not pairs:
+            raise ValueError("load_merge_lora: no lora_A / lora_B tensors in the adapter")
+        modules = dict(self.named_modules())
+        with torch.no_grad():
+            for name, ab in sorted(pairs.items()):
+                if "A" not in ab or "B" not in ab:
+                    raise ValueError(f"load_merge_lora: incomplete LoRA pair for {name}")
+                mod = modules.get(name)
+                if not isinstance(mod, nn.Linear):
+                    raise ValueError(f"load_merge_lora: target {name} is not a Linear layer of this model")
+                W = mod.weight
+                A = ab["A"].to(device=W.device, dtype=torch.float32)       # [r, in]
+                Bm = ab["B"].to(device=W.device, dtype=torch.float32)      # [out, r]
+                r = int(pattern(rank_pattern, name, r0))
+                if A.shape[0] != r or Bm.shape[1] != r:
+                    r = A.shape[0]
+                alpha = float(pattern(alpha_pattern, name, alpha0))
+                scaling = alpha / math.sqrt(r) if rslora else alpha / r
+                delta = (Bm @ A) * scaling
+                if fan_in_fan_out:
+                    delta = delta.t()
+                if delta.shape != W.shape:
+                    raise ValueError(f"load_merge_lora: {name}: delta {tuple(delta.shape)} vs weight {tuple(W.shape)}")
+                W.copy_((W.float() + delta).to(W.dtype))
+        self.__dict__["_b200_rt"] = None          # fused views / cached stacks are rebuilt from the merged weights
+        return self
 
     def _kv_for(self, cache, which: str, batch: int):
         rt = self._rt()

@@ -125,6 +125,48 @@ def test_collate_int16_matches_reference_collate_fn():
         data.collate([], pin=False)
 
 
+def test_native_lora_merge(tmp_path):
+    """load_merge_lora (midi_model.py:109-114) without peft: W += B @ A * alpha / r on every target Linear, nothing else
+    touched; accepts train.py's save_peft key layout and peft's `base_model.model.` prefixed layout."""
+    import json
+    import midi_model as mm
+    from safetensors.torch import save_file
+    try:
+        import peft  # noqa: F401
+        pytest.skip("peft installed: the reference sequence is used instead of the native merge")
+    except ImportError:
+        pass
+    torch.manual_seed(0)
+    cfg = mm.MIDIModelConfig.get_config("v2", True, n_layer=4, n_head=4, n_embd=32, n_inner=64)
+    m = mm.MIDIModel(cfg)
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(1)
+    r, alpha = 4, 8.0
+    targets = ["net.layers.0.self_attn.q_proj", "net.layers.1.self_attn.v_proj", "net_token.layers.0.self_attn.q_proj"]
+    w = {}
+    for i, t in enumerate(targets):
+        out_f, in_f = before[t + ".weight"].shape
+        prefix = "base_model.model." if i == 1 else ""
+        suffix = ".default" if i == 2 else ""
+        w[f"{prefix}{t}.lora_A{suffix}.weight"] = torch.randn(r, in_f, generator=g) * 0.1
+        w[f"{prefix}{t}.lora_B{suffix}.weight"] = torch.randn(out_f, r, generator=g) * 0.1
+    save_file(w, str(tmp_path / "adapter_model.safetensors"), metadata={"format": "pt"})
+    (tmp_path / "adapter_config.json").write_text(json.dumps(
+        {"peft_type": "LORA", "r": r, "lora_alpha": alpha, "target_modules": ["q_proj", "v_proj"], "fan_in_fan_out": False}))
+    merged = m.load_merge_lora(str(tmp_path))
+    assert merged is m
+    after = m.state_dict()
+    keys = list(w)
+    for i, t in enumerate(targets):
+        A, B = w[keys[2 * i]], w[keys[2 * i + 1]]
+        np.testing.assert_allclose(after[t + ".weight"].numpy(), (before[t + ".weight"] + (B @ A) * (alpha / r)).numpy(),
+                                   rtol=1e-6, atol=1e-7)
+    touched = {t + ".weight" for t in targets}
+    for k, v in after.items():
+        if k not in touched:
+            assert torch.equal(v, before[k]), k
+
+
 def test_no_cpu_fallback():
     import midi_model as mm
     from midi_b200.lib import B200Error
