@@ -25,6 +25,7 @@ from typing import Any, Dict, Optional, Union
 import numpy as np
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 import tqdm
 from transformers import DynamicCache, LlamaConfig, LlamaModel, PretrainedConfig, PreTrainedModel
 
@@ -180,15 +181,92 @@ class _InnerFn(torch.autograd.Function):
         model = ctx.model
         rt = model._rt()
         N, L, n_ids, has_hidden = ctx.dims
-        # caller gradients arrive dense [N, L, V]; the kernels want 16-byte row pitch
-        dl = torch.zeros((N * L, rt.pitch), dtype=torch.bfloat16, device=dlogits.device)
-        dl[:, :rt.V] = dlogits.reshape(N * L, rt.V)
+        dl = _as_pitched(dlogits, N * L, rt.pitch)
+        if dl is None:
+            # caller gradients arrive dense [N, L, V]; the kernels want 16-byte row pitch
+            dl = torch.zeros((N * L, rt.pitch), dtype=torch.bfloat16, device=dlogits.device)
+            dl[:, :rt.V] = dlogits.reshape(N * L, rt.V)
         g = rt.inner.fresh_grads()
         g_head = torch.empty_like(rt.lm_head)
         dhidden, = _inner_backward(rt, model, ctx.sv, ctx.hs, dl, ctx.ids, N, L, n_ids, has_hidden, g, g_head, False)
         ctx.sv = ctx.hs = None
         lm = [g_head] if model.lm_head.weight.requires_grad else [None]
         return (None, dhidden, None, *g.named(rt.store, rt.inner.names), *lm)
+
+
+def _as_pitched(t: torch.Tensor, rows: int, pitch: int):
+    """`t` = [..., V] view (V <= pitch) of a [rows, pitch] bf16 buffer starting at its storage base -> that buffer
+    (no copy), else None.  This is how the fused cross entropy hands its in-place gradient back to _InnerFn.backward."""
+    if t.dtype != torch.bfloat16 or t.dim() < 2 or t.stride(-1) != 1 or t.stride(-2) != pitch or t.storage_offset() != 0:
+        return None
+    if t.numel() // t.shape[-1] != rows or t.untyped_storage().nbytes() < rows * pitch * 2 or t.data_ptr() % 16:
+        return None
+    want = pitch
+    for d in range(t.dim() - 2, -1, -1):                     # leading dims must be a plain row enumeration
+        if t.shape[d] != 1 and t.stride(d) != want:
+            return None
+        want *= t.shape[d]
+    return torch.as_strided(t.detach(), (rows, pitch), (pitch, 1))
+
+
+LAZY_CE = os.environ.get("B200_LAZY_CE", "1") != "0"
+LAZY_CE_HITS = 0          # how many F.cross_entropy calls were served by the fused kernels (tests read this)
+
+
+class _LazyCEFn(torch.autograd.Function):
+    """F.cross_entropy(logits.view(-1, V), y, reduction="mean", ignore_index=pad) (train.py:180-185) on the pitched logits
+    buffer forward_token produced: one read for the loss; the backward overwrites the logits with dlogits in place and
+    returns a view of that same buffer, which _InnerFn.backward recognises (no dense [N*L, V] copies in either direction)."""
+
+    @staticmethod
+    def forward(ctx, logits2d, buf, targets, V, ignore_index):
+        lac, lse = _ops.ce_fwd(buf, targets, V, ignore_index)
+        ctx.save_for_backward(buf, targets, lse, lac)
+        ctx.V, ctx.ignore = V, ignore_index
+        return lac[0].to(logits2d.dtype)
+
+    @staticmethod
+    def backward(ctx, dloss):
+        buf, targets, lse, lac = ctx.saved_tensors
+        _ops.ce_bwd_(buf, targets, lse, lac, ctx.V, ctx.ignore, grad_scale=float(dloss))
+        return buf[:, :ctx.V], None, None, None, None
+
+
+class LazyLogits(torch.Tensor):
+    """What forward_token returns in training: an ordinary dense [N, L, V] logits tensor (every op works on it as before)
+    that remembers the pitched buffer behind it, so that the reference's loss expression is served by the fused
+    cross-entropy kernels instead of materialising log-softmax and dlogits copies of the 0.9 GB logits."""
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        if func is F.cross_entropy and LAZY_CE:
+            out = cls._fused_ce(*args, **kwargs)
+            if out is not None:
+                return out
+        ret = super().__torch_function__(func, types, args, kwargs)
+        if func in (torch.Tensor.view, torch.Tensor.reshape, torch.reshape) and isinstance(ret, LazyLogits):
+            src = args[0]
+            h = getattr(src, "_b200_lazy", None)
+            if h is not None and ret.dim() >= 1 and ret.shape[-1] == h[1] and ret.numel() == src.numel():
+                ret._b200_lazy = h                      # still the same rows in the same order
+        return ret
+
+    @staticmethod
+    def _fused_ce(input, target, weight=None, size_average=None, ignore_index=-100, reduce=None, reduction="mean",
+                  label_smoothing=0.0):
+        h = getattr(input, "_b200_lazy", None)
+        if (h is None or weight is not None or reduction != "mean" or label_smoothing != 0.0 or size_average is not None
+                or reduce is not None or input.dim() != 2 or not isinstance(target, torch.Tensor) or target.dim() != 1
+                or target.dtype != torch.long or target.shape[0] != input.shape[0] or not input.requires_grad):
+            return None
+        buf, V = h
+        if input.shape != (buf.shape[0], V) or _as_pitched(input, buf.shape[0], buf.shape[1]) is None:
+            return None
+        global LAZY_CE_HITS
+        LAZY_CE_HITS += 1
+        with torch._C.DisableTorchFunctionSubclass():
+            return _LazyCEFn.apply(input, buf, target.contiguous(), V, int(ignore_index))
 
 
 def _inner_backward(rt, model, sv, hs, dlogits, ids, N, L, n_ids, has_hidden, g, g_head, accumulate):
@@ -358,7 +436,13 @@ class MIDIModel(PreTrainedModel):
         rt = self._rt()
         if cache is None:
             params = [self._b200_param(n) for n in rt.inner.names] + [self.lm_head.weight]
-            return _InnerFn.apply(self, hidden_state, x, *params)
+            out = _InnerFn.apply(self, hidden_state, x, *params)
+            if LAZY_CE and out.requires_grad:
+                buf = _as_pitched(out, out.shape[0] * out.shape[1], rt.pitch)
+                if buf is not None:
+                    out = out.as_subclass(LazyLogits)
+                    out._b200_lazy = (buf, rt.V)
+            return out
         # cached (inference) path: midi_model.py:216-221 call modes
         N = hidden_state.shape[0] if hidden_state is not None else x.shape[0]
         kv = self._kv_for(cache, "inner", N)

@@ -614,6 +614,7 @@ def check_model_train():
     for p in model.parameters():
         p.grad = None
     x, y = batch[:, :-1].contiguous(), batch[:, 1:].contiguous()
+    hits0 = mm.LAZY_CE_HITS
     hidden = model.forward(x)
     hidden = hidden.reshape(-1, hidden.shape[-1])
     yy = y.reshape(-1, y.shape[-1])
@@ -621,6 +622,7 @@ def check_model_train():
     l2 = F.cross_entropy(logits.view(-1, model.tokenizer.vocab_size), yy.view(-1), reduction="mean",
                          ignore_index=model.tokenizer.pad_id)
     l2.backward()
+    out["lazy_ce_hits"] = float(mm.LAZY_CE_HITS - hits0)          # the reference's loss expression hit the fused CE (8 f2)
     out["autograd_loss_abs"] = float((l2.float() - ref.detach()).abs())
     tot_n = tot_d = 0.0
     for n, p in model.named_parameters():
@@ -891,7 +893,7 @@ THRESH = [
     ("loss_abs", 3e-2), ("grad_global_rel", 6e-2), ("grad_pad_row", 0.0), ("autograd_loss_abs", 5e-2),
     ("autograd_grad_global_rel", 6e-2),
     ("cached_vs_full_hidden", 3e-2), ("inner_cached_vs_full_logits", 3e-2), ("min:greedy_token_agree", 0.6),
-    ("xy_split_mismatch", 0.0), ("prefetch_mismatch", 0.0), ("int16_path_loss_mismatch", 0.0), ("int16_path_grad_rel", 1e-3), ("stream_vs_generate_mismatch", 0.0), ("stream_masked_mismatch", 0.0), ("stream_denied_ids_emitted", 0.0),
+    ("min:lazy_ce_hits", 1.0), ("xy_split_mismatch", 0.0), ("prefetch_mismatch", 0.0), ("int16_path_loss_mismatch", 0.0), ("int16_path_grad_rel", 1e-3), ("stream_vs_generate_mismatch", 0.0), ("stream_masked_mismatch", 0.0), ("stream_denied_ids_emitted", 0.0),
     ("stream_mask_leak_mismatch", 0.0), ("peaked_greedy_mismatch", 0.0), ("peaked_eager_vs_graph_mismatch", 0.0), ("peaked_invalid_events", 0.0), ("peaked_loss_last", 1.5),
     ("peaked_argmax_mismatch_vs_fp32", 0.0), ("peaked_logits_vs_fp32", 3e-2),
     ("sampled_invalid_events", 0.0), ("greedy_graph_vs_nograph_mismatch", 0.0), ("fused_decode_mismatch", 0.0), ("fused_lm_head_mismatch", 0.0),

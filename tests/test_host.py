@@ -167,6 +167,69 @@ def test_native_lora_merge(tmp_path):
             assert torch.equal(v, before[k]), k
 
 
+def test_lazy_logits_routes_cross_entropy(monkeypatch):
+    """SURVEY.md 8 f2 plumbing on CPU: the tensor forward_token returns in training is a dense logits tensor whose
+    `F.cross_entropy(logits.view(-1, V), y, reduction="mean", ignore_index=pad)` (train.py:180-185) is served by the
+    fused CE entry points on the pitched buffer, the gradient comes back as a view of that buffer, and every other use
+    falls through to the ordinary dense path.  (The CE kernels themselves are replaced by torch stand-ins here; the GPU
+    suite checks the real ones against the oracle through the same route.)"""
+    import midi_model as mm
+    import torch.nn.functional as F
+    N, L, V, pitch = 3, 4, 10, 16
+    calls = []
+
+    def ce_fwd(buf, targets, V_, ignore):
+        lg = buf[:, :V_].float()
+        lse = torch.logsumexp(lg, -1)
+        valid = targets != ignore
+        nll = lse - lg.gather(1, targets.clamp_min(0)[:, None])[:, 0]
+        cnt = valid.sum().float()
+        calls.append("fwd")
+        return torch.stack([(nll * valid).sum() / cnt, cnt]), lse
+
+    def ce_bwd_(buf, targets, lse, lac, V_, ignore, grad_scale=1.0):
+        p = torch.exp(buf[:, :V_].float() - lse[:, None])
+        p[torch.arange(p.shape[0]), targets] -= 1.0
+        p[targets == ignore] = 0.0
+        buf[:, :V_] = (p * (grad_scale / lac[1])).to(buf.dtype)
+        calls.append("bwd")
+
+    monkeypatch.setattr(mm._ops, "ce_fwd", ce_fwd)
+    monkeypatch.setattr(mm._ops, "ce_bwd_", ce_bwd_)
+    torch.manual_seed(0)
+    w = torch.randn(N * L, pitch).to(torch.bfloat16).requires_grad_(True)
+    y = torch.randint(0, V, (N * L,))
+    y[::5] = 0
+
+    def make():
+        buf = w * 1.0                                   # stands in for the lm_head GEMM output [N*L, pitch]
+        return buf.view(N, L, pitch)[:, :, :V]
+
+    ref = F.cross_entropy(make().reshape(-1, V).float(), y, reduction="mean", ignore_index=0)
+    ref.backward()
+    g_ref, w.grad = w.grad.clone(), None
+    out = make()
+    lz = out.as_subclass(mm.LazyLogits)
+    lz._b200_lazy = (mm._as_pitched(out, N * L, pitch), V)
+    hits = mm.LAZY_CE_HITS
+    loss = F.cross_entropy(lz.view(-1, V), y.view(-1), reduction="mean", ignore_index=0)
+    assert mm.LAZY_CE_HITS == hits + 1 and calls == ["fwd"]
+    assert abs(float(loss) - float(ref)) < 2e-2
+    loss.backward()
+    assert calls == ["fwd", "bwd"]
+    assert float((w.grad[:, :V].float() - g_ref[:, :V].float()).abs().max()) < 2e-3
+    assert float(w.grad[:, V:].float().abs().max()) == 0.0
+    # anything else is the ordinary dense tensor: slicing, argmax, a differently-configured loss
+    w.grad = None
+    lz2 = make().as_subclass(mm.LazyLogits)
+    lz2._b200_lazy = (mm._as_pitched(lz2, N * L, pitch), V)
+    assert torch.equal(torch.argmax(lz2, -1), torch.argmax(make(), -1))
+    l_sum = F.cross_entropy(lz2.view(-1, V).float(), y, reduction="sum", ignore_index=0)
+    assert mm.LAZY_CE_HITS == hits + 1                   # not intercepted
+    l_sum.backward()
+    assert w.grad is not None
+
+
 def test_no_cpu_fallback():
     import midi_model as mm
     from midi_b200.lib import B200Error
