@@ -48,17 +48,23 @@ def _side_stream(device) -> torch.cuda.Stream:
     return s
 
 
-def _wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, accumulate: bool, side) -> None:
+def _wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, accumulate: bool, side, hold=None) -> None:
     """dW (+)= dY^T X, on `side` when given: ordered after everything queued so far on the current stream; the caller
-    joins `side` back before the gradients are consumed."""
+    joins `side` back before the gradients are consumed.  The operands must outlive the side GEMM: `hold` (a list) takes a
+    reference the caller drops only after an event recorded on `side` has been waited for; with hold=None the caller
+    guarantees the lifetime itself.  (Tensor.record_stream would also do, but it makes the caching allocator unable to
+    reuse those blocks while the host runs ahead of the device: the 0.9 GB logits / dlogits block of every step then
+    triggers fresh cudaMallocs -- measured +5 ms per step.)"""
     if side is None:
         ops.linear_wgrad(dy, x, dw, accumulate)
         return
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
         ops.linear_wgrad(dy, x, dw, accumulate)
-    dy.record_stream(side)           # the caching allocator must not hand these blocks out before the side GEMM ran
-    x.record_stream(side)
+    if hold is not None:
+        hold.append((dy, x))
+
+
 ALIGN = 256   # elements; AdamW's no-decay flags are per 256-element block
 
 
@@ -300,26 +306,28 @@ class StackEngine:
             raise lib.B200Error("backward called without a saved forward")
         n_seq, S, cos, sin = sv["n_seq"], sv["S"], sv["cos"], sv["sin"]
         side = _side_stream(dy.device) if WGRAD_STREAM else None
+        pending = []          # (event on the side stream, operands of the wgrads issued before it), released one layer late
         dx = ops.rmsnorm_bwd(dy, sv["x_last"], self.norm, sv["rstd_f"], None, grads.norm, accumulate)
         for li in range(len(self.layers) - 1, -1, -1):
             w = self.layers[li]
             g = grads.layers[li]
+            hold = []
             x, n1, rstd1, qkv, attn, lse, h, n2, rstd2, gu, act = sv["layers"][li]
             sv["layers"][li] = None   # free as we go
             # ---- MLP block: x_out = h + down(act)
             dact = ops.linear_dgrad(dx, w.down)
-            _wgrad(dx, act, g.down, accumulate, side)
+            _wgrad(dx, act, g.down, accumulate, side, hold)
             del act
             dgu = ops.swiglu_bwd(gu, dact)
             del dact, gu
             dn2 = ops.linear_dgrad(dgu, w.gu)
-            _wgrad(dgu, n2, g.gu, accumulate, side)
+            _wgrad(dgu, n2, g.gu, accumulate, side, hold)
             del dgu, n2
             dh = ops.rmsnorm_bwd(dn2, h, w.ln2, rstd2, dx, g.ln2, accumulate)
             del dn2, h, dx
             # ---- attention block: h = x + o(attn)
             dattn = ops.linear_dgrad(dh, w.o)
-            _wgrad(dh, attn, g.o, accumulate, side)
+            _wgrad(dh, attn, g.o, accumulate, side, hold)
             rope = (cos, sin) if FUSE_ROPE else None
             if self.tiny:
                 dqkv = ops.attn_tiny_bwd(qkv, dattn, n_seq, S, nh, D, rope=rope)
@@ -329,15 +337,24 @@ class StackEngine:
             if not FUSE_ROPE:
                 ops.rope_qk_(dqkv, cos, sin, S, H, D, backward=True)
             dn1 = ops.linear_dgrad(dqkv, w.qkv)
-            _wgrad(dqkv, n1, g.qkv, accumulate, side)
+            _wgrad(dqkv, n1, g.qkv, accumulate, side, hold)
             del dqkv, n1
             dx = ops.rmsnorm_bwd(dn1, x, w.ln1, rstd1, dh, g.ln1, accumulate)
             del dn1, dh, x
+            if side is not None:
+                ev = torch.cuda.Event()
+                ev.record(side)
+                pending.append((ev, hold))
+                if len(pending) > 1:          # the previous layer's wgrads have long finished: no stall, memory bounded
+                    old_ev, old_hold = pending.pop(0)
+                    torch.cuda.current_stream().wait_event(old_ev)
+                    old_hold.clear()
             if layer_done is not None:
                 if side is not None:
                     torch.cuda.current_stream().wait_stream(side)     # this layer's weight gradients are complete
                 layer_done(li)
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
+            pending.clear()
         sv["layers"] = None
         return dx
