@@ -1,11 +1,13 @@
-// Causal attention forward for the event-level stack on the 5th-gen tensor cores (head_dim 64):
-// S = Q.K^T and O += P.V are tcgen05.mma with accumulators in TMEM, Q / K / V tiles are staged by TMA
-// (cp.async.bulk.tensor.3d, 128B swizzle, zero fill outside the sequence) straight from the packed
-// [rows, 3*hidden] QKV activation, softmax runs in fp32 with one thread per query row (no shuffles):
-//   warp 0     : TMA producer         warp 1 : TMEM allocator + MMA issuer
-//   warps 2..5 : softmax / correction / epilogue (thread <-> TMEM lane <-> query row)
-// One CTA owns 128 query rows of one (batch, head); K/V tiles of 128 keys are double-buffered.  Two CTAs share
-// an SM (113 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
+// Causal attention for the event-level stack on the 5th-gen tensor cores (head_dim 64), forward and backward:
+// every matmul is tcgen05.mma with accumulators in TMEM, Q / K / V / dO tiles are staged by TMA (cp.async.bulk.tensor.3d,
+// 128B swizzle, zero fill outside the sequence) straight from the packed [rows, 3*hidden] QKV activation, and the
+// fp32 softmax math runs on 16 warps that exchange tiles with the single MMA-issuing thread through mbarriers.
+//   warp 0 : TMA producer      warp 1 : TMEM allocator + MMA issuer      warps 2..17 : math / epilogue
+// Kernels, in file order:
+//   attn_fwd_tc05_kernel      first-generation forward (4 softmax warps, thread = query row, 2 CTAs/SM); B200_ATTN_FWD_TC=v1
+//   attn_fwd_tc05_v2_kernel   default forward: 1 CTA/SM, thread = row x 32 keys, S / P / PV double-buffered
+//   attn_bwd_tc05_kernel<M>   default backward (dK, dV and -- M = 2 -- dQ through a TMA reduce-add), half-tile pipeline
+//   attn_bwd_dq_tc05_kernel   atomic-free dQ for the `split` variant;  attn_bwd_dq_finalize_kernel: fp32 dQ -> bf16
 // Semantics = hf sdpa_attention.py:92-101 (causal, scale d^-1/2): online softmax in fp32, P rounded to bf16
 // before P.V, output rounded to bf16, LSE saved for the backward pass.
 #include <cstring>
@@ -505,17 +507,19 @@ extern "C" int b200_attn_causal_fwd_tc(const void* q, const void* k, const void*
 
 // =============================================================================================
 // backward on tcgen05: one CTA = one tile of 128 keys of one (batch, head), looping over the query tiles at or
-// after the diagonal.  Five UMMA groups per iteration, all accumulators in TMEM (448 of 512 columns):
-//   S^T  = K . Q_i^T        dP^T = V . dO_i^T                      (128 x 128 each)
-//   dV  += P^T . dO_i       dK  += dS^T . Q_i                      (128 x 64, accumulated over the whole loop)
-//   dQ_i = dS . K           (128 x 64; added to an fp32 global accumulator with red.global, like FlashAttention-2)
-// P^T and dS^T are produced by 8 compute warps (thread = key row x half of the query columns), rounded to bf16 and
-// written to 128B-swizzled shared memory where the UMMAs read them: K-major for dV / dK, and the same dS^T tile
-// viewed MN-major as the A operand of dQ -- so no transposes and no recomputation (5 matmuls, not 7).
+// after the diagonal.  Five UMMA groups per query tile, all accumulators in TMEM (448 of 512 columns):
+//   S^T  = K . Q_i^T        dP^T = V . dO_i^T       (two half tiles of 128 x 64, each in its own TMEM buffer, issued
+//                                                    two pipeline units ahead of the math)
+//   dV  += P^T . dO_i       dK  += dS^T . Q_i       (128 x 64, accumulated over the whole loop)
+//   dQ_i = dS . K                                   (128 x 64 per tile; TMEM -> swizzled fp32 staging -> TMA reduce-add)
+// P^T and dS^T are produced by two ping-pong groups of 8 math warps (group g = half g of every tile; thread = key row x
+// 32 query columns), rounded to bf16 and written to 128B-swizzled shared memory where the UMMAs read them: K-major for
+// dV / dK, and the same dS^T tile viewed MN-major as the A operand of dQ -- no transposes, no recomputation
+// (5 matmuls, not 7).  DESIGN.md 3.1b has the measured history (1.01 ms mma.sync -> 0.41 ms).
 // =============================================================================================
 namespace {
 
-constexpr int BWD_CWARPS = 16;                   // compute warps: thread = (key row, 32 of the 128 query columns)
+constexpr int BWD_CWARPS = 16;                   // math warps: two groups of 8, thread = (key row, 32 of a half tile's 64 query columns)
 constexpr int BWD_THREADS = 64 + 32 * BWD_CWARPS; // warp 0 TMA, warp 1 MMA, warps 2..17 compute
 constexpr int SB_K = 0, SB_V = 16384;
 constexpr int QS = 3;                            // (Q, dO) stages (4 measured no faster than 3; the 4th stage's 32 KB now stages dQ)

@@ -23,17 +23,18 @@ import os
 
 BF16 = torch.bfloat16
 # RoPE backward is fused into the attention backward kernels (B200_FUSE_ROPE=0 -> stand-alone kernel).
-# The forward fusion into the QKV GEMM epilogue exists (ops.linear_rope, bit-identical) but is OFF by default:
-# measured on B200 (profiles/r1_*) the per-row cos/sin gathers make the epilogue longer than the K=1024 main loop
-# (QKV GEMM 1213 -> 843 TFLOP/s), a net loss of 0.8 ms/step against the HBM-roofline stand-alone kernel.
+# The forward fusion into the QKV GEMM epilogue exists (ops.linear_rope, bit-identical, per-thread or TMA-staged stores)
+# but is OFF by default: four epilogue warps doing the rotation outlast the K=1024 main loop.  Measured A/B on one box
+# with the staged epilogue: +0.2 ms/step against the HBM-roofline stand-alone kernel (QKV GEMM 1213 -> 843 TFLOP/s with
+# the earlier per-thread stores).
 FUSE_ROPE = os.environ.get("B200_FUSE_ROPE", "1") != "0"
 FUSE_ROPE_FWD = os.environ.get("B200_FUSE_ROPE_FWD", "0") != "0"
 # SwiGLU formed in the epilogue of the gate|up GEMM (ops.linear_swiglu, bit-identical to GEMM + stand-alone kernel) exists
-# but is OFF by default: measured on B200 the heavier epilogue (2 MUFU ops + 3 stores per element pair on 4 epilogue
-# warps) outlasts the K=1024 main loop (gate|up GEMM 1122 -> 686 TFLOP/s), a net loss of 1.3 ms/step; 8 epilogue warps
-# did not help (plain GEMMs got 6 % slower).  B200_FUSE_SWIGLU=1 enables it.
+# but is OFF by default: the heavier epilogue (2 MUFU ops per element, three output boxes per 64 features, on 4 epilogue
+# warps) outlasts the K=1024 main loop.  Measured A/B on one box with the TMA-staged epilogue: +1.5 ms/step; 8 epilogue
+# warps did not help (plain GEMMs got 6 % slower).  B200_FUSE_SWIGLU=1 enables it.
 FUSE_SWIGLU = os.environ.get("B200_FUSE_SWIGLU", "0") != "0"
-# Weight-gradient GEMMs on a second (lower-priority) stream: dW = dY^T X is off the backward's critical path, so it can run
+# Weight-gradient GEMMs on a second stream: dW = dY^T X is off the backward's critical path, so it can run
 # under the HBM-bound kernels that follow on the main stream (SwiGLU / RMSNorm backward leave the tensor pipe idle, and an
 # elementwise CTA fits next to a GEMM CTA on an SM).  B200_WGRAD_STREAM=0 keeps everything on one stream.
 WGRAD_STREAM = os.environ.get("B200_WGRAD_STREAM", "1") != "0"
