@@ -230,6 +230,39 @@ def test_lazy_logits_routes_cross_entropy(monkeypatch):
     assert w.grad is not None
 
 
+def test_pitched_view_detection():
+    """_as_pitched only accepts a [..., V] view that enumerates the rows of a [rows, pitch] bf16 buffer from its base."""
+    import midi_model as mm
+    buf = torch.zeros(12, 16, dtype=torch.bfloat16)
+    v3 = buf.view(3, 4, 16)[:, :, :10]
+    got = mm._as_pitched(v3, 12, 16)
+    assert got is not None and got.shape == (12, 16) and got.data_ptr() == buf.data_ptr()
+    assert mm._as_pitched(v3.reshape(-1, 10), 12, 16) is not None              # [12, 10] with row stride 16: still a view
+    assert mm._as_pitched(buf[:, :10], 12, 16) is not None
+    assert mm._as_pitched(buf[1:, :10], 11, 16) is None                        # not at the storage base
+    assert mm._as_pitched(buf[:, :10].contiguous(), 12, 16) is None            # dense copy: pitch is V, not 16
+    assert mm._as_pitched(buf.float()[:, :10], 12, 16) is None                 # wrong dtype
+    assert mm._as_pitched(buf.view(3, 4, 16)[:, :2, :10], 6, 16) is None       # rows are not a plain enumeration
+
+
+def test_grammar_lut_matches_tokenizer_tables():
+    """decode.GrammarLUT (id ranges consumed by the fused sampler) == midi_tokenizer.py:517-535 as restated in
+    tokenizer_tables: step 0 = eos + event ids, step i = the i-th parameter's contiguous id range."""
+    from midi_b200.decode import GrammarLUT
+    from midi_b200.tokenizer_tables import TokenizerTables
+    tok = TokenizerTables("v2")
+    g = GrammarLUT(tok, "cpu")
+    assert (g.eos, g.pad, g.n_event_types) == (tok.eos_id, tok.pad_id, len(tok.event_ids))
+    lut = g.lut.numpy()
+    for name, params in tok.events.items():
+        e = tok.event_ids[name] - (tok.eos_id + 1)
+        for i, pn in enumerate(params):
+            ids = tok.parameter_ids[pn]
+            assert tuple(lut[e, i]) == (ids[0], ids[-1] + 1), (name, pn)
+        assert (lut[e, len(params):] == 0).all()
+        assert g.n_params[tok.event_ids[name]] == len(params)
+
+
 def test_no_cpu_fallback():
     import midi_model as mm
     from midi_b200.lib import B200Error
