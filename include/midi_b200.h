@@ -137,7 +137,9 @@ int b200_ce_fwd(const void* logits, const long long* targets, float* lse, float*
                 float* loss_and_count /*float[2]: mean loss, #targets*/, long long rows, int V, int ld,
                 long long ignore_index, cudaStream_t s);
 int b200_ce_bwd(void* logits_inout, const long long* targets, const float* lse, const float* loss_and_count,
-                long long rows, int V, int ld, long long ignore_index, float grad_scale, cudaStream_t s);
+                long long rows, int V, int ld, long long ignore_index, float grad_scale,
+                const void* grad_scale_dev /*may be NULL: device scalar multiplied into grad_scale*/,
+                int grad_scale_is_bf16, cudaStream_t s);
 
 /* ---- optimizer (train.py:121-138 AdamW groups; :464 gradient_clip_val) ----------------------------- */
 int b200_gradnorm_parts(void);

@@ -87,7 +87,10 @@ __global__ void ce_reduce_kernel(const float* __restrict__ row_loss, const long 
 __global__ void __launch_bounds__(CE_THREADS)
 ce_bwd_kernel(bf16* __restrict__ logits, const long long* __restrict__ targets, const float* __restrict__ lse_in,
               const float* __restrict__ loss_and_count, int V, int ld, int n_cols_store, long long ignore_index,
-              float gscale) {
+              float gscale, const void* __restrict__ gscale_dev, int gscale_is_bf16) {
+    // upstream d(loss) as a device scalar (autograd hands it over as a tensor: no host sync to read it)
+    if (gscale_dev) gscale *= gscale_is_bf16 ? __bfloat162float(*reinterpret_cast<const bf16*>(gscale_dev))
+                                             : *reinterpret_cast<const float*>(gscale_dev);
     const size_t r = blockIdx.x;
     bf16* row = logits + r * ld;
     const long long t = targets[r];
@@ -189,12 +192,14 @@ extern "C" int b200_ce_fwd(const void* logits, const long long* targets, float* 
 }
 
 extern "C" int b200_ce_bwd(void* logits_inout, const long long* targets, const float* lse, const float* loss_and_count,
-                           long long rows, int V, int ld, long long ignore_index, float grad_scale, cudaStream_t stream) {
+                           long long rows, int V, int ld, long long ignore_index, float grad_scale,
+                           const void* grad_scale_dev, int grad_scale_is_bf16, cudaStream_t stream) {
     B200_CHECK_ARG(ld % 8 == 0 && ld >= V, "ce_bwd: ld must be a multiple of 8 and >= V");
     if (rows == 0) return B200_OK;
     const int n_cols_store = ((V + 7) / 8) * 8;
     ce_bwd_kernel<<<(unsigned)rows, CE_THREADS, 0, stream>>>((bf16*)logits_inout, targets, lse, loss_and_count, V, ld,
-                                                             n_cols_store, ignore_index, grad_scale);
+                                                             n_cols_store, ignore_index, grad_scale, grad_scale_dev,
+                                                             grad_scale_is_bf16);
     B200_CHECK_LAUNCH("ce_bwd");
     return B200_OK;
 }

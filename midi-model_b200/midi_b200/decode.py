@@ -40,6 +40,27 @@ class PagedKV:
     def reset(self):
         self.length = 0
 
+    def grow(self, capacity: int) -> None:
+        """Re-allocate the pools for at least `capacity` positions, keeping the cached keys / values (row b owns pages
+        [b * max_pages, (b+1) * max_pages), so the old pages are copied to the front of each row's new range).  The
+        reference's DynamicCache has no capacity (hf cache_utils.py:119-120 keeps concatenating); neither may we."""
+        if capacity <= self.capacity:
+            return
+        old_mp = self.max_pages
+        self.max_pages = (max(capacity, 2 * self.capacity) + self.page - 1) // self.page
+        self.capacity = self.max_pages * self.page
+        c = self.cfg
+        dev = self.block_table.device
+        shape = (self.batch * self.max_pages, c.n_head, self.page, c.head_dim)
+        for pools in (self.k, self.v):
+            for li in range(c.n_layer):
+                new = torch.empty(shape, dtype=BF16, device=dev)
+                new.view(self.batch, self.max_pages, c.n_head, self.page, c.head_dim)[:, :old_mp].copy_(
+                    pools[li].view(self.batch, old_mp, c.n_head, self.page, c.head_dim))
+                pools[li] = new
+        self.block_table = torch.arange(self.batch * self.max_pages, dtype=torch.int32, device=dev).view(
+            self.batch, self.max_pages).contiguous()
+
 
 def _linear(x: torch.Tensor, w: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """nn.Linear on a few rows: weight-streaming skinny GEMM for <= 16 rows, tcgen05 GEMM otherwise."""
@@ -84,8 +105,21 @@ class CachedStack:
 
     def __init__(self, eng: StackEngine, max_pos: int, inv_freq: torch.Tensor):
         self.eng = eng
+        self.inv_freq = inv_freq
         self.cos, self.sin = ops.rope_table(inv_freq, max_pos)
         self.max_pos = max_pos
+        self.version = 0            # bumped when the tables are re-created (captured graphs hold the old addresses)
+
+    def ensure_positions(self, n_pos: int) -> bool:
+        """cos/sin tables for positions 0 .. n_pos-1.  `max_position_embeddings` (4096) is only the initial size: hf computes
+        the rotation from the position ids on the fly (modeling_llama.py:124-135), so contexts longer than that are legal
+        (app.py: max_len = prompt + up to 4096 generated events).  Returns True when the tables were re-created."""
+        if n_pos <= self.max_pos:
+            return False
+        self.max_pos = max(n_pos, 2 * self.max_pos)
+        self.cos, self.sin = ops.rope_table(self.inv_freq, self.max_pos)
+        self.version += 1
+        return True
 
     def step(self, x: torch.Tensor, kv: PagedKV, s_new: int, pos_dev: Optional[torch.Tensor] = None,
              max_T: Optional[int] = None, final_norm: bool = True) -> torch.Tensor:
@@ -98,8 +132,13 @@ class CachedStack:
         dev_pos = pos_dev is not None
         past = 0 if dev_pos else kv.length
         T = max_T if dev_pos else past + s_new
-        if T > kv.capacity or T > self.max_pos:
-            raise lib.B200Error(f"KV cache overflow: {T} positions > capacity {min(kv.capacity, self.max_pos)}")
+        if dev_pos:
+            # graph replay: pools and tables were sized by the generator (addresses are baked into the graph)
+            if T > kv.capacity or T > self.max_pos:
+                raise lib.B200Error(f"KV cache overflow: {T} positions > capacity {min(kv.capacity, self.max_pos)}")
+        else:
+            self.ensure_positions(T)
+            kv.grow(T)
         scale = 1.0 / math.sqrt(D)
         n_split = max(1, min(32, (T + 255) // 256)) if D == 64 else 1
         pd = lib.ptr(pos_dev)
@@ -215,6 +254,8 @@ class GraphGenerator:
         self.outer, self.inner, self.lm_head, self.pitch, self.V = outer, inner, lm_head, pitch, V
         self.tok, self.g, self.B, self.max_len = tok, grammar, batch, max_len
         self.T = tok.max_token_seq
+        outer.ensure_positions(max_len)            # max_len may exceed max_position_embeddings (app.py: prompt + 4096 new events)
+        self.table_version = outer.version
         self.temp, self.top_p, self.top_k, self.seed = float(temp), float(top_p), int(top_k), int(seed) & ((1 << 63) - 1)
         self.kv1 = PagedKV(outer.eng.cfg, batch, max_len, 64, dev)
         self.kv2 = PagedKV(inner.eng.cfg, batch, self.T, self.T, dev)
@@ -278,6 +319,8 @@ class GraphGenerator:
     def _prepare(self, prompt: torch.Tensor, use_graph: bool) -> None:
         """Load the prompt into the device state; capture the per-event graph on first use (current stream = self.stream)."""
         self._set_state(prompt)
+        if self.table_version != self.outer.version:    # RoPE tables were re-created: the captured addresses are stale
+            self.graph, self.table_version = None, self.outer.version
         if use_graph and self.graph is None:
             self._event()                       # warm-up (allocations, function attributes) outside capture
             torch.cuda.synchronize()

@@ -109,9 +109,11 @@ class ParamStore:
         self.nodecay = flags.to(dev)
 
     def valid(self) -> bool:
-        """False once somebody re-created the parameters (.to(dtype), .cuda(), ...)."""
-        for n in (self.names[0], self.names[-1]):
-            if self._params[n].data_ptr() != self.views[n].data_ptr():
+        """False once somebody re-created or re-pointed ANY parameter (.to(dtype), .cuda(), p.data = ..., ...): the
+        engine reads the flat buffer, so a parameter living elsewhere would silently be ignored."""
+        views, params = self.views, self._params
+        for n in self.names:
+            if params[n].data_ptr() != views[n].data_ptr():
                 return False
         return True
 

@@ -53,7 +53,7 @@ SIGNATURES = {
     "b200_attn_tiny_fwd": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp]),
     "b200_attn_tiny_bwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp]),
     "b200_ce_fwd": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i64, vp]),
-    "b200_ce_bwd": (i32, [vp, vp, vp, vp, i64, i32, i32, i64, f32, vp]),
+    "b200_ce_bwd": (i32, [vp, vp, vp, vp, i64, i32, i32, i64, f32, vp, i32, vp]),
     "b200_gradnorm_parts": (i32, []),
     "b200_grad_clip_coef": (i32, [vp, i64, f32, vp, vp, sz, vp]),
     "b200_adamw_step": (i32, [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, vp, vp]),

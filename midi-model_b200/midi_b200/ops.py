@@ -359,7 +359,13 @@ def ce_fwd(logits: torch.Tensor, targets: torch.Tensor, V: int, ignore_index: in
 
 
 def ce_bwd_(logits: torch.Tensor, targets: torch.Tensor, lse: torch.Tensor, lac: torch.Tensor, V: int, ignore_index: int,
-            grad_scale: float = 1.0):
+            grad_scale: float = 1.0, grad_scale_dev: Optional[torch.Tensor] = None):
+    """In place: logits <- d(loss)/d(logits) * grad_scale [* grad_scale_dev (0-dim CUDA tensor, fp32 or bf16)]."""
     R, ld = logits.shape[0], logits.stride(0)
+    is_bf16 = 0
+    if grad_scale_dev is not None:
+        if grad_scale_dev.dtype not in (torch.float32, BF16) or not grad_scale_dev.is_cuda:
+            grad_scale_dev = grad_scale_dev.to(device=logits.device, dtype=torch.float32)
+        is_bf16 = int(grad_scale_dev.dtype == BF16)
     lib.call("b200_ce_bwd", logits.data_ptr(), targets.data_ptr(), lse.data_ptr(), lac.data_ptr(), R, V, ld, ignore_index,
-             grad_scale, lib.stream())
+             grad_scale, lib.ptr(grad_scale_dev), is_bf16, lib.stream())

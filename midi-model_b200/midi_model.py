@@ -116,12 +116,16 @@ class _Runtime:
         self.V = self.lm_head.shape[0]
         self.pitch = (self.V + 7) // 8 * 8
         self.H = nc.hidden_size
-        self.opt_state = None
         self.cached_outer = None
         self.cached_inner = None
         self.grammar = None
-        self.graph_gen = {}
-        self.gen_lock = threading.RLock()      # gradio serves generate from several threads (app.py:496)
+        # Device-resident generate loops (decode.GraphGenerator: KV pools, CUDA graph, RNG / position state, own stream).
+        # gradio serves app.generate from up to 10 worker threads sharing one model (app.py:496) and may resume a
+        # suspended generator from another thread, so no thread-owned lock is ever held across a `yield`: a generation
+        # CHECKS OUT a generator (creating one when none is idle), owns it exclusively until it finishes or is closed,
+        # then returns it.  `pool_lock` only guards the free list.
+        self.gen_pool = {}                      # key -> [idle GraphGenerator]
+        self.pool_lock = threading.Lock()
 
 
 def _flat_ids(x: torch.Tensor) -> torch.Tensor:
@@ -228,7 +232,10 @@ class _LazyCEFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dloss):
         buf, targets, lse, lac = ctx.saved_tensors
-        _ops.ce_bwd_(buf, targets, lse, lac, ctx.V, ctx.ignore, grad_scale=float(dloss))
+        # the logits buffer now holds dlogits (in place, through a raw pointer): bump its version counter so that autograd
+        # raises if anything else saved these logits for a later backward, instead of silently reading gradients
+        _ops.ce_bwd_(buf, targets, lse, lac, ctx.V, ctx.ignore, grad_scale=1.0, grad_scale_dev=dloss)
+        torch.autograd.graph.increment_version(buf)
         return buf[:, :ctx.V], None, None, None, None
 
 
@@ -513,22 +520,36 @@ class MIDIModel(PreTrainedModel):
                             constant_values=tok.pad_id)
         return torch.from_numpy(np.ascontiguousarray(prompt)).to(dtype=torch.long, device=dev)
 
-    def _graph_generator(self, batch_size, max_len, temp, top_p, top_k, generator):
-        """The (cached) device-resident generate loop for these settings, reseeded from `generator`."""
+    def _checkout_generator(self, batch_size, max_len, temp, top_p, top_k, generator):
+        """Exclusive use of a device-resident generate loop for these settings, reseeded from `generator`; hand it back
+        with _return_generator.  Idle generators are reused (graph capture and KV pools are the expensive part)."""
         rt = self._rt()
         gen_dev = generator.device if generator is not None else torch.device("cpu")
         seed = int(torch.randint(0, 2 ** 62, (1,), generator=generator, device=gen_dev).item())
         key = (batch_size, max_len, float(temp), float(top_p), int(top_k))
-        gg = rt.graph_gen.get(key)
+        with rt.pool_lock:
+            idle = rt.gen_pool.get(key)
+            gg = idle.pop() if idle else None
+            if gg is None:
+                for k in [k for k in rt.gen_pool if k != key]:      # other settings: drop their idle pools (KV is large)
+                    del rt.gen_pool[k]
+                if rt.grammar is None:
+                    rt.grammar = _dec.GrammarLUT(self.tokenizer, rt.store.device)
+                outer, inner = self._cached_stack("outer"), self._cached_stack("inner")
         if gg is None:
-            if rt.grammar is None:
-                rt.grammar = _dec.GrammarLUT(self.tokenizer, rt.store.device)
-            gg = _dec.GraphGenerator(self._cached_stack("outer"), self._cached_stack("inner"), rt.lm_head, rt.pitch,
-                                     rt.V, self.tokenizer, rt.grammar, batch_size, max_len, temp, top_p, top_k, seed)
-            rt.graph_gen.clear()               # keep one (KV pools are large)
-            rt.graph_gen[key] = gg
+            gg = _dec.GraphGenerator(outer, inner, rt.lm_head, rt.pitch, rt.V, self.tokenizer, rt.grammar, batch_size,
+                                     max_len, temp, top_p, top_k, seed)
         gg.seed = seed & ((1 << 63) - 1)
-        return gg
+        return key, gg
+
+    def _return_generator(self, key, gg) -> None:
+        rt = self.__dict__.get("_b200_rt")
+        if rt is None or gg.outer is not rt.cached_outer:         # the runtime was rebuilt meanwhile: drop it
+            return
+        with rt.pool_lock:
+            idle = rt.gen_pool.setdefault(key, [])
+            if len(idle) < 2:                                      # keep at most two idle loops per setting
+                idle.append(gg)
 
     @torch.inference_mode()
     def generate_stream(self, prompt=None, batch_size=1, max_len=512, temp=1.0, top_p=0.98, top_k=20,
@@ -552,14 +573,15 @@ class MIDIModel(PreTrainedModel):
         if inp.shape[1] >= max_len:
             return
         mode = os.environ.get("B200_GENERATE", "graph")
-        with rt.gen_lock:                      # one generation at a time per model: the loop's state lives on the device
-            gg = self._graph_generator(batch_size, max_len, temp, top_p, top_k, generator)
+        # this generation owns its loop state (no lock is held across the yields; see _Runtime.gen_pool)
+        key, gg = self._checkout_generator(batch_size, max_len, temp, top_p, top_k, generator)
+        try:
             gg.set_deny(deny)
-            try:
-                for ev in gg.events(inp, use_graph=(mode not in ("nograph", "eager"))):
-                    yield ev.numpy()
-            finally:
-                gg.set_deny(())
+            for ev in gg.events(inp, use_graph=(mode not in ("nograph", "eager"))):
+                yield ev.numpy()
+        finally:
+            gg.set_deny(())
+            self._return_generator(key, gg)
 
     def generate(self, prompt=None, batch_size=1, max_len=512, temp=1.0, top_p=0.98, top_k=20, generator=None):
         """midi_model.py:167-250 with the per-token work on the device (see midi_b200/decode.py)."""
@@ -576,12 +598,14 @@ class MIDIModel(PreTrainedModel):
         mode = os.environ.get("B200_GENERATE", "graph")
         if mode != "eager" and max_len - cur_len >= 4:
             # device-resident loop: one CUDA graph replay per event (midi_b200/decode.py::GraphGenerator)
-            with rt.gen_lock:
-                gg = self._graph_generator(batch_size, max_len, temp, top_p, top_k, generator)
+            key, gg = self._checkout_generator(batch_size, max_len, temp, top_p, top_k, generator)
+            try:
                 gg.set_deny(())
                 bar = tqdm.tqdm(desc="generating", total=max_len - cur_len)
                 with bar:
                     out = gg.run(inp, use_graph=(mode != "nograph"), progress=bar.update)
+            finally:
+                self._return_generator(key, gg)
             return out.cpu().numpy()
         seq = torch.full((batch_size, max_len, T), tok.pad_id, dtype=torch.long, device=dev)
         seq[:, :cur_len] = inp
@@ -690,18 +714,33 @@ class MIDIModel(PreTrainedModel):
             rt.store.publish_grads()
         return loss
 
+    def _opt_state(self, rt):
+        """AdamW moments over the flat parameter buffer (fp32).  They live on the MODEL, not on the runtime, so they
+        survive a runtime rebuild (the flat layout is a function of named_parameters() only); a model whose parameter
+        list changed gets fresh moments and says so."""
+        st = self.__dict__.get("_b200_opt")
+        n, dev = rt.store.numel, rt.store.device
+        if st is not None and (st["m"].numel() != n or st["m"].device != dev):
+            if st["m"].numel() != n:
+                import warnings
+                warnings.warn("fused AdamW: the parameter list changed; optimizer moments restart from zero")
+                st = None
+            else:
+                st = {k: v.to(dev) for k, v in st.items()}
+                self.__dict__["_b200_opt"] = st
+        if st is None:
+            st = dict(m=torch.zeros(n, dtype=torch.float32, device=dev), v=torch.zeros(n, dtype=torch.float32, device=dev),
+                      nc=torch.zeros(2, dtype=torch.float32, device=dev), step=torch.zeros(1, dtype=torch.int64))
+            self.__dict__["_b200_opt"] = st
+        return st
+
     def fused_optimizer_step(self, lr: float, step: int, weight_decay: float = 0.01, betas=(0.9, 0.99), eps: float = 1e-8,
                              max_grad_norm: float = 1.0):
         """Global-norm clip (train.py:464) + AdamW with the no-decay split (train.py:121-138) over the flat
         parameter / gradient buffers: two small reductions and one update launch."""
         rt = self._rt()
-        st = rt.opt_state
+        st = self._opt_state(rt)
         n = rt.store.numel
-        if st is None:
-            st = dict(m=torch.zeros(n, dtype=torch.float32, device=rt.store.device),
-                      v=torch.zeros(n, dtype=torch.float32, device=rt.store.device),
-                      nc=torch.zeros(2, dtype=torch.float32, device=rt.store.device))
-            rt.opt_state = st
         parts = _lib.query("b200_gradnorm_parts")
         ws = _ops._ws("gradnorm", parts * 4, rt.store.device)
         _lib.call("b200_grad_clip_coef", rt.store.gflat.data_ptr(), n, float(max_grad_norm), st["nc"].data_ptr(),
@@ -709,4 +748,36 @@ class MIDIModel(PreTrainedModel):
         _lib.call("b200_adamw_step", rt.store.flat.data_ptr(), rt.store.gflat.data_ptr(), st["m"].data_ptr(),
                   st["v"].data_ptr(), rt.store.nodecay.data_ptr(), n, float(lr), float(betas[0]), float(betas[1]),
                   float(eps), float(weight_decay), int(step), st["nc"].data_ptr(), _lib.stream())
+        st["step"][0] = int(step)
         return st["nc"]
+
+    def optimizer_state_dict(self) -> Dict[str, Any]:
+        """Checkpointable state of the fused AdamW, in torch.optim's vocabulary: {"step": int, "state": {parameter name:
+        {"exp_avg", "exp_avg_sq"}}} (fp32 CPU tensors shaped like the parameter).  Empty before the first step."""
+        st = self.__dict__.get("_b200_opt")
+        if st is None:
+            return {"step": 0, "state": {}}
+        rt = self._rt()
+        out = {}
+        for name in rt.store.names:
+            o, v = rt.store.offsets[name], rt.store.views[name]
+            out[name] = {"exp_avg": st["m"][o:o + v.numel()].view(v.shape).cpu().clone(),
+                         "exp_avg_sq": st["v"][o:o + v.numel()].view(v.shape).cpu().clone()}
+        return {"step": int(st["step"][0]), "state": out}
+
+    def load_optimizer_state_dict(self, sd: Dict[str, Any]) -> int:
+        """Inverse of optimizer_state_dict(); returns the step to resume from (pass step + 1 to fused_optimizer_step)."""
+        rt = self._rt()
+        st = self._opt_state(rt)
+        st["m"].zero_()
+        st["v"].zero_()
+        for name, ent in sd.get("state", {}).items():
+            if name not in rt.store.offsets:
+                raise KeyError(f"load_optimizer_state_dict: unknown parameter {name}")
+            o, v = rt.store.offsets[name], rt.store.views[name]
+            if tuple(ent["exp_avg"].shape) != tuple(v.shape):
+                raise ValueError(f"load_optimizer_state_dict: {name}: shape {tuple(ent['exp_avg'].shape)} vs {tuple(v.shape)}")
+            st["m"][o:o + v.numel()].view(v.shape).copy_(ent["exp_avg"])
+            st["v"][o:o + v.numel()].view(v.shape).copy_(ent["exp_avg_sq"])
+        st["step"][0] = int(sd.get("step", 0))
+        return int(sd.get("step", 0))

@@ -187,11 +187,13 @@ def test_lazy_logits_routes_cross_entropy(monkeypatch):
         calls.append("fwd")
         return torch.stack([(nll * valid).sum() / cnt, cnt]), lse
 
-    def ce_bwd_(buf, targets, lse, lac, V_, ignore, grad_scale=1.0):
+    def ce_bwd_(buf, targets, lse, lac, V_, ignore, grad_scale=1.0, grad_scale_dev=None):
+        if grad_scale_dev is not None:
+            grad_scale = grad_scale * float(grad_scale_dev)
         p = torch.exp(buf[:, :V_].float() - lse[:, None])
         p[torch.arange(p.shape[0]), targets] -= 1.0
         p[targets == ignore] = 0.0
-        buf[:, :V_] = (p * (grad_scale / lac[1])).to(buf.dtype)
+        buf.data[:, :V_] = (p * (grad_scale / lac[1])).to(buf.dtype)     # raw write, like the kernel (no version bump)
         calls.append("bwd")
 
     monkeypatch.setattr(mm._ops, "ce_fwd", ce_fwd)
