@@ -352,9 +352,13 @@ class GraphGenerator:
         cur.wait_stream(self.stream)
 
     def run(self, prompt: torch.Tensor, use_graph: bool = True, check_every: int = 32, progress=None,
-            stop_on_eos: bool = True) -> torch.Tensor:
+            stop_on_eos: bool = True, max_new: Optional[int] = None) -> torch.Tensor:
+        """`max_new` stops after that many generated events although the pools (and the split-T attention) are sized for
+        max_len: a serving process keeps ONE loop with full-context pools and cuts individual requests short."""
         P = prompt.shape[1]
         n_new = self.max_len - P
+        if max_new is not None:
+            n_new = min(n_new, int(max_new))
         if n_new <= 0:
             return prompt
         cur = torch.cuda.current_stream()
