@@ -641,24 +641,29 @@ def generate_leg(model, dev, world, rank, peak_gbs, cpu=False):
                                 dec.GrammarLUT(tok, dev), B, n_new + 1, 1.0, 0.98, 20, 1234 + rank)
         prompt = torch.full((B, 1, tok.max_token_seq), tok.pad_id, dtype=torch.long, device=dev)
         prompt[:, 0, 0] = tok.bos_id
-        gg.run(prompt, check_every=1 << 30, stop_on_eos=False)      # captures the graph + warm-up
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        out = gg.run(prompt, check_every=1 << 30, stop_on_eos=False)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        assert out.shape[1] == n_new + 1
+        def timed_run(mode):
+            gg.run(prompt, use_graph=mode, check_every=1 << 30, stop_on_eos=False)      # warm-up (+ graph capture)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            out = gg.run(prompt, use_graph=mode, check_every=64, stop_on_eos=False)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            assert out.shape[1] == n_new + 1
+            return dt
+        dt_graph = timed_run(True)                 # one CUDA-graph replay (~210 kernel nodes) per event
+        dt = timed_run("persist")                  # default: persistent cooperative kernel, 64 events per launch
         kv_bytes = oc.n_layer * B * (n_new / 2) * 2 * oc.hidden * 2            # K and V of the mean context, every layer
         step_bytes = w_outer + w_inner + kv_bytes
         ms = 1e3 * dt / n_new
         res[f"batch{B}"] = {"events_per_s": world * B * n_new / dt, "ms_per_event_step": ms, "rows": world * B,
-                            "new_events_per_row": n_new,
+                            "new_events_per_row": n_new, "loop": "persistent kernel (csrc/decode_persist.cu), 64 events per launch",
+                            "graph_loop_events_per_s": world * B * n_new / dt_graph,
                             "roofline": {"bound": "hbm", "bytes_per_event_step": int(step_bytes),
                                          "achieved": step_bytes / (ms * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
                                          "frac": step_bytes / (ms * 1e-3) / 1e9 / peak_gbs,

@@ -185,6 +185,41 @@ int b200_add_int(int* p, int v, cudaStream_t s);
 int b200_event_commit(const long long* ev_t, long long* seq, long long* ev_next, int* pos_dev, int B, int T, int max_len,
                       cudaStream_t s);
 
+
+/* ---- persistent generate kernel (midi_model.py:192-248: one generated event = event-level decode step + up to 8
+ *      token-level decode steps with grammar-masked sampling + commit) -------------------------------------------
+ *      ONE cooperative launch runs `n_events` whole events on one CTA per SM with grid-wide barriers between the
+ *      dependent phases (csrc/decode_persist.cu).  All pointers are device pointers; the descriptor itself is host
+ *      memory.  State (`pos`, `ev_in`, `seq`, `rng_state`) is the same device-resident state the launch-per-phase loop
+ *      (b200_gemv_fused / b200_attn_decode_fused / b200_sample_from_logits / b200_event_commit) works on, so the two
+ *      loops are interchangeable event by event. */
+typedef struct b200_decode_desc {
+    const long long* outer_w;   /* device table [n_outer][6] of device addresses: qkv [3H,H], o [H,H], gate|up [2I,H],
+                                   down [H,I], input_layernorm [H], post_attention_layernorm [H]  (hf :303-332) */
+    const long long* inner_w;   /* same for the token-level stack, [n_inner][6] */
+    int n_outer, n_inner;
+    const void *outer_norm, *inner_norm, *lm_head /*[V,H]*/, *emb_outer /*[V,H]*/, *emb_inner /*[V,H]*/;
+    int H, I_outer, I_inner, nh_outer, nh_inner, V, pitch /* logits row pitch >= V */;
+    float eps;
+    const long long* kv_outer;  /* device table [n_outer][2]: k pool, v pool ([pages][heads][page][64], b200_kv_append layout) */
+    const int* block_table;     /* [batch][max_pages] */
+    int max_pages, page;
+    const void *cos_outer, *sin_outer /*[>= max_len][32]*/, *cos_inner, *sin_inner /*[>= 8][128]*/;
+    int* pos;                   /* events already in the KV cache = index of the event fed next (incremented) */
+    long long* ev_in;           /* [batch][8] the event fed next (rewritten with every generated event) */
+    long long* seq;             /* [batch][max_len][8] output; event pos+1 is written */
+    int max_len;
+    unsigned long long* rng_state;   /* {counter (advanced by 8 per event), seed}: as b200_uniform_fill */
+    const unsigned char* dense_mask; /* may be NULL: [batch][V] extra sampling mask ANDed with the grammar */
+    const int* lut;             /* [n_event_types][8][2] parameter id ranges (midi_tokenizer.py:517-535) */
+    int n_event_types, eos_id, pad_id;
+    float temp, top_p;
+    int top_k, batch;
+} b200_decode_desc;
+size_t b200_decode_events_workspace_bytes(const b200_decode_desc* d);
+int b200_decode_events(const b200_decode_desc* d, int n_events, void* workspace /*256-byte aligned*/,
+                       size_t workspace_bytes, cudaStream_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "midi_b200", "libmidi_b200.so")
-SOURCES = ["runtime.cu", "elementwise.cu", "gemm_tcgen05.cu", "attn_flash.cu", "attn_tc05.cu", "attn_tiny.cu", "train_misc.cu", "decode.cu"]
+SOURCES = ["runtime.cu", "elementwise.cu", "gemm_tcgen05.cu", "attn_flash.cu", "attn_tc05.cu", "attn_tiny.cu", "train_misc.cu", "decode.cu", "decode_persist.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--threads", "2"]
 

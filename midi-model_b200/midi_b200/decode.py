@@ -270,6 +270,55 @@ class GraphGenerator:
         self.mask = torch.ones((batch, V), dtype=torch.uint8, device=dev)
         self.graph = None
         self.stream = torch.cuda.Stream(device=dev)
+        self._persist = None            # (descriptor, pointer tables, workspace) of the persistent kernel, built on first use
+
+    # ------------------------------------------------------------------ persistent kernel (csrc/decode_persist.cu)
+    def persistent_ok(self) -> bool:
+        c1, c2 = self.outer.eng.cfg, self.inner.eng.cfg
+        return (self.B <= 16 and c1.hidden == 1024 and c2.hidden == 1024 and c1.head_dim == 64 and c2.head_dim == 256
+                and c1.inner % 256 == 0 and c2.inner % 256 == 0 and self.T == 8 and self.kv1.page % 32 == 0)
+
+    def _persistent(self):
+        """b200_decode_desc for this loop's state: whole events run inside ONE cooperative kernel (one CTA per SM, grid
+        barriers between the dependent phases) instead of ~210 launches per event."""
+        if self._persist is not None and self._persist[0] == self.outer.version:
+            return self._persist[1:]
+        import ctypes
+        dev = self.lm_head.device
+
+        def table(eng):
+            rows = [[w.qkv.data_ptr(), w.o.data_ptr(), w.gu.data_ptr(), w.down.data_ptr(), w.ln1.data_ptr(), w.ln2.data_ptr()]
+                    for w in eng.layers]
+            return torch.tensor(rows, dtype=torch.int64, device=dev)
+
+        t_outer, t_inner = table(self.outer.eng), table(self.inner.eng)
+        t_kv = torch.tensor([[k.data_ptr(), v.data_ptr()] for k, v in zip(self.kv1.k, self.kv1.v)], dtype=torch.int64, device=dev)
+        c1, c2 = self.outer.eng.cfg, self.inner.eng.cfg
+        d = lib.DecodeDesc()
+        d.outer_w, d.inner_w, d.n_outer, d.n_inner = t_outer.data_ptr(), t_inner.data_ptr(), c1.n_layer, c2.n_layer
+        d.outer_norm, d.inner_norm = self.outer.eng.norm.data_ptr(), self.inner.eng.norm.data_ptr()
+        d.lm_head, d.emb_outer, d.emb_inner = self.lm_head.data_ptr(), self.outer.eng.embed.data_ptr(), self.inner.eng.embed.data_ptr()
+        d.H, d.I_outer, d.I_inner, d.nh_outer, d.nh_inner = c1.hidden, c1.inner, c2.inner, c1.n_head, c2.n_head
+        d.V, d.pitch, d.eps = self.V, self.pitch, c1.eps
+        d.kv_outer, d.block_table = t_kv.data_ptr(), self.kv1.block_table.data_ptr()
+        d.max_pages, d.page = self.kv1.max_pages, self.kv1.page
+        d.cos_outer, d.sin_outer = self.outer.cos.data_ptr(), self.outer.sin.data_ptr()
+        d.cos_inner, d.sin_inner = self.inner.cos.data_ptr(), self.inner.sin.data_ptr()
+        d.pos, d.ev_in, d.seq, d.max_len = self.pos.data_ptr(), self.ev_in.data_ptr(), self.seq.data_ptr(), self.max_len
+        d.rng_state, d.dense_mask, d.lut = self.counter.data_ptr(), self.mask.data_ptr(), self.g.lut.data_ptr()
+        d.n_event_types, d.eos_id, d.pad_id = self.g.n_event_types, self.g.eos, self.g.pad
+        d.temp, d.top_p, d.top_k, d.batch = self.temp, self.top_p, max(1, self.top_k), self.B
+        nbytes = lib.load().b200_decode_events_workspace_bytes(ctypes.byref(d))
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+        off = (-ws.data_ptr()) % 256
+        self._persist = (self.outer.version, d, ws[off:off + nbytes], (t_outer, t_inner, t_kv))
+        return self._persist[1:]
+
+    def _events_persistent(self, n: int) -> None:
+        """Run `n` generated events in one launch (stops early inside the kernel at max_len)."""
+        import ctypes
+        d, ws, _ = self._persistent()
+        lib.call("b200_decode_events", ctypes.byref(d), int(n), ws.data_ptr(), ws.numel(), lib.stream())
 
     def set_deny(self, ids) -> None:
         """Token ids that may never be sampled (empty = plain grammar)."""
@@ -316,11 +365,13 @@ class GraphGenerator:
         self.ev_in.copy_(prompt[:, P - 1])
         self.counter.copy_(torch.tensor([0, self.seed], dtype=torch.int64))
 
-    def _prepare(self, prompt: torch.Tensor, use_graph: bool) -> None:
+    def _prepare(self, prompt: torch.Tensor, use_graph) -> None:
         """Load the prompt into the device state; capture the per-event graph on first use (current stream = self.stream)."""
         self._set_state(prompt)
         if self.table_version != self.outer.version:    # RoPE tables were re-created: the captured addresses are stale
             self.graph, self.table_version = None, self.outer.version
+        if use_graph == "persist":
+            return
         if use_graph and self.graph is None:
             self._event()                       # warm-up (allocations, function attributes) outside capture
             torch.cuda.synchronize()
@@ -330,10 +381,18 @@ class GraphGenerator:
             self.graph = g
             self._set_state(prompt)             # undo the warm-up's state changes
 
-    def events(self, prompt: torch.Tensor, use_graph: bool = True):
+    def _mode(self, use_graph):
+        """True / "graph": CUDA-graph replay per event; False: the same launches issued from the host; "persist": the
+        persistent kernel (falls back to the graph loop for shapes it is not built for)."""
+        if use_graph == "persist" and not self.persistent_ok():
+            return True
+        return use_graph
+
+    def events(self, prompt: torch.Tensor, use_graph=True):
         """Generator form (app.py:27-120): yields each new event as an int64 [B, T] CPU tensor right after its graph
-        replay -- one device->host copy per EVENT, none per token -- and stops after the event in which every row
+        replay / kernel -- one device->host copy per EVENT, none per token -- and stops after the event in which every row
         emitted EOS (app.py:119) or at max_len."""
+        use_graph = self._mode(use_graph)
         P = prompt.shape[1]
         cur = torch.cuda.current_stream()
         self.stream.wait_stream(cur)
@@ -341,7 +400,9 @@ class GraphGenerator:
             self._prepare(prompt, use_graph)
         for i in range(self.max_len - P):
             with torch.cuda.stream(self.stream):          # not held across the yield
-                if use_graph:
+                if use_graph == "persist":
+                    self._events_persistent(1)
+                elif use_graph:
                     self.graph.replay()
                 else:
                     self._event()
@@ -351,7 +412,7 @@ class GraphGenerator:
                 break
         cur.wait_stream(self.stream)
 
-    def run(self, prompt: torch.Tensor, use_graph: bool = True, check_every: int = 32, progress=None,
+    def run(self, prompt: torch.Tensor, use_graph=True, check_every: int = 32, progress=None,
             stop_on_eos: bool = True, max_new: Optional[int] = None) -> torch.Tensor:
         """`max_new` stops after that many generated events although the pools (and the split-T attention) are sized for
         max_len: a serving process keeps ONE loop with full-context pools and cuts individual requests short."""
@@ -359,6 +420,7 @@ class GraphGenerator:
         n_new = self.max_len - P
         if max_new is not None:
             n_new = min(n_new, int(max_new))
+        use_graph = self._mode(use_graph)
         if n_new <= 0:
             return prompt
         cur = torch.cuda.current_stream()
@@ -369,11 +431,14 @@ class GraphGenerator:
             stop_at = None
             while done < n_new:
                 n = min(check_every, n_new - done)
-                for _ in range(n):
-                    if use_graph:
-                        self.graph.replay()
-                    else:
-                        self._event()
+                if use_graph == "persist":
+                    self._events_persistent(n)           # one launch for the whole block of events
+                else:
+                    for _ in range(n):
+                        if use_graph:
+                            self.graph.replay()
+                        else:
+                            self._event()
                 done += n
                 if progress is not None:
                     progress(n)

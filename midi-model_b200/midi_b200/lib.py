@@ -68,7 +68,23 @@ SIGNATURES = {
     "b200_uniform_fill": (i32, [vp, i32, u64, vp, vp]),
     "b200_add_int": (i32, [vp, i32, vp]),
     "b200_event_commit": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
+    "b200_decode_events_workspace_bytes": (sz, [vp]),
+    "b200_decode_events": (i32, [vp, i32, vp, sz, vp]),
 }
+
+
+class DecodeDesc(C.Structure):
+    """b200_decode_desc of include/midi_b200.h (field for field)."""
+    _fields_ = [("outer_w", vp), ("inner_w", vp), ("n_outer", i32), ("n_inner", i32),
+                ("outer_norm", vp), ("inner_norm", vp), ("lm_head", vp), ("emb_outer", vp), ("emb_inner", vp),
+                ("H", i32), ("I_outer", i32), ("I_inner", i32), ("nh_outer", i32), ("nh_inner", i32), ("V", i32), ("pitch", i32),
+                ("eps", f32),
+                ("kv_outer", vp), ("block_table", vp), ("max_pages", i32), ("page", i32),
+                ("cos_outer", vp), ("sin_outer", vp), ("cos_inner", vp), ("sin_inner", vp),
+                ("pos", vp), ("ev_in", vp), ("seq", vp), ("max_len", i32),
+                ("rng_state", vp), ("dense_mask", vp), ("lut", vp),
+                ("n_event_types", i32), ("eos_id", i32), ("pad_id", i32),
+                ("temp", f32), ("top_p", f32), ("top_k", i32), ("batch", i32)]
 
 
 class B200Error(RuntimeError):

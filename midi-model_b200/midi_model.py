@@ -296,6 +296,14 @@ def _inner_backward(rt, model, sv, hs, dlogits, ids, N, L, n_ids, has_hidden, g,
     return (dhidden,)
 
 
+def _loop_mode(mode: str):
+    """B200_GENERATE: "persist" (default: one persistent cooperative kernel per block of events), "graph" (one CUDA-graph
+    replay per event), "nograph" (the graph's launches issued from the host), "eager" (host-driven reference-shaped loop)."""
+    if mode == "persist":
+        return "persist"
+    return mode not in ("nograph", "eager")
+
+
 class _KVState:
     """Paged KV cache hung off the caller's (opaque) DynamicCache object."""
 
@@ -572,12 +580,12 @@ class MIDIModel(PreTrainedModel):
         inp = self._prompt_tensor(prompt, batch_size, dev)[:, -4096:]
         if inp.shape[1] >= max_len:
             return
-        mode = os.environ.get("B200_GENERATE", "graph")
+        mode = os.environ.get("B200_GENERATE", "persist")
         # this generation owns its loop state (no lock is held across the yields; see _Runtime.gen_pool)
         key, gg = self._checkout_generator(batch_size, max_len, temp, top_p, top_k, generator)
         try:
             gg.set_deny(deny)
-            for ev in gg.events(inp, use_graph=(mode not in ("nograph", "eager"))):
+            for ev in gg.events(inp, use_graph=_loop_mode(mode)):
                 yield ev.numpy()
         finally:
             gg.set_deny(())
@@ -595,7 +603,7 @@ class MIDIModel(PreTrainedModel):
             return inp.cpu().numpy()
         if rt.grammar is None:
             rt.grammar = _dec.GrammarLUT(tok, dev)
-        mode = os.environ.get("B200_GENERATE", "graph")
+        mode = os.environ.get("B200_GENERATE", "persist")
         if mode != "eager" and max_len - cur_len >= 4:
             # device-resident loop: one CUDA graph replay per event (midi_b200/decode.py::GraphGenerator)
             key, gg = self._checkout_generator(batch_size, max_len, temp, top_p, top_k, generator)
@@ -603,7 +611,7 @@ class MIDIModel(PreTrainedModel):
                 gg.set_deny(())
                 bar = tqdm.tqdm(desc="generating", total=max_len - cur_len)
                 with bar:
-                    out = gg.run(inp, use_graph=(mode != "nograph"), progress=bar.update)
+                    out = gg.run(inp, use_graph=_loop_mode(mode), progress=bar.update)
             finally:
                 self._return_generator(key, gg)
             return out.cpu().numpy()

@@ -1,6 +1,6 @@
 """A/B of the tcgen05 attention kernels against torch's F.scaled_dot_product_attention (the reference's backend,
 hf integrations/sdpa_attention.py:92-101) at the benchmark shape (8 sequences, 16 heads, 2048 events, head_dim 64,
-causal, bf16), forward and backward, plus the token-level shape (131 072 sequences of 8 tokens, 4 heads of 256).
+causal, bf16), forward and backward, plus the token-level shape (16 384 events x 8 tokens, 4 heads of 256).
 CUDA events, 3 warm-up + 20 launches.  Writes gpurun_out/attn_vs_sdpa.json.
 
     python tools/attn_vs_sdpa.py
@@ -56,8 +56,8 @@ def main():
     res["event_bwd"] = {"ours_ms": t, "sdpa_ms": t_ref, "ours_tflops": 2.5 * fl_f / t / 1e9, "sdpa_tflops": 2.5 * fl_f / t_ref / 1e9, "ratio": t_ref / t}
     res["event_fwd_maxabs_vs_sdpa"] = float((o.view(B, S, nh, D).transpose(1, 2).float() - out_ref.float()).abs().max())
     del q, k, v, out_ref, qkv, do
-    # token level: 131 072 sequences x 8 positions, 4 heads x 256 (what hf runs through SDPA as (N, 4, 8, 256))
-    N, L, nh, D = 131072, 8, 4, 256
+    # token level: 16 384 events x 8 positions, 4 heads x 256 (what hf runs through SDPA as (N, 4, 8, 256))
+    N, L, nh, D = 16384, 8, 4, 256
     H = nh * D
     qkv = torch.randn(N * L, 3 * H, generator=g, device=DEV).to(BF)
     do = torch.randn(N * L, H, generator=g, device=DEV).to(BF)
