@@ -43,6 +43,7 @@ struct DD {                              // b200_decode_desc with typed pointers
     int n_event_types, eos_id, pad_id;
     float temp, top_p;
     int top_k, batch;
+    unsigned long long* prof;            // optional: per-phase clock64 totals of CTA 0 (tuning hook)
 };
 
 struct PD {                              // kernel parameters (device pointers resolved on the host)
@@ -103,6 +104,22 @@ __device__ __forceinline__ void grid_sync(GridBar& gb) {
     }
     __syncthreads();
 }
+
+// tuning hook: phase id -> cycles spent by CTA 0 between the barrier that opened the phase and the one that closed it
+enum { PH_QKV_O, PH_ATT_O, PH_CMB_O, PH_OPROJ_O, PH_GU_O, PH_DOWN_O, PH_QKV_I, PH_ATT_I, PH_OPROJ_I, PH_GU_I, PH_DOWN_I,
+       PH_LMHEAD, PH_SAMPLE, PH_COMMIT, PH_COUNT };
+struct Prof {
+    unsigned long long* buf;
+    long long last;
+    __device__ __forceinline__ void mark(int id) {
+        if (buf != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+            const long long t = clock64();
+            buf[id] += (unsigned long long)(t - last);
+            buf[32 + id] += 1ull;
+            last = t;
+        }
+    }
+};
 
 struct LayerW {
     const bf16 *qkv, *o, *gu, *down, *ln1, *ln2;
@@ -546,6 +563,7 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
 
     int events_done = 0;
     Pre pre;
+    Prof prof{d.prof, clock64()};
     for (int e = 0; e < p.n_events; e++) {
         if (pos + 1 >= d.max_len) break;
         // =============================== event-level stack: one new position per row ===============================
@@ -553,7 +571,7 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
             const LayerW w = layer_w(d.outer_w, l);
             // ---- norm + QKV
             prefetch_rows<false>(pre, w.qkv, H, 3 * H, gw, lane, pol_stream);
-            if (l > 0) grid_sync(gb);     // layer 0 reads only this CTA's copy of the event (cur_ev): nothing to wait for
+            if (l > 0) { grid_sync(gb); prof.mark(PH_DOWN_O); }   // layer 0 reads only this CTA's copy of the event: no wait
             if (warp < B) {
                 bf16* row = xs + (size_t)warp * H;
                 if (l == 0) {
@@ -583,20 +601,27 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
             // ---- RoPE + KV append + attention over positions 0..pos
             prefetch_rows<false>(pre, w.o, H, H, gw, lane, pol_stream);
             grid_sync(gb);
+            prof.mark(PH_QKV_O);
             int n_chunks;
             outer_attention(p, l, pos, B, gw, ngw, lane, q_s, kn_s, vn_s, n_chunks);
             if (n_chunks > 1) {
                 grid_sync(gb);
+                prof.mark(PH_ATT_O);
                 outer_attention_combine(p, B, n_chunks, gw, ngw, lane);
+                grid_sync(gb);
+                prof.mark(PH_CMB_O);
+            } else {
+                grid_sync(gb);
+                prof.mark(PH_ATT_O);
             }
             // ---- o_proj + residual
-            grid_sync(gb);
             if (warp < B) copy_row_from_global(xs + (size_t)warp * H, p.attn + (size_t)warp * H, H, lane);
             __syncthreads();
             gemv_pairs<BM, false>(xs, H, w.o, H, H, B, p.x, H, p.h, H, gw, ngw, lane, pre, pol_stream);
             // ---- norm + gate|up + SwiGLU
             prefetch_rows<true>(pre, w.gu, H, d.I_outer, gw, lane, pol_stream);
             grid_sync(gb);
+            prof.mark(PH_OPROJ_O);
             if (warp < B) {
                 copy_row_from_global(xs + (size_t)warp * H, p.h + (size_t)warp * H, H, lane);
                 __syncwarp();
@@ -607,6 +632,7 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
             // ---- down + residual
             prefetch_rows<false>(pre, w.down, d.I_outer, H, gw, lane, pol_stream);
             grid_sync(gb);
+            prof.mark(PH_GU_O);
             __syncthreads();
             if (warp < B) copy_row_from_global(xs + (size_t)warp * d.I_outer, p.act + (size_t)warp * d.I_outer, d.I_outer, lane);
             __syncthreads();
@@ -620,6 +646,7 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
                 const LayerW w = layer_w(d.inner_w, l);
                 prefetch_rows<false>(pre, w.qkv, H, 3 * H, gw, lane, pol_keep);
                 grid_sync(gb);
+                prof.mark(l > 0 ? PH_DOWN_I : (i > 0 ? PH_SAMPLE : PH_DOWN_O));
                 if (i == 1 && l == 0) {
                     // how many token steps this event needs (midi_model.py:234-237: stop once every live row has all its
                     // parameters; two steps at least, like the reference's loop)
@@ -660,13 +687,16 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
                 gemv_pairs<BM, false>(xs, H, w.qkv, H, 3 * H, B, nullptr, 0, p.qkv, 3 * H, gw, ngw, lane, pre, pol_keep);
                 prefetch_rows<false>(pre, w.o, H, H, gw, lane, pol_keep);
                 grid_sync(gb);
+                prof.mark(PH_QKV_I);
                 inner_attention(p, l, i, B, gw, ngw, lane);
                 grid_sync(gb);
+                prof.mark(PH_ATT_I);
                 if (warp < B) copy_row_from_global(xs + (size_t)warp * H, p.attn + (size_t)warp * H, H, lane);
                 __syncthreads();
                 gemv_pairs<BM, false>(xs, H, w.o, H, H, B, p.x2, H, p.h2, H, gw, ngw, lane, pre, pol_keep);
                 prefetch_rows<true>(pre, w.gu, H, d.I_inner, gw, lane, pol_keep);
                 grid_sync(gb);
+                prof.mark(PH_OPROJ_I);
                 if (warp < B) {
                     copy_row_from_global(xs + (size_t)warp * H, p.h2 + (size_t)warp * H, H, lane);
                     __syncwarp();
@@ -676,6 +706,7 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
                 gemv_pairs<BM, true>(xs, H, w.gu, H, d.I_inner, B, nullptr, 0, p.act, d.I_inner, gw, ngw, lane, pre, pol_keep);
                 prefetch_rows<false>(pre, w.down, d.I_inner, H, gw, lane, pol_keep);
                 grid_sync(gb);
+                prof.mark(PH_GU_I);
                 if (warp < B) copy_row_from_global(xs + (size_t)warp * d.I_inner, p.act + (size_t)warp * d.I_inner, d.I_inner, lane);
                 __syncthreads();
                 gemv_pairs<BM, false>(xs, d.I_inner, w.down, d.I_inner, H, B, p.h2, H, p.x2, H, gw, ngw, lane, pre, pol_keep);
@@ -683,6 +714,7 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
             // ---- final norm + lm_head
             prefetch_rows<false>(pre, d.lm_head, H, d.V, gw, lane, pol_keep);
             grid_sync(gb);
+            prof.mark(PH_DOWN_I);
             if (warp < B) {
                 copy_row_from_global(xs + (size_t)warp * H, p.x2 + (size_t)warp * H, H, lane);
                 __syncwarp();
@@ -692,6 +724,7 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
             gemv_pairs<BM, false>(xs, H, d.lm_head, H, d.V, B, nullptr, 0, p.logits, d.pitch, gw, ngw, lane, pre, pol_keep);
             // ---- sample (one CTA per row): temperature softmax, grammar range, top-p / top-k, draw
             grid_sync(gb);
+            prof.mark(PH_LMHEAD);
             if ((int)blockIdx.x < B) {
                 const int b = blockIdx.x;
                 const long long ev0 = (i == 0) ? 0 : __ldcg(p.ev_t + b);
@@ -702,6 +735,7 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
         }
         // =============================== commit the event ========================================================
         grid_sync(gb);                                   // every row's tokens are visible
+        prof.mark(PH_SAMPLE);
         __syncthreads();
         for (int k = threadIdx.x; k < B * PD_T; k += PD_THREADS) {
             const int b = k / PD_T, t = k % PD_T;
@@ -713,6 +747,7 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
             }
         }
         __syncthreads();
+        prof.mark(PH_COMMIT);
         pos++;
         events_done++;
     }
@@ -777,6 +812,7 @@ extern "C" int b200_decode_events(const b200_decode_desc* desc, int n_events, vo
     t.pos = d.pos; t.ev_in = d.ev_in; t.seq = d.seq; t.max_len = d.max_len; t.rng_state = d.rng_state;
     t.dense_mask = d.dense_mask; t.lut = d.lut; t.n_event_types = d.n_event_types; t.eos_id = d.eos_id; t.pad_id = d.pad_id;
     t.temp = d.temp; t.top_p = d.top_p; t.top_k = d.top_k; t.batch = d.batch;
+    t.prof = d.prof;
     p.bar = (unsigned int*)(ws + L.bar);
     p.x = (bf16*)(ws + L.x); p.h = (bf16*)(ws + L.h); p.x2 = (bf16*)(ws + L.x2); p.h2 = (bf16*)(ws + L.h2);
     p.qkv = (bf16*)(ws + L.qkv); p.attn = (bf16*)(ws + L.attn); p.act = (bf16*)(ws + L.act);

@@ -65,6 +65,60 @@ ce_fwd_kernel(const bf16* __restrict__ logits, const long long* __restrict__ tar
     }
 }
 
+// Warp-per-row variant: the whole row (<= 16 vectors of 8 per lane, i.e. V <= 4096) is loaded ONCE into registers with all
+// loads in flight, max and sum-of-exponentials are then two passes over registers, reductions are shuffles (no block
+// barrier).  The CTA-per-row kernel above re-read the row and went through four __syncthreads per 6.8 KB row: 0.28 of the
+// copy bandwidth (profiles/r2_bench_1gpu_start.json).
+constexpr int CEW_WARPS = 4;
+template <int VPL>
+__global__ void __launch_bounds__(CEW_WARPS * 32)
+ce_fwd_warp_kernel(const bf16* __restrict__ logits, const long long* __restrict__ targets, float* __restrict__ lse_out,
+                   float* __restrict__ row_loss, long long R, int V, int ld, long long ignore_index) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nvec = (V + 7) / 8;
+    for (long long r = (long long)blockIdx.x * CEW_WARPS + warp; r < R; r += (long long)gridDim.x * CEW_WARPS) {
+        const bf16* row = logits + (size_t)r * ld;
+        uint4 raw[VPL];
+#pragma unroll
+        for (int k = 0; k < VPL; k++) {
+            const int v = lane + 32 * k;
+            if (v < nvec) raw[k] = ld_nc16(row + v * 8);
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < VPL; k++) {
+            const int v = lane + 32 * k;
+            if (v < nvec) {
+                float f[8];
+                unpack8(raw[k], f);
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (v * 8 + j < V) mx = fmaxf(mx, f[j]);
+            }
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPL; k++) {
+            const int v = lane + 32 * k;
+            if (v < nvec) {
+                float f[8];
+                unpack8(raw[k], f);
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (v * 8 + j < V) sum += __expf(f[j] - mx);
+            }
+        }
+        sum = warp_sum(sum);
+        if (lane == 0) {
+            const float lse = mx + logf(sum);
+            lse_out[r] = lse;
+            const long long t = targets[r];
+            row_loss[r] = (t == ignore_index || t < 0 || t >= V) ? 0.f : lse - __bfloat162float(row[t]);
+        }
+    }
+}
+
 // single CTA: loss_sum = sum(row_loss), count = #(target != ignore); out[0] = mean loss, out[1] = count
 __global__ void ce_reduce_kernel(const float* __restrict__ row_loss, const long long* __restrict__ targets, size_t R, int V,
                                  long long ignore_index, float* __restrict__ out) {
@@ -182,8 +236,17 @@ extern "C" int b200_ce_fwd(const void* logits, const long long* targets, float* 
     B200_CHECK_ARG(ld % 8 == 0 && ld >= V, "ce_fwd: ld (%d) must be a multiple of 8 and >= V (%d)", ld, V);
     B200_CHECK_ARG(((V + 7) / 8) * 8 <= ld, "ce_fwd: row pitch too small for vector loads");
     if (rows > 0) {
-        ce_fwd_kernel<<<(unsigned)rows, CE_THREADS, 0, stream>>>((const bf16*)logits, targets, lse, row_loss, V, ld,
-                                                                 ignore_index);
+        const int vpl = ((V + 7) / 8 + 31) / 32;          // 16-byte vectors per lane when one warp holds a row
+        long long blocks = (rows + CEW_WARPS - 1) / CEW_WARPS;
+        const long long cap = (long long)b200_num_sms() * 16;
+        const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
+#define B200_CE_FWDW(VPL) ce_fwd_warp_kernel<VPL><<<grid, CEW_WARPS * 32, 0, stream>>>((const bf16*)logits, targets, lse, row_loss, rows, V, ld, ignore_index)
+        if (vpl <= 4) B200_CE_FWDW(4);
+        else if (vpl <= 8) B200_CE_FWDW(8);
+        else if (vpl <= 14) B200_CE_FWDW(14);
+        else if (vpl <= 16) B200_CE_FWDW(16);
+        else ce_fwd_kernel<<<(unsigned)rows, CE_THREADS, 0, stream>>>((const bf16*)logits, targets, lse, row_loss, V, ld, ignore_index);
+#undef B200_CE_FWDW
         B200_CHECK_LAUNCH("ce_fwd");
     }
     ce_reduce_kernel<<<1, 1024, 0, stream>>>(row_loss, targets, (size_t)rows, V, ignore_index, loss_and_count);

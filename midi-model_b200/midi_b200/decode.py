@@ -308,6 +308,10 @@ class GraphGenerator:
         d.rng_state, d.dense_mask, d.lut = self.counter.data_ptr(), self.mask.data_ptr(), self.g.lut.data_ptr()
         d.n_event_types, d.eos_id, d.pad_id = self.g.n_event_types, self.g.eos, self.g.pad
         d.temp, d.top_p, d.top_k, d.batch = self.temp, self.top_p, max(1, self.top_k), self.B
+        self.prof = None
+        if __import__("os").environ.get("B200_DECODE_PROFILE"):
+            self.prof = torch.zeros(64, dtype=torch.int64, device=dev)
+            d.prof = self.prof.data_ptr()
         nbytes = lib.load().b200_decode_events_workspace_bytes(ctypes.byref(d))
         ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
         off = (-ws.data_ptr()) % 256

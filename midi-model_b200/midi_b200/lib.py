@@ -84,7 +84,7 @@ class DecodeDesc(C.Structure):
                 ("pos", vp), ("ev_in", vp), ("seq", vp), ("max_len", i32),
                 ("rng_state", vp), ("dense_mask", vp), ("lut", vp),
                 ("n_event_types", i32), ("eos_id", i32), ("pad_id", i32),
-                ("temp", f32), ("top_p", f32), ("top_k", i32), ("batch", i32)]
+                ("temp", f32), ("top_p", f32), ("top_k", i32), ("batch", i32), ("prof", vp)]
 
 
 class B200Error(RuntimeError):
