@@ -215,10 +215,11 @@ typedef struct b200_decode_desc {
     int n_event_types, eos_id, pad_id;
     float temp, top_p;
     int top_k, batch;
-    unsigned long long* prof;   /* may be NULL.  Tuning hook: device array of 64 counters; [i] += SM cycles CTA 0 spent in phase i
+    unsigned long long* prof;   /* may be NULL.  Tuning hook: device array of 128 counters; [i] += SM cycles CTA 0 spent in phase i
                                    (incl. the closing barrier), [32 + i] += 1; phases: qkv, attention, combine, o_proj, gate|up,
                                    down of the event-level stack (0-5) and of the token-level stack (6-10, no combine),
-                                   lm_head (11), sample (12), commit (13) */
+                                   lm_head (11), sample (12), commit (13); [64 + 2i] / [65 + 2i] += the part of phase i
+                                   spent staging activations / doing the phase's own work (the rest = barrier wait) */
 } b200_decode_desc;
 size_t b200_decode_events_workspace_bytes(const b200_decode_desc* d);
 int b200_decode_events(const b200_decode_desc* d, int n_events, void* workspace /*256-byte aligned*/,

@@ -543,8 +543,8 @@ sample_logits_kernel(const bf16* __restrict__ logits, int V, int ld, float temp,
                      long long* __restrict__ out, int out_stride) {
     __shared__ float s_p[SMP_MAXV];
     __shared__ int s_i[SMP_MAXV];
-    __shared__ int s_cnt[SMP_THREADS + 1];
-    __shared__ float s_red[16];
+    __shared__ int s_cnt[SMP_THREADS + 8];
+    __shared__ float s_red[64];
     const int r = blockIdx.x;
     int lo, hi;
     if (step == 0) {
@@ -559,43 +559,10 @@ sample_logits_kernel(const bf16* __restrict__ logits, int V, int ld, float temp,
             if (hi <= lo) { lo = pad_id; hi = pad_id + 1; }
         }
     }
-    // softmax(logits / temp) in bf16 semantics: x = bf16(l / temp); p = bf16(exp(x - max) / sum)
-    float mx = -INFINITY;
-    for (int i = threadIdx.x; i < V; i += blockDim.x) {
-        const float x = bf16_round(__bfloat162float(logits[(size_t)r * ld + i]) / temp);
-        s_p[i] = x;
-        mx = fmaxf(mx, x);
-    }
-    mx = warp_max(mx);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
-    __syncthreads();
-    mx = s_red[0];
-    for (int w = 1; w < SMP_THREADS / 32; w++) mx = fmaxf(mx, s_red[w]);
-    float sum = 0.f;
-    for (int i = threadIdx.x; i < V; i += blockDim.x) sum += __expf(s_p[i] - mx);
-    sum = warp_sum(sum);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) s_red[8 + (threadIdx.x >> 5)] = sum;
-    __syncthreads();
-    sum = 0.f;
-    for (int w = 0; w < SMP_THREADS / 32; w++) sum += s_red[8 + w];
-    const float inv = 1.f / sum;
-    for (int i = threadIdx.x; i < V; i += blockDim.x) {
-        bool ok = (i >= lo && i < hi);
-        if (ok && dense_mask) ok = dense_mask[(size_t)r * V + i] != 0;
-        s_p[i] = ok ? bf16_round(__expf(s_p[i] - mx) * inv) : 0.f;
-    }
-    __syncthreads();
-    int n = smp::compact_nonzero<SMP_THREADS>(s_p, s_i, V, s_cnt);
-    int id;
-    if (n == 0) {
-        // every allowed probability underflowed: the reference would raise inside multinomial (Appendix E.3);
-        // fall back to the lowest allowed id instead of crashing.
-        id = lo;
-    } else {
-        n = smp::preselect_topk<SMP_THREADS>(s_p, s_i, n, top_k, s_cnt);      // s_cnt (257 ints) is free again after the compaction
-        id = smp::sample_tail<SMP_THREADS>(s_p, s_i, n, top_p, top_k, uniforms[r], true);
-    }
+    // temperature softmax, grammar range / mask, top-p, top-k, draw (sampler.cuh)
+    const int id = smp::sample_logits_row<SMP_THREADS>(logits + (size_t)r * ld, V, temp, top_p, top_k, lo, hi,
+                                                       dense_mask ? dense_mask + (size_t)r * V : nullptr, uniforms[r], s_p, s_i,
+                                                       s_cnt, s_red, false);
     if (threadIdx.x == 0) out[(size_t)r * out_stride] = id;
 }
 

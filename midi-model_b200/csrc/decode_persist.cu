@@ -84,23 +84,31 @@ struct GridBar {
     unsigned int* ctr;
     unsigned int target, n;
 };
-// all CTAs are co-resident (cooperative launch).  Same protocol as cooperative_groups::grid_group::sync(): CTA barrier,
-// one thread publishes (fence + atomic) and spins until every CTA of this generation has arrived, CTA barrier.
-// The spin is bounded: a protocol bug traps instead of hanging the GPU.
+// All CTAs are co-resident (cooperative launch).  CTA barrier; one thread publishes with a release reduction and polls
+// with relaxed loads until every CTA of this generation has arrived; CTA barrier.  No acquire fence is needed after the
+// poll: every cross-CTA datum of this kernel is read with ld.global.cg (L2, where the release made it visible) and only
+// after the closing bar.sync, and a gpu-scope acquire would cost an L1 invalidation (CCTL.IVALL) per poll.  The polling
+// thread belongs to warp 0, which never has prefetch loads in flight (a release waits for the issuing thread's own
+// outstanding loads).  The spin is bounded: a protocol bug traps instead of hanging the GPU.
 __device__ __forceinline__ void grid_sync(GridBar& gb) {
     __syncthreads();
     gb.target += gb.n;
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(gb.ctr, 1u);
-        const long long t0 = clock64();
-        while (ld_acquire_u32(gb.ctr) < gb.target) {
-            if (clock64() - t0 > 4000000000LL) {
-                printf("b200: decode grid barrier timeout (block %d, target %u, counter %u)\n", blockIdx.x, gb.target, *gb.ctr);
-                __trap();
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(gb.ctr) : "memory");
+        unsigned v;
+        unsigned spins = 0;
+        long long t0 = 0;
+        for (;;) {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gb.ctr) : "memory");
+            if (v >= gb.target) break;
+            if ((++spins & 1023u) == 0) {
+                if (t0 == 0) t0 = clock64();
+                else if (clock64() - t0 > 4000000000LL) {
+                    printf("b200: decode grid barrier timeout (block %d, target %u, counter %u)\n", blockIdx.x, gb.target, v);
+                    __trap();
+                }
             }
         }
-        __threadfence();
     }
     __syncthreads();
 }
@@ -110,13 +118,22 @@ enum { PH_QKV_O, PH_ATT_O, PH_CMB_O, PH_OPROJ_O, PH_GU_O, PH_DOWN_O, PH_QKV_I, P
        PH_LMHEAD, PH_SAMPLE, PH_COMMIT, PH_COUNT };
 struct Prof {
     unsigned long long* buf;
-    long long last;
+    long long last, last_sub;
     __device__ __forceinline__ void mark(int id) {
         if (buf != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
             const long long t = clock64();
             buf[id] += (unsigned long long)(t - last);
             buf[32 + id] += 1ull;
             last = t;
+            last_sub = t;
+        }
+    }
+    // sub-interval k of phase id (0: staging the activations, 1: the phase's own work; the rest is barrier wait)
+    __device__ __forceinline__ void sub(int id, int k) {
+        if (buf != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+            const long long t = clock64();
+            buf[64 + id * 2 + k] += (unsigned long long)(t - last_sub);
+            last_sub = t;
         }
     }
 };
@@ -272,7 +289,7 @@ __device__ __forceinline__ size_t kv_base(const int* bt, int max_pages, int page
     return (((size_t)pg * nh + h) * page + (t % page)) * D;
 }
 
-__device__ __forceinline__ void outer_attention(const PD& p, int layer, int pos, int B, int gw, int ngw, int lane,
+__device__ __noinline__ void outer_attention(const PD& p, int layer, int pos, int B, int gw, int ngw, int lane,
                                                 float* q_s, bf16* kn_s, bf16* vn_s, int& n_chunks_out) {
     const DD& d = p.d;
     constexpr int D = 64;
@@ -356,17 +373,25 @@ __device__ __forceinline__ void outer_attention(const PD& p, int layer, int pos,
             const float pb = bf16_round(pr);                    // P rounded to bf16 before P.V (flash semantics)
             const int nk = min(32, t1 - tb);
             const bf16* vp = vpool + base + 2 * lane;
-#pragma unroll 8
-            for (int j = 0; j < nk; j++) {
-                const float pj = __shfl_sync(0xffffffffu, pb, j);
-                float2 vf;
-                if (tb + j == pos) vf = __bfloat1622float2(*reinterpret_cast<const bf162*>(vn_s + 2 * lane));
-                else {
-                    const unsigned int raw = __ldcg(reinterpret_cast<const unsigned int*>(vp + (size_t)j * D));
-                    vf = __bfloat1622float2(*reinterpret_cast<const bf162*>(&raw));
+            // the 32 value rows of the block (4 bytes per lane each) in flight together, then the FMAs
+            unsigned int vraw[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+                if (j < nk && tb + j != pos) vraw[j] = __ldcg(reinterpret_cast<const unsigned int*>(vp + (size_t)j * D));
+            if (owns_new && pos >= tb && pos < tb + 32) {
+                const unsigned int mine = *reinterpret_cast<const unsigned int*>(vn_s + 2 * lane);
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                    if (tb + j == pos) vraw[j] = mine;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                if (j < nk) {
+                    const float pj = __shfl_sync(0xffffffffu, pb, j);
+                    const float2 vf = __bfloat1622float2(*reinterpret_cast<const bf162*>(&vraw[j]));
+                    a0 = fmaf(pj, vf.x, a0);
+                    a1 = fmaf(pj, vf.y, a1);
                 }
-                a0 = fmaf(pj, vf.x, a0);
-                a1 = fmaf(pj, vf.y, a1);
             }
         }
         if (n_chunks == 1) {
@@ -382,7 +407,7 @@ __device__ __forceinline__ void outer_attention(const PD& p, int layer, int pos,
     }
 }
 
-__device__ __forceinline__ void outer_attention_combine(const PD& p, int B, int n_chunks, int gw, int ngw, int lane) {
+__device__ __noinline__ void outer_attention_combine(const PD& p, int B, int n_chunks, int gw, int ngw, int lane) {
     constexpr int D = 64;
     const int nh = p.d.nh_outer, H = p.d.H;
     for (int bh = gw; bh < B * nh; bh += ngw) {
@@ -407,7 +432,7 @@ __device__ __forceinline__ void outer_attention_combine(const PD& p, int B, int 
 }
 
 // ---- token-level attention (context <= 8, head_dim 256): one warp per (row, head), as decode_attn_small_kernel -------
-__device__ __forceinline__ void inner_attention(const PD& p, int layer, int step, int B, int gw, int ngw, int lane) {
+__device__ __noinline__ void inner_attention(const PD& p, int layer, int step, int B, int gw, int ngw, int lane) {
     const DD& d = p.d;
     constexpr int D = 256;
     const int nh = d.nh_inner, H = d.H;
@@ -438,29 +463,42 @@ __device__ __forceinline__ void inner_attention(const PD& p, int layer, int step
             *reinterpret_cast<uint4*>(v2 + o) = v_new;
         }
         const int T = step + 1;
-        float my_s = -INFINITY;
-        for (int t = 0; t < T; t++) {
-            float kf[8];
-            if (t == step) unpack8(k_new, kf);
-            else unpack8(ldcg16(k2 + ((size_t)b * PD_T + t) * H + h * D + lane * 8), kf);
-            float s = 0.f;
+        // all cached keys / values of this head at once (<= 7 rows of 16 bytes per lane): one L2 latency, not T
+        uint4 kraw[PD_T], vraw[PD_T];
 #pragma unroll
-            for (int j = 0; j < 8; j++) s = fmaf(kf[j], qr[j], s);
-            s = warp_sum(s) * scale;
-            if (lane == t) my_s = s;
+        for (int t = 0; t < PD_T; t++) {
+            if (t < step) {
+                kraw[t] = ldcg16(k2 + ((size_t)b * PD_T + t) * H + h * D + lane * 8);
+                vraw[t] = ldcg16(v2 + ((size_t)b * PD_T + t) * H + h * D + lane * 8);
+            }
+        }
+        float my_s = -INFINITY;
+#pragma unroll
+        for (int t = 0; t < PD_T; t++) {
+            if (t < T) {
+                float kf[8];
+                unpack8(t == step ? k_new : kraw[t], kf);
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; j++) s = fmaf(kf[j], qr[j], s);
+                s = warp_sum(s) * scale;
+                if (lane == t) my_s = s;
+            }
         }
         const float mx = warp_max(my_s);
         const float pr = (lane < T) ? __expf(my_s - mx) : 0.f;
         const float sum = warp_sum(pr);
         const float pb = bf16_round(pr);
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int t = 0; t < T; t++) {
-            const float pt = __shfl_sync(0xffffffffu, pb, t);
-            float vf[8];
-            if (t == step) unpack8(v_new, vf);
-            else unpack8(ldcg16(v2 + ((size_t)b * PD_T + t) * H + h * D + lane * 8), vf);
 #pragma unroll
-            for (int j = 0; j < 8; j++) acc[j] = fmaf(pt, vf[j], acc[j]);
+        for (int t = 0; t < PD_T; t++) {
+            if (t < T) {
+                const float pt = __shfl_sync(0xffffffffu, pb, t);
+                float vf[8];
+                unpack8(t == step ? v_new : vraw[t], vf);
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[j] = fmaf(pt, vf[j], acc[j]);
+            }
         }
         const float inv = 1.f / sum;
 #pragma unroll
@@ -470,7 +508,7 @@ __device__ __forceinline__ void inner_attention(const PD& p, int layer, int step
 }
 
 // ---- sampling of one row by one CTA (sample_logits_kernel of decode.cu, for PD_THREADS threads) -------------------
-__device__ int sample_row(const PD& p, int b, int step, long long ev0, float u, float* s_p, int* s_i, int* s_cnt, float* s_red) {
+__device__ __noinline__ int sample_row(const PD& p, int b, int step, long long ev0, float u, float* s_p, int* s_i, int* s_cnt, float* s_red) {
     const DD& d = p.d;
     const int V = d.V;
     int lo, hi;
@@ -485,43 +523,9 @@ __device__ int sample_row(const PD& p, int b, int step, long long ev0, float u, 
             if (hi <= lo) { lo = d.pad_id; hi = d.pad_id + 1; }
         }
     }
-    const bf16* logits = p.logits + (size_t)b * d.pitch;
-    float mx = -INFINITY;
-    for (int i = threadIdx.x; i < V; i += PD_THREADS) {
-        const float x = bf16_round(__bfloat162float(__ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(logits + i)))) / d.temp);
-        s_p[i] = x;
-        mx = fmaxf(mx, x);
-    }
-    mx = warp_max(mx);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
-    __syncthreads();
-    mx = s_red[0];
-    for (int w = 1; w < PD_WARPS; w++) mx = fmaxf(mx, s_red[w]);
-    float sum = 0.f;
-    for (int i = threadIdx.x; i < V; i += PD_THREADS) sum += __expf(s_p[i] - mx);
-    sum = warp_sum(sum);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) s_red[PD_WARPS + (threadIdx.x >> 5)] = sum;
-    __syncthreads();
-    sum = 0.f;
-    for (int w = 0; w < PD_WARPS; w++) sum += s_red[PD_WARPS + w];
-    const float inv = 1.f / sum;
-    const unsigned char* mrow = d.dense_mask ? d.dense_mask + (size_t)b * V : nullptr;
-    for (int i = threadIdx.x; i < V; i += PD_THREADS) {
-        bool ok = (i >= lo && i < hi);
-        if (ok && mrow) ok = mrow[i] != 0;
-        s_p[i] = ok ? bf16_round(__expf(s_p[i] - mx) * inv) : 0.f;
-    }
-    __syncthreads();
-    int n = smp::compact_nonzero<PD_THREADS>(s_p, s_i, V, s_cnt);
-    int id;
-    if (n == 0) {
-        id = lo;
-    } else {
-        n = smp::preselect_topk<PD_THREADS>(s_p, s_i, n, d.top_k, s_cnt);
-        id = smp::sample_tail<PD_THREADS>(s_p, s_i, n, d.top_p, d.top_k, u, true);
-    }
-    return id;
+    return smp::sample_logits_row<PD_THREADS>(p.logits + (size_t)b * d.pitch, V, d.temp, d.top_p, d.top_k, lo, hi,
+                                              d.dense_mask ? d.dense_mask + (size_t)b * V : nullptr, u, s_p, s_i, s_cnt, s_red,
+                                              true);
 }
 
 __device__ __forceinline__ float rng_uniform(unsigned long long seed, unsigned long long c, int i) {
@@ -542,14 +546,17 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
     float* s_p = reinterpret_cast<float*>(pd_smem + (size_t)BM * p.k_max * 2);      // sampler: probabilities
     int* s_i = reinterpret_cast<int*>(s_p + smp::SMP_MAXV);
     int* s_cnt = s_i + smp::SMP_MAXV;                                               // [PD_THREADS + 1]
-    float* s_red = reinterpret_cast<float*>(s_cnt + PD_THREADS + 8);                // [2 * PD_WARPS]
-    float* q_all = s_red + 2 * PD_WARPS;                                            // [PD_WARPS][64]
+    float* s_red = reinterpret_cast<float*>(s_cnt + PD_THREADS + 8);                // [64]
+    float* q_all = s_red + 64;                                                      // [PD_WARPS][64]
     bf16* kn_all = reinterpret_cast<bf16*>(q_all + PD_WARPS * 64);                  // [PD_WARPS][64]
     bf16* vn_all = kn_all + PD_WARPS * 64;
     int* cur_ev = reinterpret_cast<int*>(vn_all + PD_WARPS * 64);                   // [BM][8] event fed to the event-level stack
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ngw = gridDim.x * PD_WARPS;
     const int gw = warp * gridDim.x + blockIdx.x;      // interleave the CTAs: consecutive row pairs land on different SMs
+    // projections run on warps 1..15: warp 0 owns the grid barrier and must not have weight prefetches in flight
+    const int ngwv = gridDim.x * (PD_WARPS - 1);
+    const int gwv = warp == 0 ? 0x3fffffff : (warp - 1) * gridDim.x + blockIdx.x;
     float* q_s = q_all + warp * 64;
     bf16* kn_s = kn_all + warp * 64;
     bf16* vn_s = vn_all + warp * 64;
@@ -563,14 +570,14 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
 
     int events_done = 0;
     Pre pre;
-    Prof prof{d.prof, clock64()};
+    Prof prof{d.prof, clock64(), clock64()};
     for (int e = 0; e < p.n_events; e++) {
         if (pos + 1 >= d.max_len) break;
         // =============================== event-level stack: one new position per row ===============================
         for (int l = 0; l < d.n_outer; l++) {
             const LayerW w = layer_w(d.outer_w, l);
             // ---- norm + QKV
-            prefetch_rows<false>(pre, w.qkv, H, 3 * H, gw, lane, pol_stream);
+            prefetch_rows<false>(pre, w.qkv, H, 3 * H, gwv, lane, pol_stream);
             if (l > 0) { grid_sync(gb); prof.mark(PH_DOWN_O); }   // layer 0 reads only this CTA's copy of the event: no wait
             if (warp < B) {
                 bf16* row = xs + (size_t)warp * H;
@@ -597,29 +604,35 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
                 norm_row_inplace(row, H, w.ln1, d.eps, lane);
             }
             __syncthreads();
-            gemv_pairs<BM, false>(xs, H, w.qkv, H, 3 * H, B, nullptr, 0, p.qkv, 3 * H, gw, ngw, lane, pre, pol_stream);
+            prof.sub(PH_QKV_O, 0);
+            gemv_pairs<BM, false>(xs, H, w.qkv, H, 3 * H, B, nullptr, 0, p.qkv, 3 * H, gwv, ngwv, lane, pre, pol_stream);
+            prof.sub(PH_QKV_O, 1);
             // ---- RoPE + KV append + attention over positions 0..pos
-            prefetch_rows<false>(pre, w.o, H, H, gw, lane, pol_stream);
             grid_sync(gb);
             prof.mark(PH_QKV_O);
             int n_chunks;
             outer_attention(p, l, pos, B, gw, ngw, lane, q_s, kn_s, vn_s, n_chunks);
+            prof.sub(PH_ATT_O, 1);
             if (n_chunks > 1) {
                 grid_sync(gb);
                 prof.mark(PH_ATT_O);
                 outer_attention_combine(p, B, n_chunks, gw, ngw, lane);
+                prefetch_rows<false>(pre, w.o, H, H, gwv, lane, pol_stream);
                 grid_sync(gb);
                 prof.mark(PH_CMB_O);
             } else {
+                prefetch_rows<false>(pre, w.o, H, H, gwv, lane, pol_stream);
                 grid_sync(gb);
                 prof.mark(PH_ATT_O);
             }
             // ---- o_proj + residual
             if (warp < B) copy_row_from_global(xs + (size_t)warp * H, p.attn + (size_t)warp * H, H, lane);
             __syncthreads();
-            gemv_pairs<BM, false>(xs, H, w.o, H, H, B, p.x, H, p.h, H, gw, ngw, lane, pre, pol_stream);
+            prof.sub(PH_OPROJ_O, 0);
+            gemv_pairs<BM, false>(xs, H, w.o, H, H, B, p.x, H, p.h, H, gwv, ngwv, lane, pre, pol_stream);
+            prof.sub(PH_OPROJ_O, 1);
             // ---- norm + gate|up + SwiGLU
-            prefetch_rows<true>(pre, w.gu, H, d.I_outer, gw, lane, pol_stream);
+            prefetch_rows<true>(pre, w.gu, H, d.I_outer, gwv, lane, pol_stream);
             grid_sync(gb);
             prof.mark(PH_OPROJ_O);
             if (warp < B) {
@@ -628,15 +641,19 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
                 norm_row_inplace(xs + (size_t)warp * H, H, w.ln2, d.eps, lane);
             }
             __syncthreads();
-            gemv_pairs<BM, true>(xs, H, w.gu, H, d.I_outer, B, nullptr, 0, p.act, d.I_outer, gw, ngw, lane, pre, pol_stream);
+            prof.sub(PH_GU_O, 0);
+            gemv_pairs<BM, true>(xs, H, w.gu, H, d.I_outer, B, nullptr, 0, p.act, d.I_outer, gwv, ngwv, lane, pre, pol_stream);
+            prof.sub(PH_GU_O, 1);
             // ---- down + residual
-            prefetch_rows<false>(pre, w.down, d.I_outer, H, gw, lane, pol_stream);
+            prefetch_rows<false>(pre, w.down, d.I_outer, H, gwv, lane, pol_stream);
             grid_sync(gb);
             prof.mark(PH_GU_O);
             __syncthreads();
             if (warp < B) copy_row_from_global(xs + (size_t)warp * d.I_outer, p.act + (size_t)warp * d.I_outer, d.I_outer, lane);
             __syncthreads();
-            gemv_pairs<BM, false>(xs, d.I_outer, w.down, d.I_outer, H, B, p.h, H, p.x, H, gw, ngw, lane, pre, pol_stream);
+            prof.sub(PH_DOWN_O, 0);
+            gemv_pairs<BM, false>(xs, d.I_outer, w.down, d.I_outer, H, B, p.h, H, p.x, H, gwv, ngwv, lane, pre, pol_stream);
+            prof.sub(PH_DOWN_O, 1);
         }
         // =============================== token-level stack: up to 8 steps =========================================
         int n_steps = PD_T;
@@ -644,7 +661,7 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
             if (i >= n_steps) break;
             for (int l = 0; l < d.n_inner; l++) {
                 const LayerW w = layer_w(d.inner_w, l);
-                prefetch_rows<false>(pre, w.qkv, H, 3 * H, gw, lane, pol_keep);
+                prefetch_rows<false>(pre, w.qkv, H, 3 * H, gwv, lane, pol_keep);
                 grid_sync(gb);
                 prof.mark(l > 0 ? PH_DOWN_I : (i > 0 ? PH_SAMPLE : PH_DOWN_O));
                 if (i == 1 && l == 0) {
@@ -684,17 +701,22 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
                     norm_row_inplace(row, H, w.ln1, d.eps, lane);
                 }
                 __syncthreads();
-                gemv_pairs<BM, false>(xs, H, w.qkv, H, 3 * H, B, nullptr, 0, p.qkv, 3 * H, gw, ngw, lane, pre, pol_keep);
-                prefetch_rows<false>(pre, w.o, H, H, gw, lane, pol_keep);
+                prof.sub(PH_QKV_I, 0);
+                gemv_pairs<BM, false>(xs, H, w.qkv, H, 3 * H, B, nullptr, 0, p.qkv, 3 * H, gwv, ngwv, lane, pre, pol_keep);
+                prof.sub(PH_QKV_I, 1);
                 grid_sync(gb);
                 prof.mark(PH_QKV_I);
                 inner_attention(p, l, i, B, gw, ngw, lane);
+                prof.sub(PH_ATT_I, 1);
+                prefetch_rows<false>(pre, w.o, H, H, gwv, lane, pol_keep);
                 grid_sync(gb);
                 prof.mark(PH_ATT_I);
                 if (warp < B) copy_row_from_global(xs + (size_t)warp * H, p.attn + (size_t)warp * H, H, lane);
                 __syncthreads();
-                gemv_pairs<BM, false>(xs, H, w.o, H, H, B, p.x2, H, p.h2, H, gw, ngw, lane, pre, pol_keep);
-                prefetch_rows<true>(pre, w.gu, H, d.I_inner, gw, lane, pol_keep);
+                prof.sub(PH_OPROJ_I, 0);
+                gemv_pairs<BM, false>(xs, H, w.o, H, H, B, p.x2, H, p.h2, H, gwv, ngwv, lane, pre, pol_keep);
+                prof.sub(PH_OPROJ_I, 1);
+                prefetch_rows<true>(pre, w.gu, H, d.I_inner, gwv, lane, pol_keep);
                 grid_sync(gb);
                 prof.mark(PH_OPROJ_I);
                 if (warp < B) {
@@ -703,16 +725,20 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
                     norm_row_inplace(xs + (size_t)warp * H, H, w.ln2, d.eps, lane);
                 }
                 __syncthreads();
-                gemv_pairs<BM, true>(xs, H, w.gu, H, d.I_inner, B, nullptr, 0, p.act, d.I_inner, gw, ngw, lane, pre, pol_keep);
-                prefetch_rows<false>(pre, w.down, d.I_inner, H, gw, lane, pol_keep);
+                prof.sub(PH_GU_I, 0);
+                gemv_pairs<BM, true>(xs, H, w.gu, H, d.I_inner, B, nullptr, 0, p.act, d.I_inner, gwv, ngwv, lane, pre, pol_keep);
+                prof.sub(PH_GU_I, 1);
+                prefetch_rows<false>(pre, w.down, d.I_inner, H, gwv, lane, pol_keep);
                 grid_sync(gb);
                 prof.mark(PH_GU_I);
                 if (warp < B) copy_row_from_global(xs + (size_t)warp * d.I_inner, p.act + (size_t)warp * d.I_inner, d.I_inner, lane);
                 __syncthreads();
-                gemv_pairs<BM, false>(xs, d.I_inner, w.down, d.I_inner, H, B, p.h2, H, p.x2, H, gw, ngw, lane, pre, pol_keep);
+                prof.sub(PH_DOWN_I, 0);
+                gemv_pairs<BM, false>(xs, d.I_inner, w.down, d.I_inner, H, B, p.h2, H, p.x2, H, gwv, ngwv, lane, pre, pol_keep);
+                prof.sub(PH_DOWN_I, 1);
             }
             // ---- final norm + lm_head
-            prefetch_rows<false>(pre, d.lm_head, H, d.V, gw, lane, pol_keep);
+            prefetch_rows<false>(pre, d.lm_head, H, d.V, gwv, lane, pol_keep);
             grid_sync(gb);
             prof.mark(PH_DOWN_I);
             if (warp < B) {
@@ -721,7 +747,9 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
                 norm_row_inplace(xs + (size_t)warp * H, H, d.inner_norm, d.eps, lane);
             }
             __syncthreads();
-            gemv_pairs<BM, false>(xs, H, d.lm_head, H, d.V, B, nullptr, 0, p.logits, d.pitch, gw, ngw, lane, pre, pol_keep);
+            prof.sub(PH_LMHEAD, 0);
+            gemv_pairs<BM, false>(xs, H, d.lm_head, H, d.V, B, nullptr, 0, p.logits, d.pitch, gwv, ngwv, lane, pre, pol_keep);
+            prof.sub(PH_LMHEAD, 1);
             // ---- sample (one CTA per row): temperature softmax, grammar range, top-p / top-k, draw
             grid_sync(gb);
             prof.mark(PH_LMHEAD);
@@ -732,6 +760,7 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
                 const int id = sample_row(p, b, i, ev0, u, s_p, s_i, s_cnt, s_red);
                 if (threadIdx.x == 0) p.ev_t[(size_t)i * B + b] = id;
             }
+            prof.sub(PH_SAMPLE, 1);
         }
         // =============================== commit the event ========================================================
         grid_sync(gb);                                   // every row's tokens are visible
@@ -825,7 +854,7 @@ extern "C" int b200_decode_events(const b200_decode_desc* desc, int n_events, vo
     if (p.k_max < d.H) p.k_max = d.H;
     B200_CUDA(cudaMemsetAsync(p.bar, 0, 256, stream), "decode_events: barrier reset");
     const int bm = d.batch <= 1 ? 1 : d.batch <= 2 ? 2 : d.batch <= 4 ? 4 : d.batch <= 8 ? 8 : 16;
-    const size_t smem = (size_t)bm * p.k_max * 2 + (size_t)smp::SMP_MAXV * 8 + (PD_THREADS + 8) * 4 + 2 * PD_WARPS * 4 +
+    const size_t smem = (size_t)bm * p.k_max * 2 + (size_t)smp::SMP_MAXV * 8 + (PD_THREADS + 8) * 4 + 64 * 4 +
                         PD_WARPS * 64 * (4 + 2 + 2) + (size_t)bm * PD_T * 4 + 64;
     void* args[] = {(void*)&p};
     const void* fn = nullptr;

@@ -310,7 +310,7 @@ class GraphGenerator:
         d.temp, d.top_p, d.top_k, d.batch = self.temp, self.top_p, max(1, self.top_k), self.B
         self.prof = None
         if __import__("os").environ.get("B200_DECODE_PROFILE"):
-            self.prof = torch.zeros(64, dtype=torch.int64, device=dev)
+            self.prof = torch.zeros(128, dtype=torch.int64, device=dev)
             d.prof = self.prof.data_ptr()
         nbytes = lib.load().b200_decode_events_workspace_bytes(ctypes.byref(d))
         ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)

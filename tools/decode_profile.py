@@ -41,14 +41,15 @@ def main():
     dt = time.perf_counter() - t0
     prof = gg.prof.cpu().tolist()
     tot = sum(prof[:14])
-    mhz = torch.cuda.clock_rate() / 1e3 if hasattr(torch.cuda, "clock_rate") else 1900.0
+    mhz = 1900.0        # nominal SM clock under this light load (sm_max 1965 MHz); cycles are exact, microseconds approximate
     print(f"batch {B}, {n_new} events: {1e3 * dt / n_new:.3f} ms/event, {B * n_new / dt:.0f} events/s; SM clock {mhz:.0f} MHz (assumed for us)")
-    print(f"{'phase':18s} {'calls/event':>11s} {'cycles/call':>11s} {'us/call':>8s} {'us/event':>9s} {'share':>6s}")
+    print(f"{'phase':18s} {'calls/event':>11s} {'cycles/call':>11s} {'stage':>7s} {'work':>7s} {'barrier':>8s} {'us/call':>8s} {'us/event':>9s} {'share':>6s}")
     for i, n in enumerate(NAMES):
         c, k = prof[i], prof[32 + i]
         if k == 0:
             continue
-        print(f"{n:18s} {k / n_new:11.1f} {c / k:11.0f} {c / k / mhz:8.2f} {c / n_new / mhz:9.1f} {c / tot:6.1%}")
+        st, wk = prof[64 + 2 * i] / k, prof[64 + 2 * i + 1] / k
+        print(f"{n:18s} {k / n_new:11.1f} {c / k:11.0f} {st:7.0f} {wk:7.0f} {c / k - st - wk:8.0f} {c / k / mhz:8.2f} {c / n_new / mhz:9.1f} {c / tot:6.1%}")
     print(f"{'total':18s} {sum(prof[32:46]) / n_new:11.1f} {'':11s} {'':8s} {tot / n_new / mhz:9.1f}")
 
 
