@@ -72,6 +72,17 @@ __device__ __forceinline__ float warp_max(float v) {
 // round-to-nearest-even fp32 -> bf16 -> fp32 (a "rounding point" of the reference's eager bf16 path)
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+// silu(x) = x * sigmoid(x) with the SFU approximations (ex2.approx, rcp.approx: relative error ~2^-22, far below the bf16
+// rounding that follows).  ONE definition for every kernel that forms SwiGLU (stand-alone kernels, GEMM epilogue, decode
+// projections), so that fused and unfused paths stay bit-identical to each other.
+__device__ __forceinline__ float sigmoid_f(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-x * 1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+    return r;
+}
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
+
 struct __align__(16) bf16x8 {
     bf162 v[4];
 };

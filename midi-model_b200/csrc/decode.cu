@@ -173,7 +173,7 @@ gemv_fused_kernel(const bf16* __restrict__ x, const long long* __restrict__ ids,
                 float o = acc[b];
                 if (swiglu) {
                     const float g = bf16_round(o), u = bf16_round(acc2[b]);
-                    o = bf16_round(g / (1.f + __expf(-g))) * u;
+                    o = bf16_round(silu_f(g)) * u;
                 }
                 if (res) o = bf16_round(o) + __bfloat162float(res[(size_t)b * ldr + n]);
                 y[(size_t)b * ldy + n] = __float2bfloat16_rn(o);

@@ -235,7 +235,7 @@ __device__ __forceinline__ void gemv_pairs(const bf16* xs, int K, const bf16* __
         }
         if (SWIGLU && lane < B) {
             const float g = bf16_round(my0), u = bf16_round(my1);
-            y[(size_t)lane * ldy + r0] = __float2bfloat16_rn(bf16_round(g / (1.f + __expf(-g))) * u);
+            y[(size_t)lane * ldy + r0] = __float2bfloat16_rn(bf16_round(silu_f(g)) * u);
         }
         if (!SWIGLU && lane < B) {
             const int b = lane;
@@ -333,33 +333,45 @@ __device__ __noinline__ void outer_attention(const PD& p, int layer, int pos, in
             if (lane < 8) *reinterpret_cast<uint4*>(kpool + o + lane * 8) = *reinterpret_cast<const uint4*>(kn_s + lane * 8);
             else if (lane < 16) *reinterpret_cast<uint4*>(vpool + o + (lane - 8) * 8) = *reinterpret_cast<const uint4*>(vn_s + (lane - 8) * 8);
         }
-        float m_run = -INFINITY, l_run = 0.f, a0 = 0.f, a1 = 0.f;
+        // Scores: lane <-> key (the lane reads its key's 128-byte row).  P.V: 8 lanes per key, each with 8 of the 64 dims as one
+        // 16-byte load -- key j = (lane >> 3) + 4 i, dims 8 (lane & 7) .. + 7 -- so a 32-key block is 8 + 8 vector loads per
+        // lane, all issued together (one memory latency per block), then two shuffle steps fold the four key groups.
+        const int kg = lane >> 3, dl = lane & 7;
+        float m_run = -INFINITY, l_run = 0.f;
+        float av[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int tb = t0; tb < t1; tb += 32) {
             const size_t base = kv_base(d.block_table, d.max_pages, d.page, nh, D, b, h, tb);   // 32-aligned: one page
             const int t = tb + lane;
+            uint4 kr[8], vr[8];
+#pragma unroll
+            for (int dv = 0; dv < 8; dv++) {
+                kr[dv] = make_uint4(0, 0, 0, 0);
+                if (t < t1 && t != pos) kr[dv] = ldcg16(kpool + base + (size_t)lane * D + dv * 8);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int tj = tb + kg + 4 * i;
+                vr[i] = make_uint4(0, 0, 0, 0);
+                if (tj < t1 && tj != pos) vr[i] = ldcg16(vpool + base + (size_t)(kg + 4 * i) * D + dl * 8);
+            }
+            if (owns_new && pos >= tb && pos < tb + 32) {      // the new position's key / value come from shared memory
+                if (t == pos) {
+#pragma unroll
+                    for (int dv = 0; dv < 8; dv++) kr[dv] = *reinterpret_cast<const uint4*>(kn_s + dv * 8);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    if (tb + kg + 4 * i == pos) vr[i] = *reinterpret_cast<const uint4*>(vn_s + dl * 8);
+            }
             float s = -INFINITY;
             if (t < t1) {
                 float acc = 0.f;
-                if (t == pos) {
 #pragma unroll
-                    for (int dv = 0; dv < 8; dv++) {
-                        float kf[8];
-                        unpack8(*reinterpret_cast<const uint4*>(kn_s + dv * 8), kf);
+                for (int dv = 0; dv < 8; dv++) {
+                    float kf[8];
+                    unpack8(kr[dv], kf);
 #pragma unroll
-                        for (int j = 0; j < 8; j++) acc = fmaf(kf[j], q_s[dv * 8 + j], acc);
-                    }
-                } else {
-                    const bf16* kp = kpool + base + (size_t)lane * D;
-                    uint4 kr[8];
-#pragma unroll
-                    for (int dv = 0; dv < 8; dv++) kr[dv] = ldcg16(kp + dv * 8);
-#pragma unroll
-                    for (int dv = 0; dv < 8; dv++) {
-                        float kf[8];
-                        unpack8(kr[dv], kf);
-#pragma unroll
-                        for (int j = 0; j < 8; j++) acc = fmaf(kf[j], q_s[dv * 8 + j], acc);
-                    }
+                    for (int j = 0; j < 8; j++) acc = fmaf(kf[j], q_s[dv * 8 + j], acc);
                 }
                 s = acc * scale;
             }
@@ -367,41 +379,38 @@ __device__ __noinline__ void outer_attention(const PD& p, int layer, int pos, in
             const float pr = (t < t1) ? __expf(s - m_new) : 0.f;
             const float corr = __expf(m_run - m_new);          // 0 on the first block (m_run = -inf)
             l_run = l_run * corr + warp_sum(pr);
-            a0 *= corr;
-            a1 *= corr;
             m_run = m_new;
             const float pb = bf16_round(pr);                    // P rounded to bf16 before P.V (flash semantics)
-            const int nk = min(32, t1 - tb);
-            const bf16* vp = vpool + base + 2 * lane;
-            // the 32 value rows of the block (4 bytes per lane each) in flight together, then the FMAs
-            unsigned int vraw[32];
 #pragma unroll
-            for (int j = 0; j < 32; j++)
-                if (j < nk && tb + j != pos) vraw[j] = __ldcg(reinterpret_cast<const unsigned int*>(vp + (size_t)j * D));
-            if (owns_new && pos >= tb && pos < tb + 32) {
-                const unsigned int mine = *reinterpret_cast<const unsigned int*>(vn_s + 2 * lane);
+            for (int j = 0; j < 8; j++) av[j] *= corr;
 #pragma unroll
-                for (int j = 0; j < 32; j++)
-                    if (tb + j == pos) vraw[j] = mine;
-            }
+            for (int i = 0; i < 8; i++) {
+                const float pj = __shfl_sync(0xffffffffu, pb, kg + 4 * i);     // 0 for keys past the chunk
+                float vf[8];
+                unpack8(vr[i], vf);
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                if (j < nk) {
-                    const float pj = __shfl_sync(0xffffffffu, pb, j);
-                    const float2 vf = __bfloat1622float2(*reinterpret_cast<const bf162*>(&vraw[j]));
-                    a0 = fmaf(pj, vf.x, a0);
-                    a1 = fmaf(pj, vf.y, a1);
-                }
+                for (int j = 0; j < 8; j++) av[j] = fmaf(pj, vf[j], av[j]);
             }
         }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            av[j] += __shfl_xor_sync(0xffffffffu, av[j], 8);
+            av[j] += __shfl_xor_sync(0xffffffffu, av[j], 16);
+        }
         if (n_chunks == 1) {
-            const float inv = 1.f / l_run;
-            *reinterpret_cast<bf162*>(p.attn + (size_t)b * H + h * D + 2 * lane) = __floats2bfloat162_rn(a0 * inv, a1 * inv);
+            if (kg == 0) {
+                const float inv = 1.f / l_run;
+#pragma unroll
+                for (int j = 0; j < 8; j++) av[j] *= inv;
+                *reinterpret_cast<uint4*>(p.attn + (size_t)b * H + h * D + dl * 8) = pack8(av);
+            }
         } else {
             float* po = p.partial + ((size_t)bh * PD_MAXC + c) * (D + 2);
             if (lane == 0) { po[0] = m_run; po[1] = l_run; }
-            po[2 + 2 * lane] = a0;
-            po[3 + 2 * lane] = a1;
+            if (kg == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) po[2 + dl * 8 + j] = av[j];
+            }
         }
         __syncwarp();
     }

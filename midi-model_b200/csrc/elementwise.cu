@@ -455,7 +455,7 @@ __global__ void rope_kernel(bf16* __restrict__ qkv, const bf16* __restrict__ cos
 // ---------------------------------------------------------------------------
 // SwiGLU on packed [rows, 2*I] = [gate | up]
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return sigmoid_f(x); }
 
 // act = bf16( bf16(silu(g)) * u )   (two roundings, A.6)
 __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict__ act, size_t rows, int I) {
@@ -467,7 +467,7 @@ __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict_
         unpack8(ld_nc16(gu + r * 2 * I + c), g);
         unpack8(ld_nc16(gu + r * 2 * I + I + c), u);
 #pragma unroll
-        for (int j = 0; j < 8; j++) o[j] = bf16_round(g[j] * sigmoidf_(g[j])) * u[j];
+        for (int j = 0; j < 8; j++) o[j] = bf16_round(silu_f(g[j])) * u[j];
         *reinterpret_cast<uint4*>(act + r * I + c) = pack8(o);
     }
 }

@@ -18,8 +18,9 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
 constexpr int EPI_WARP0 = 2;
+// threads = TMA warp + MMA warp + EG groups of four epilogue warps (a group covers the 128 TMEM lanes once)
+__host__ __device__ constexpr int num_threads(int eg) { return 64 + 128 * eg; }
 
 enum { EPI_STORE = 0, EPI_RESIDUAL = 1, EPI_PARTIAL_F32 = 2, EPI_ROPE = 3, EPI_SWIGLU = 4 };
 
@@ -87,8 +88,8 @@ __device__ __forceinline__ WorkItem decode_item(const GemmParams& p, int item) {
     return w;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BLOCK_N, bool A_MN, bool B_MN, int EG>
+__global__ void __launch_bounds__(num_threads(EG), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
     using L = SmemLayout<BLOCK_N>;
@@ -117,7 +118,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         for (int s = 0; s < 2; s++) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 4);
+            mbar_init(&tempty_bar[s], 4 * EG);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -202,7 +203,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     } else {
         // ===================== epilogue warps =====================
         const int quarter = warp & 3;               // TMEM lane quarter this warp may access
-        int acc = 0, out_buf = 0;
+        // EG == 2: two groups of four epilogue warps split the tile's 64-column boxes between them (group g takes boxes
+        // g, g + 2, ...; for SwiGLU feature half g), each group with its own staging box, named barrier and store leader:
+        // twice the threads for the conversions / SFU work of the fused epilogues, and the two groups' TMA stores overlap.
+        const int grp = (warp - EPI_WARP0) >> 2;
+        int acc = 0, out_buf = (EG == 2) ? grp : 0;
         uint32_t acc_phase = 0;
         for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
             const WorkItem wi = decode_item(p, item);
@@ -215,29 +220,38 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // ---- staged output: the thread's 64 consecutive columns (8 x 16 B) of row r_t go into a 128B-swizzled
             // [128 x 64] staging box, one TMA store per box (see the plain-store branch below for the why)
             const int r_t = quarter * 32 + lane;
-            const bool leader = (warp == EPI_WARP0 && lane == 0);
-            auto box_row = [&]() -> uint8_t* { return out_stage + out_buf * (BLOCK_M * 128) + r_t * 128; };
+            const bool leader = (warp == EPI_WARP0 + 4 * grp && lane == 0);
+            const int bar_id = 1 + grp;
+            auto box_row = [&]() -> uint8_t* {
+                if (EG == 2) {
+                    // one box per group: the previous store of this group must have finished reading it
+                    if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                }
+                return out_stage + out_buf * (BLOCK_M * 128) + r_t * 128;
+            };
             auto box_put = [&](uint8_t* dst, int chunk, const float* f8) {
                 *reinterpret_cast<uint4*>(dst + ((chunk ^ (r_t & 7)) << 4)) = pack8(f8);
             };
             auto box_send = [&](const CUtensorMap* tm, int gcol) {
                 fence_proxy_async_smem();
-                // the previous box's store has finished reading the other buffer before anyone writes it again
-                if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                // EG == 1: two boxes ping-pong; the previous box's store has finished reading the other buffer before anyone
+                // writes it again
+                if (EG == 1 && leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                 if (leader) {
                     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                                  ::"l"(tm), "r"(smem_u32(out_stage + out_buf * (BLOCK_M * 128))), "r"(gcol), "r"(m_blk * BLOCK_M)
                                  : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-                out_buf ^= 1;
+                if (EG == 1) out_buf ^= 1;
             };
             if (wi.tail >= 0) {
                 // K-slice of a tail tile: fp32 partial, tile-local layout [128][BLOCK_N]
                 float* dstp = p.tail_ws + ((size_t)(wi.tail * p.tail_splits + split) * BLOCK_M + r_t) * BLOCK_N;
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N / 32; c++) {
+                for (int c = grp; c < BLOCK_N / 32; c += EG) {
                     uint32_t r[32];
                     tmem_ld32(taddr + c * 32, r);
                     tmem_ld_wait();
@@ -250,7 +264,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 // gate, up (both kept for the backward) and act = bf16(silu(gate)) * up.  TMEM is re-read for the act
                 // pass instead of holding 128 values per thread in registers.
 #pragma unroll 1
-                for (int fb = 0; fb < 2; fb++) {
+                for (int fb = grp; fb < 2; fb += EG) {
                     const int f0 = n_blk * 128 + fb * 64;
                     if (f0 >= p.swiglu_I) break;
 #pragma unroll 1
@@ -285,7 +299,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             for (int q = 0; q < 8; q++) {
                                 const float g = bf16_round(__uint_as_float(r1[8 * v + q]));
                                 const float u = bf16_round(__uint_as_float(r2[8 * v + q]));
-                                a[q] = bf16_round(g / (1.f + __expf(-g))) * u;
+                                a[q] = bf16_round(silu_f(g)) * u;
                             }
                             box_put(dst, hc * 4 + v, a);
                         }
@@ -299,7 +313,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const bf16* cp = p.rope_cos + (size_t)pos * 32;
                 const bf16* sp = p.rope_sin + (size_t)pos * 32;
 #pragma unroll 1
-                for (int bx = 0; bx < BLOCK_N / 64; bx++) {
+                for (int bx = grp; bx < BLOCK_N / 64; bx += EG) {
                     const int col0 = n_blk * BLOCK_N + bx * 64;
                     if (col0 >= p.N) break;
                     uint8_t* dst = box_row();
@@ -339,7 +353,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 // features, [128,256) the matching up features.  g, u = bf16(acc) are stored (backward needs them) and
                 // act = bf16(bf16(silu(g)) * u) -- same rounding points as the stand-alone kernel.
 #pragma unroll 1
-                for (int c = 0; c < 4; c++) {
+                for (int c = grp; c < 4; c += EG) {
                     uint32_t r1[32], r2[32];
                     tmem_ld32(taddr + c * 32, r1);
                     tmem_ld32(taddr + 128 + c * 32, r2);
@@ -356,7 +370,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             for (int q = 0; q < 8; q++) {
                                 g[q] = bf16_round(__uint_as_float(r1[8 * v + q]));
                                 u[q] = bf16_round(__uint_as_float(r2[8 * v + q]));
-                                a[q] = bf16_round(g[q] / (1.f + __expf(-g[q]))) * u[q];
+                                a[q] = bf16_round(silu_f(g[q])) * u[q];
                             }
                             *reinterpret_cast<uint4*>(dg + v * 8) = pack8(g);
                             *reinterpret_cast<uint4*>(du + v * 8) = pack8(u);
@@ -371,7 +385,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int cph = half >> 5;                      // 32-column chunks per half head (1 for d=64, 4 for d=256)
                 const int pos = row_ok ? row % p.rope_S : 0;
 #pragma unroll 1
-                for (int c0 = 0; c0 < BLOCK_N / 32; c0 += 2 * cph) {
+                for (int c0 = grp * 2 * cph; c0 < BLOCK_N / 32; c0 += EG * 2 * cph) {
 #pragma unroll 1
                     for (int j = 0; j < cph; j++) {
                         uint32_t r1[32], r2[32];
@@ -418,9 +432,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 // made the epilogue longer than a K=1024 main loop (tensor pipe 64% busy); instead the tile goes
                 // through two 128B-swizzled [128 x 64] staging boxes and leaves with one TMA store per box.
 #pragma unroll 1
-                for (int bx = 0; bx < BLOCK_N / 64; bx++) {
+                for (int bx = grp; bx < BLOCK_N / 64; bx += EG) {
                     const int col0 = n_blk * BLOCK_N + bx * 64;
-                    if (col0 >= p.N) break;                                   // uniform
+                    if (col0 >= p.N) break;                                   // uniform within the group
                     uint8_t* dst = box_row();
 #pragma unroll
                     for (int hc = 0; hc < 2; hc++) {
@@ -439,7 +453,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
             } else
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; c++) {
+            for (int c = grp; c < BLOCK_N / 32; c += EG) {
                 uint32_t r[32];
                 tmem_ld32(taddr + c * 32, r);
                 tmem_ld_wait();
@@ -480,7 +494,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (p.tma_store && warp == EPI_WARP0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (p.tma_store && ((warp - EPI_WARP0) & 3) == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 
     tc_fence_before();
@@ -534,11 +548,11 @@ __global__ void tail_reduce_kernel(const float* __restrict__ ws, bf16* __restric
     }
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, int EG>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmD, const GemmParams& p,
            cudaStream_t stream) {
     using L = SmemLayout<BLOCK_N>;
-    auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN>;
+    auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, EG>;
     static bool configured = false;
     if (!configured) {
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL), "gemm smem attr");
@@ -546,7 +560,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
     }
     const int items = p.total_items;
     const int grid = items < b200_num_sms() ? items : b200_num_sms();
-    kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, tmC, tmD, p);
+    kern<<<grid, num_threads(EG), L::TOTAL, stream>>>(tmA, tmB, tmC, tmD, p);
     B200_CHECK_LAUNCH("gemm_tcgen05");
     return B200_OK;
 }
@@ -860,15 +874,25 @@ static int gemm_impl(const void* A, const void* B, void* C, const void* R, int M
     if (rc) return rc;
     if (!p.tma_store) { tmC = tmA; tmD = tmA; }      // unused by the kernel, but must be valid maps
 
-#define B200_DISPATCH(BN)                                                                   \
+    // epilogue warp groups: one (4 warps) for the plain epilogues, two (8 warps) for the fused RoPE / SwiGLU epilogues whose
+    // conversions and SFU work would otherwise outlast a K = 1024 main loop (B200_GEMM_EG_PLAIN / B200_GEMM_EG_FUSED override)
+    static int eg_plain = -1, eg_fused = -1;
+    if (eg_plain < 0) {
+        const char* e1 = getenv("B200_GEMM_EG_PLAIN");
+        const char* e2 = getenv("B200_GEMM_EG_FUSED");
+        eg_plain = (e1 && e1[0] == '2') ? 2 : 1;
+        eg_fused = (e2 && e2[0] == '1') ? 1 : 2;
+    }
+    const int eg = (p.epilogue == EPI_ROPE || p.epilogue == EPI_SWIGLU) ? eg_fused : eg_plain;
+#define B200_DISPATCH(BN, EGV)                                                                   \
     do {                                                                                    \
-        if (!a_mn_major && !b_mn_major) rc = launch<BN, false, false>(tmA, tmB, tmC, tmD, p, stream);  \
-        else if (!a_mn_major && b_mn_major) rc = launch<BN, false, true>(tmA, tmB, tmC, tmD, p, stream); \
-        else if (a_mn_major && b_mn_major) rc = launch<BN, true, true>(tmA, tmB, tmC, tmD, p, stream);  \
-        else rc = launch<BN, true, false>(tmA, tmB, tmC, tmD, p, stream);                              \
+        if (!a_mn_major && !b_mn_major) rc = launch<BN, false, false, EGV>(tmA, tmB, tmC, tmD, p, stream);  \
+        else if (!a_mn_major && b_mn_major) rc = launch<BN, false, true, EGV>(tmA, tmB, tmC, tmD, p, stream); \
+        else if (a_mn_major && b_mn_major) rc = launch<BN, true, true, EGV>(tmA, tmB, tmC, tmD, p, stream);  \
+        else rc = launch<BN, true, false, EGV>(tmA, tmB, tmC, tmD, p, stream);                              \
     } while (0)
-    if (block_n == 256) B200_DISPATCH(256);
-    else B200_DISPATCH(128);
+    if (block_n == 256) { if (eg == 2) B200_DISPATCH(256, 2); else B200_DISPATCH(256, 1); }
+    else { if (eg == 2) B200_DISPATCH(128, 2); else B200_DISPATCH(128, 1); }
 #undef B200_DISPATCH
     if (rc) return rc;
 

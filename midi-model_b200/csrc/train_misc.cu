@@ -71,45 +71,50 @@ ce_fwd_kernel(const bf16* __restrict__ logits, const long long* __restrict__ tar
 // copy bandwidth (profiles/r2_bench_1gpu_start.json).
 constexpr int CEW_WARPS = 4;
 template <int VPL>
-__global__ void __launch_bounds__(CEW_WARPS * 32)
+__global__ void __launch_bounds__(CEW_WARPS * 32, 8)
 ce_fwd_warp_kernel(const bf16* __restrict__ logits, const long long* __restrict__ targets, float* __restrict__ lse_out,
                    float* __restrict__ row_loss, long long R, int V, int ld, long long ignore_index) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nvec = (V + 7) / 8;
+    const int tail = V - (nvec - 1) * 8;              // valid elements of the last vector (1..8)
+    constexpr int CH = 8;                             // vectors per lane in flight at a time (32 registers)
     for (long long r = (long long)blockIdx.x * CEW_WARPS + warp; r < R; r += (long long)gridDim.x * CEW_WARPS) {
         const bf16* row = logits + (size_t)r * ld;
-        uint4 raw[VPL];
+        float m = -INFINITY, s = 0.f;                 // running max / sum of exp(x - m) of this lane (online softmax)
 #pragma unroll
-        for (int k = 0; k < VPL; k++) {
-            const int v = lane + 32 * k;
-            if (v < nvec) raw[k] = ld_nc16(row + v * 8);
-        }
-        float mx = -INFINITY;
+        for (int k0 = 0; k0 < VPL; k0 += CH) {
+            uint4 raw[CH];
 #pragma unroll
-        for (int k = 0; k < VPL; k++) {
-            const int v = lane + 32 * k;
-            if (v < nvec) {
+            for (int k = 0; k < CH; k++) {
+                const int v = lane + 32 * (k0 + k);
+                raw[k] = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);   // -inf: contributes nothing
+                if (k0 + k < VPL && v < nvec) raw[k] = ld_nc16(row + v * 8);
+                if (v == nvec - 1 && tail < 8) {      // pad columns of the pitched row do not belong to the vocabulary
+                    auto fix = [&](unsigned int w, int e0) -> unsigned int {
+                        if (e0 >= tail) w = (w & 0xFFFF0000u) | 0xFF80u;
+                        if (e0 + 1 >= tail) w = (w & 0x0000FFFFu) | 0xFF800000u;
+                        return w;
+                    };
+                    raw[k].x = fix(raw[k].x, 0); raw[k].y = fix(raw[k].y, 2); raw[k].z = fix(raw[k].z, 4); raw[k].w = fix(raw[k].w, 6);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < CH; k++) {
                 float f[8];
                 unpack8(raw[k], f);
+                float m8 = fmaxf(fmaxf(fmaxf(f[0], f[1]), fmaxf(f[2], f[3])), fmaxf(fmaxf(f[4], f[5]), fmaxf(f[6], f[7])));
+                if (m8 > m) {                         // (never taken with m8 = -inf)
+                    s *= __expf(m - m8);              // m = -inf: s is 0 and stays 0
+                    m = m8;
+                }
+                if (m > -INFINITY) {
 #pragma unroll
-                for (int j = 0; j < 8; j++)
-                    if (v * 8 + j < V) mx = fmaxf(mx, f[j]);
+                    for (int j = 0; j < 8; j++) s += __expf(f[j] - m);
+                }
             }
         }
-        mx = warp_max(mx);
-        float sum = 0.f;
-#pragma unroll
-        for (int k = 0; k < VPL; k++) {
-            const int v = lane + 32 * k;
-            if (v < nvec) {
-                float f[8];
-                unpack8(raw[k], f);
-#pragma unroll
-                for (int j = 0; j < 8; j++)
-                    if (v * 8 + j < V) sum += __expf(f[j] - mx);
-            }
-        }
-        sum = warp_sum(sum);
+        const float mx = warp_max(m);
+        const float sum = warp_sum(m > -INFINITY ? s * __expf(m - mx) : 0.f);
         if (lane == 0) {
             const float lse = mx + logf(sum);
             lse_out[r] = lse;
