@@ -29,11 +29,13 @@ BF16 = torch.bfloat16
 # the earlier per-thread stores).
 FUSE_ROPE = os.environ.get("B200_FUSE_ROPE", "1") != "0"
 FUSE_ROPE_FWD = os.environ.get("B200_FUSE_ROPE_FWD", "0") != "0"
-# SwiGLU formed in the epilogue of the gate|up GEMM (ops.linear_swiglu, bit-identical to GEMM + stand-alone kernel) exists
-# but is OFF by default: the heavier epilogue (2 MUFU ops per element, three output boxes per 64 features, on 4 epilogue
-# warps) outlasts the K=1024 main loop.  Measured A/B on one box with the TMA-staged epilogue: +1.5 ms/step; 8 epilogue
-# warps did not help (plain GEMMs got 6 % slower).  B200_FUSE_SWIGLU=1 enables it.
-FUSE_SWIGLU = os.environ.get("B200_FUSE_SWIGLU", "0") != "0"
+# SwiGLU formed in the epilogue of the gate|up GEMM (ops.linear_swiglu, bit-identical to GEMM + stand-alone kernel): ON.
+# Round 1 measured it slower (+1.5 ms/step: four epilogue warps doing an IEEE division and two SFU ops per element outlasted
+# the K=1024 main loop).  With two epilogue warp groups (8 warps, each group its own staging box and store leader) and
+# silu through ex2.approx / rcp.approx the fused GEMM costs +1.0 ms of GEMM time per step and removes the 1.5 ms/step
+# stand-alone kernel plus its 17.6 GB of traffic: 56.4 -> 54.8 ms/step on one box (profiles/r2_epilogue_ab.txt).
+# B200_FUSE_SWIGLU=0 restores GEMM + kernel.  (The fused RoPE epilogue stays off: neutral within box noise.)
+FUSE_SWIGLU = os.environ.get("B200_FUSE_SWIGLU", "1") != "0"
 # Weight-gradient GEMMs on a second stream: dW = dY^T X is off the backward's critical path, so it can run
 # under the HBM-bound kernels that follow on the main stream (SwiGLU / RMSNorm backward leave the tensor pipe idle, and an
 # elementwise CTA fits next to a GEMM CTA on an SM).  B200_WGRAD_STREAM=0 keeps everything on one stream.
