@@ -50,12 +50,13 @@ struct GemmParams {
 
 using namespace tc05;
 
-template <int BLOCK_N>
+// CG = CTAs per UMMA (1, or 2 = CTA pair: cta_group::2, M = 256 per MMA, each CTA stages its 128 rows of A and HALF of B)
+template <int BLOCK_N, int CG = 1>
 struct SmemLayout {
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
-    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;   // 16/32 KB
+    static constexpr int B_BYTES = (BLOCK_N / CG) * BLOCK_K * 2;   // 16/32 KB (half of it per CTA of a pair)
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+    static constexpr int STAGES = (CG == 2) ? 5 : ((BLOCK_N == 256) ? 4 : 6);
     static constexpr int OUT_BYTES = 2 * BLOCK_M * 64 * 2;  // two [128 rows x 128 B] staging boxes for the TMA-store epilogue
     static constexpr int BAR_BYTES = 1024;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES + 1024;   // +1024 for manual alignment
@@ -88,11 +89,16 @@ __device__ __forceinline__ WorkItem decode_item(const GemmParams& p, int item) {
     return w;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int EG>
+template <int BLOCK_N, bool A_MN, bool B_MN, int EG, int CG>
 __global__ void __launch_bounds__(num_threads(EG), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
-    using L = SmemLayout<BLOCK_N>;
+    using L = SmemLayout<BLOCK_N, CG>;
+    // CTA pair: this CTA's rank in its 2-CTA cluster (0 = leader: issues the MMAs, owns the full / tmem-empty barriers)
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const bool leader_cta = rank == 0;
+    const int first_item = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int item_stride = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     constexpr int STAGES = L::STAGES;
     constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;   // double-buffered accumulator (256 or 512 columns)
 
@@ -118,13 +124,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         for (int s = 0; s < 2; s++) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 4 * EG);
+            mbar_init(&tempty_bar[s], 4 * EG * CG);      // pair: the epilogue warps of BOTH CTAs release the leader's accumulator
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 1) {
+        if (CG == 2) tmem_alloc_pair(tmem_slot, TMEM_COLS);
+        else tmem_alloc(tmem_slot, TMEM_COLS);
+    }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();             // the peer's barriers exist before anything arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -135,32 +145,57 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+            for (int item = first_item; item < total_items; item += item_stride) {
                 const WorkItem wi = decode_item(p, item);
-                const int n_blk = wi.n_blk, m_blk = wi.m_blk, kb0 = wi.kb0, kb1 = wi.kb1;
+                const int n_blk = wi.n_blk, m_blk = wi.m_blk * CG + (int)rank, kb0 = wi.kb0, kb1 = wi.kb1;
                 for (int kb = kb0; kb < kb1; kb++) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sA = smem + stage * L::STAGE_BYTES;
                     uint8_t* sB = sA + L::A_BYTES;
-                    mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-                    if (!A_MN) {
-                        tma_load_2d(sA, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < BLOCK_M / 64; c++)
-                            tma_load_2d(sA + c * (BLOCK_K * 128), &tmA, &full_bar[stage], m_blk * BLOCK_M + c * 64, kb * BLOCK_K);
-                    }
-                    if (!B_MN) {
-                        if (BLOCK_N == 256 && p.epilogue == EPI_SWIGLU) {   // gate half | up half (tensor map box = 128 rows)
-                            tma_load_2d(sB, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * 128);
-                            tma_load_2d(sB + 128 * BLOCK_K * 2, &tmB, &full_bar[stage], kb * BLOCK_K, p.swiglu_I + n_blk * 128);
+                    if (CG == 1) {
+                        mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                        if (!A_MN) {
+                            tma_load_2d(sA, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
                         } else {
-                            tma_load_2d(sB, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+#pragma unroll
+                            for (int c = 0; c < BLOCK_M / 64; c++)
+                                tma_load_2d(sA + c * (BLOCK_K * 128), &tmA, &full_bar[stage], m_blk * BLOCK_M + c * 64, kb * BLOCK_K);
+                        }
+                        if (!B_MN) {
+                            if (BLOCK_N == 256 && p.epilogue == EPI_SWIGLU) {   // gate half | up half (tensor map box = 128 rows)
+                                tma_load_2d(sB, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * 128);
+                                tma_load_2d(sB + 128 * BLOCK_K * 2, &tmB, &full_bar[stage], kb * BLOCK_K, p.swiglu_I + n_blk * 128);
+                            } else {
+                                tma_load_2d(sB, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < BLOCK_N / 64; c++)
+                                tma_load_2d(sB + c * (BLOCK_K * 128), &tmB, &full_bar[stage], n_blk * BLOCK_N + c * 64, kb * BLOCK_K);
                         }
                     } else {
+                        // pair: both CTAs' loads are counted on the LEADER's full barrier (it alone waits on it); the leader
+                        // announces the bytes of both.  This CTA stages its own 128 rows of A and its half of B's N range.
+                        const uint32_t fb = map_to_cta(smem_u32(&full_bar[stage]), 0);
+                        if (leader_cta) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+                        if (!A_MN) {
+                            tma_load_2d_pair(sA, &tmA, fb, kb * BLOCK_K, m_blk * BLOCK_M);
+                        } else {
 #pragma unroll
-                        for (int c = 0; c < BLOCK_N / 64; c++)
-                            tma_load_2d(sB + c * (BLOCK_K * 128), &tmB, &full_bar[stage], n_blk * BLOCK_N + c * 64, kb * BLOCK_K);
+                            for (int c = 0; c < BLOCK_M / 64; c++)
+                                tma_load_2d_pair(sA + c * (BLOCK_K * 128), &tmA, fb, m_blk * BLOCK_M + c * 64, kb * BLOCK_K);
+                        }
+                        constexpr int HALF_N = BLOCK_N / 2;
+                        if (!B_MN) {
+                            if (p.epilogue == EPI_SWIGLU)      // leader: gate rows, peer: the matching up rows
+                                tma_load_2d_pair(sB, &tmB, fb, kb * BLOCK_K, (int)rank * p.swiglu_I + n_blk * 128);
+                            else
+                                tma_load_2d_pair(sB, &tmB, fb, kb * BLOCK_K, n_blk * BLOCK_N + (int)rank * HALF_N);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < HALF_N / 64; c++)
+                                tma_load_2d_pair(sB + c * (BLOCK_K * 128), &tmB, fb, n_blk * BLOCK_N + (int)rank * HALF_N + c * 64, kb * BLOCK_K);
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -168,13 +203,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, A_MN, B_MN);
+        if (lane == 0 && leader_cta) {
+            constexpr uint32_t idesc = make_idesc(BLOCK_M * CG, BLOCK_N, A_MN, B_MN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+            for (int item = first_item; item < total_items; item += item_stride) {
                 const WorkItem wi = decode_item(p, item);
                 const int kb0 = wi.kb0, kb1 = wi.kb1;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -191,12 +226,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                                     : make_smem_desc(sA + k * (UMMA_K * 2), 16, 1024);
                         const uint64_t bdesc = B_MN ? make_smem_desc(sB + k * (UMMA_K * 128), p.mn_lbo, p.mn_sbo)
                                                     : make_smem_desc(sB + k * (UMMA_K * 2), 16, 1024);
-                        umma_f16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        if (CG == 2) umma_f16_pair(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        else umma_f16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+                    if (CG == 2) umma_commit_pair(&empty_bar[stage]);   // frees the slot in BOTH CTAs
+                    else umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[acc]);          // accumulator ready for the epilogue
+                if (CG == 2) umma_commit_pair(&tfull_bar[acc]);   // accumulator halves ready for both CTAs' epilogues
+                else umma_commit(&tfull_bar[acc]);          // accumulator ready for the epilogue
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -209,9 +247,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int grp = (warp - EPI_WARP0) >> 2;
         int acc = 0, out_buf = (EG == 2) ? grp : 0;
         uint32_t acc_phase = 0;
-        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        for (int item = first_item; item < total_items; item += item_stride) {
             const WorkItem wi = decode_item(p, item);
-            const int split = wi.split, n_blk = wi.n_blk, m_blk = wi.m_blk;
+            const int split = wi.split, n_blk = wi.n_blk, m_blk = wi.m_blk * CG + (int)rank;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const int row = m_blk * BLOCK_M + quarter * 32 + lane;
@@ -491,7 +529,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+                if (CG == 1 || leader_cta) mbar_arrive(&tempty_bar[acc]);
+                else mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[acc]), 0));
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (p.tma_store && ((warp - EPI_WARP0) & 3) == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -499,9 +540,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();             // nobody leaves while the peer's MMAs / commits may still touch this CTA
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if (CG == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+        else tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -548,19 +591,38 @@ __global__ void tail_reduce_kernel(const float* __restrict__ ws, bf16* __restric
     }
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int EG>
+template <int BLOCK_N, bool A_MN, bool B_MN, int EG, int CG>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmD, const GemmParams& p,
            cudaStream_t stream) {
-    using L = SmemLayout<BLOCK_N>;
-    auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, EG>;
+    using L = SmemLayout<BLOCK_N, CG>;
+    auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, EG, CG>;
     static bool configured = false;
     if (!configured) {
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL), "gemm smem attr");
         configured = true;
     }
     const int items = p.total_items;
-    const int grid = items < b200_num_sms() ? items : b200_num_sms();
-    kern<<<grid, num_threads(EG), L::TOTAL, stream>>>(tmA, tmB, tmC, tmD, p);
+    if (CG == 1) {
+        const int grid = items < b200_num_sms() ? items : b200_num_sms();
+        kern<<<grid, num_threads(EG), L::TOTAL, stream>>>(tmA, tmB, tmC, tmD, p);
+    } else {
+        // CTA pairs: clusters of two CTAs (same TPC), one 256-row tile pair per cluster at a time
+        const int pairs = b200_num_sms() / 2;
+        const int grid = 2 * (items < pairs ? items : pairs);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(num_threads(EG));
+        cfg.dynamicSmemBytes = L::TOTAL;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        B200_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmD, p), "gemm pair launch");
+    }
     B200_CHECK_LAUNCH("gemm_tcgen05");
     return B200_OK;
 }
@@ -797,7 +859,15 @@ static int gemm_impl(const void* A, const void* B, void* C, const void* R, int M
     p.kb_per_split = (p.num_kb + splits - 1) / splits;
     splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;   // no empty splits
     p.splits = splits;
-    p.m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    // CTA pairs (cta_group::2, 256-row tile pairs) for the 256-wide tiles: halves the B-operand shared-memory traffic per
+    // MMA and the B bytes each CTA pulls through TMA.  B200_GEMM_CTA_PAIR=0 keeps one CTA per tile.
+    static int pair_ok = -1;
+    if (pair_ok < 0) {
+        const char* e = getenv("B200_GEMM_CTA_PAIR");
+        pair_ok = (e && e[0] == '0') ? 0 : 1;
+    }
+    const int cg = (pair_ok && block_n == 256 && M > BLOCK_M) ? 2 : 1;
+    p.m_tiles = (M + BLOCK_M * cg - 1) / (BLOCK_M * cg);
     p.n_tiles = (N + block_n - 1) / block_n;
     p.mn_lbo = BLOCK_K * 128;
     p.mn_sbo = 1024;
@@ -845,7 +915,7 @@ static int gemm_impl(const void* A, const void* B, void* C, const void* R, int M
     p.tail_tile0 = p.m_tiles * p.n_tiles;
     p.tail_splits = 1; p.tail_kb = p.num_kb; p.tail_ws = nullptr;
     int n_tail = 0;
-    if (p.epilogue == EPI_STORE && p.splits == 1 && !accumulate && workspace != nullptr) {
+    if (cg == 1 && p.epilogue == EPI_STORE && p.splits == 1 && !accumulate && workspace != nullptr) {
         const int tiles = p.m_tiles * p.n_tiles, sms = b200_num_sms();
         const int ts = plan_tail(tiles, p.num_kb, sms);
         const size_t need = (size_t)(tiles % sms) * ts * BLOCK_M * block_n * sizeof(float);
@@ -869,7 +939,7 @@ static int gemm_impl(const void* A, const void* B, void* C, const void* R, int M
     if (!a_mn_major) rc = tc05::make_tmap_2d(&tmA, A, K, M, lda, BLOCK_K, BLOCK_M);
     else             rc = tc05::make_tmap_2d(&tmA, A, M, K, lda, 64, BLOCK_K);
     if (rc) return rc;
-    if (!b_mn_major) rc = tc05::make_tmap_2d(&tmB, B, K, N, ldb, BLOCK_K, swiglu ? 128 : block_n);
+    if (!b_mn_major) rc = tc05::make_tmap_2d(&tmB, B, K, N, ldb, BLOCK_K, swiglu ? 128 : block_n / cg);
     else             rc = tc05::make_tmap_2d(&tmB, B, N, K, ldb, 64, BLOCK_K);
     if (rc) return rc;
     if (!p.tma_store) { tmC = tmA; tmD = tmA; }      // unused by the kernel, but must be valid maps
@@ -884,15 +954,17 @@ static int gemm_impl(const void* A, const void* B, void* C, const void* R, int M
         eg_fused = (e2 && e2[0] == '1') ? 1 : 2;
     }
     const int eg = (p.epilogue == EPI_ROPE || p.epilogue == EPI_SWIGLU) ? eg_fused : eg_plain;
-#define B200_DISPATCH(BN, EGV)                                                                   \
+#define B200_DISPATCH(BN, EGV, CGV)                                                                   \
     do {                                                                                    \
-        if (!a_mn_major && !b_mn_major) rc = launch<BN, false, false, EGV>(tmA, tmB, tmC, tmD, p, stream);  \
-        else if (!a_mn_major && b_mn_major) rc = launch<BN, false, true, EGV>(tmA, tmB, tmC, tmD, p, stream); \
-        else if (a_mn_major && b_mn_major) rc = launch<BN, true, true, EGV>(tmA, tmB, tmC, tmD, p, stream);  \
-        else rc = launch<BN, true, false, EGV>(tmA, tmB, tmC, tmD, p, stream);                              \
+        if (!a_mn_major && !b_mn_major) rc = launch<BN, false, false, EGV, CGV>(tmA, tmB, tmC, tmD, p, stream);  \
+        else if (!a_mn_major && b_mn_major) rc = launch<BN, false, true, EGV, CGV>(tmA, tmB, tmC, tmD, p, stream); \
+        else if (a_mn_major && b_mn_major) rc = launch<BN, true, true, EGV, CGV>(tmA, tmB, tmC, tmD, p, stream);  \
+        else rc = launch<BN, true, false, EGV, CGV>(tmA, tmB, tmC, tmD, p, stream);                              \
     } while (0)
-    if (block_n == 256) { if (eg == 2) B200_DISPATCH(256, 2); else B200_DISPATCH(256, 1); }
-    else { if (eg == 2) B200_DISPATCH(128, 2); else B200_DISPATCH(128, 1); }
+    if (block_n == 256) {
+        if (cg == 2) { if (eg == 2) B200_DISPATCH(256, 2, 2); else B200_DISPATCH(256, 1, 2); }
+        else { if (eg == 2) B200_DISPATCH(256, 2, 1); else B200_DISPATCH(256, 1, 1); }
+    } else { if (eg == 2) B200_DISPATCH(128, 2, 1); else B200_DISPATCH(128, 1, 1); }
 #undef B200_DISPATCH
     if (rc) return rc;
 

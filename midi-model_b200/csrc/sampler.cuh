@@ -181,7 +181,7 @@ __device__ int preselect_topk(float* s_p, int* s_i, int n, int top_k, int* s_his
 // Results are identical to the general path (sample_tail on the compacted candidates), which remains for top_k > 64.
 // Scratch: s_p [SMP_MAXV] floats, s_i [SMP_MAXV] ints, s_cnt [NT + 8] ints, s_red [64] floats.
 // ---------------------------------------------------------------------------------------------
-template <int NT>
+template <int NT, bool FAST_ONLY = false>
 __device__ int sample_logits_row(const bf16* __restrict__ logits, int V, float temp, float top_p, int top_k, int lo, int hi,
                                  const unsigned char* __restrict__ mrow, float u, float* s_p, int* s_i, int* s_cnt,
                                  float* s_red, bool coherent_loads) {
@@ -212,7 +212,7 @@ __device__ int sample_logits_row(const bf16* __restrict__ logits, int V, float t
     for (int w = 0; w < NW; w++) sum += s_red[32 + w];
     const float inv = 1.f / sum;
 
-    if (top_k > 64) {                                  // general path
+    if (!FAST_ONLY && top_k > 64) {                    // general path
         __syncthreads();
         for (int i = tid; i < V; i += NT) {
             bool ok = (i >= lo && i < hi);

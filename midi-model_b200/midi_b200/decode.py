@@ -275,7 +275,7 @@ class GraphGenerator:
     # ------------------------------------------------------------------ persistent kernel (csrc/decode_persist.cu)
     def persistent_ok(self) -> bool:
         c1, c2 = self.outer.eng.cfg, self.inner.eng.cfg
-        return (self.B <= 16 and c1.hidden == 1024 and c2.hidden == 1024 and c1.head_dim == 64 and c2.head_dim == 256
+        return (self.B <= 16 and 1 <= self.top_k <= 64 and c1.hidden == 1024 and c2.hidden == 1024 and c1.head_dim == 64 and c2.head_dim == 256
                 and c1.inner % 256 == 0 and c2.inner % 256 == 0 and self.T == 8 and self.kv1.page % 32 == 0)
 
     def _persistent(self):
