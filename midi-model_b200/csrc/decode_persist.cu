@@ -44,6 +44,7 @@ struct DD {                              // b200_decode_desc with typed pointers
     float temp, top_p;
     int top_k, batch;
     unsigned long long* prof;            // optional: per-phase clock64 totals of CTA 0 (tuning hook)
+    int l2_prefetch;                     // stream the event-level weights into L2 ahead of use
 };
 
 struct PD {                              // kernel parameters (device pointers resolved on the host)
@@ -195,6 +196,12 @@ __device__ __forceinline__ void gemv_pairs(const bf16* xs, int K, const bf16* __
         float acc0[BM], acc1[BM];
 #pragma unroll
         for (int b = 0; b < BM; b++) { acc0[b] = 0.f; acc1[b] = 0.f; }
+        // residual values of this pair (lane b <-> batch row b): requested now, needed only after the reduction
+        unsigned short res0 = 0, res1 = 0;
+        if (!SWIGLU && res != nullptr && lane < B) {
+            res0 = __ldcg(reinterpret_cast<const unsigned short*>(res + (size_t)lane * ldr + r0));
+            if (has1) res1 = __ldcg(reinterpret_cast<const unsigned short*>(res + (size_t)lane * ldr + r1));
+        }
         const bool first = (pi == gw);
         for (int i0 = 0; i0 < nblk; i0 += 4) {
             uint4 wa[4], wb[4];
@@ -241,12 +248,8 @@ __device__ __forceinline__ void gemv_pairs(const bf16* xs, int K, const bf16* __
             const int b = lane;
             float o0 = my0, o1 = my1;
             if (res) {
-                const unsigned short ra = __ldcg(reinterpret_cast<const unsigned short*>(res + (size_t)b * ldr + r0));
-                o0 = bf16_round(o0) + __bfloat162float(__ushort_as_bfloat16(ra));
-                if (has1) {
-                    const unsigned short rb = __ldcg(reinterpret_cast<const unsigned short*>(res + (size_t)b * ldr + r1));
-                    o1 = bf16_round(o1) + __bfloat162float(__ushort_as_bfloat16(rb));
-                }
+                o0 = bf16_round(o0) + __bfloat162float(__ushort_as_bfloat16(res0));
+                if (has1) o1 = bf16_round(o1) + __bfloat162float(__ushort_as_bfloat16(res1));
             }
             y[(size_t)b * ldy + r0] = __float2bfloat16_rn(o0);
             if (has1) y[(size_t)b * ldy + r1] = __float2bfloat16_rn(o1);
@@ -255,6 +258,9 @@ __device__ __forceinline__ void gemv_pairs(const bf16* xs, int K, const bf16* __
 }
 
 // ---- staging of the activations into shared memory (one warp per batch row) -------------------------------------
+// Every loop below issues its global loads in batches of four 16-byte vectors per lane BEFORE using any of them (K = 1024 is
+// exactly one batch): with a runtime trip count the compiler emits load -> use -> load -> use, i.e. one L2 round trip
+// (300-600 cycles) per vector on the critical path of every phase.
 // RMSNorm in place on a shared row (hf :62-67: fp32 statistics, round, times weight, round)
 __device__ __forceinline__ void norm_row_inplace(bf16* row, int K, const bf16* __restrict__ w, float eps, int lane) {
     const int nvec = K / 8;
@@ -267,17 +273,36 @@ __device__ __forceinline__ void norm_row_inplace(bf16* row, int K, const bf16* _
     }
     ss = warp_sum(ss);
     const float rstd = rsqrtf(ss / (float)K + eps);
-    for (int v = lane; v < nvec; v += 32) {
-        float f[8], wv[8];
-        unpack8(*reinterpret_cast<const uint4*>(row + v * 8), f);
-        unpack8(*reinterpret_cast<const uint4*>(w + v * 8), wv);
+    for (int v0 = lane; v0 < nvec; v0 += 128) {
+        uint4 wr[4];
 #pragma unroll
-        for (int j = 0; j < 8; j++) f[j] = wv[j] * bf16_round(f[j] * rstd);
-        *reinterpret_cast<uint4*>(row + v * 8) = pack8(f);
+        for (int i = 0; i < 4; i++)
+            if (v0 + 32 * i < nvec) wr[i] = *reinterpret_cast<const uint4*>(w + (v0 + 32 * i) * 8);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int v = v0 + 32 * i;
+            if (v < nvec) {
+                float f[8], wv[8];
+                unpack8(*reinterpret_cast<const uint4*>(row + v * 8), f);
+                unpack8(wr[i], wv);
+#pragma unroll
+                for (int j = 0; j < 8; j++) f[j] = wv[j] * bf16_round(f[j] * rstd);
+                *reinterpret_cast<uint4*>(row + v * 8) = pack8(f);
+            }
+        }
     }
 }
 __device__ __forceinline__ void copy_row_from_global(bf16* dst, const bf16* src, int K, int lane) {
-    for (int v = lane; v < K / 8; v += 32) *reinterpret_cast<uint4*>(dst + v * 8) = ldcg16(src + v * 8);
+    const int nvec = K / 8;
+    for (int v0 = lane; v0 < nvec; v0 += 128) {
+        uint4 r[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (v0 + 32 * i < nvec) r[i] = ldcg16(src + (v0 + 32 * i) * 8);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (v0 + 32 * i < nvec) *reinterpret_cast<uint4*>(dst + (v0 + 32 * i) * 8) = r[i];
+    }
 }
 __device__ __forceinline__ void copy_row_to_global(bf16* dst, const bf16* src, int K, int lane) {
     for (int v = lane; v < K / 8; v += 32) *reinterpret_cast<uint4*>(dst + v * 8) = *reinterpret_cast<const uint4*>(src + v * 8);
@@ -577,12 +602,18 @@ __device__ __noinline__ void stage_phase(const PD& p, const StageArgs& a, bf16* 
         } else if (a.kind == 1) {
             // embed_tokens(x).sum(-2) (midi_model.py:145-146): fp32 accumulate over the 8 ids, one rounding
             for (int v = lane; v < a.K / 8; v += 32) {
-                float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                for (int t = 0; t < PD_T; t++) {
+                uint4 er[PD_T];
+#pragma unroll
+                for (int t = 0; t < PD_T; t++) {          // the 8 embedding rows of the event: loads in flight together
                     const int id = cur_ev[warp * PD_T + t];
-                    if (id < 0 || id >= d.V) continue;
+                    er[t] = make_uint4(0, 0, 0, 0);
+                    if (id >= 0 && id < d.V) er[t] = *reinterpret_cast<const uint4*>(d.emb_outer + (size_t)id * a.K + v * 8);
+                }
+                float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+                for (int t = 0; t < PD_T; t++) {
                     float f[8];
-                    unpack8(*reinterpret_cast<const uint4*>(d.emb_outer + (size_t)id * a.K + v * 8), f);
+                    unpack8(er[t], f);
 #pragma unroll
                     for (int j = 0; j < 8; j++) acc[j] += f[j];
                 }
@@ -591,8 +622,7 @@ __device__ __noinline__ void stage_phase(const PD& p, const StageArgs& a, bf16* 
         } else {
             long long id = __ldcg(a.ids + warp);       // embedding of the token sampled at the previous step (midi_model.py:128)
             if (id < 0 || id >= d.V) id = 0;
-            for (int v = lane; v < a.K / 8; v += 32)
-                *reinterpret_cast<uint4*>(row + v * 8) = *reinterpret_cast<const uint4*>(d.emb_inner + (size_t)id * a.K + v * 8);
+            copy_row_from_global(row, d.emb_inner + (size_t)id * a.K, a.K, lane);
         }
         __syncwarp();
         if (a.norm_a) {
@@ -644,6 +674,7 @@ __device__ __forceinline__ void l2_prefetch_slice(const bf16* base, size_t elems
 // weights (kept with evict_last) and the KV cache.
 __device__ __forceinline__ void l2_prefetch_layer(const PD& p, int layer, int part) {
     const DD& d = p.d;
+    if (!d.l2_prefetch) return;
     const LayerW w = layer_w(d.outer_w, layer);
     const size_t H = d.H, I = d.I_outer;
     if (part == 0) {
@@ -891,6 +922,14 @@ extern "C" int b200_decode_events(const b200_decode_desc* desc, int n_events, vo
     t.dense_mask = d.dense_mask; t.lut = d.lut; t.n_event_types = d.n_event_types; t.eos_id = d.eos_id; t.pad_id = d.pad_id;
     t.temp = d.temp; t.top_p = d.top_p; t.top_k = d.top_k; t.batch = d.batch;
     t.prof = d.prof;
+    {
+        static int l2pf = -1;
+        if (l2pf < 0) {
+            const char* e = getenv("B200_DECODE_L2_PREFETCH");
+            l2pf = (e && e[0] == '0') ? 0 : 1;
+        }
+        t.l2_prefetch = l2pf;
+    }
     p.bar = (unsigned int*)(ws + L.bar);
     p.x = (bf16*)(ws + L.x); p.h = (bf16*)(ws + L.h); p.x2 = (bf16*)(ws + L.x2); p.h2 = (bf16*)(ws + L.h2);
     p.qkv = (bf16*)(ws + L.qkv); p.attn = (bf16*)(ws + L.attn); p.act = (bf16*)(ws + L.act);

@@ -748,13 +748,25 @@ extern "C" size_t b200_gemm_tail_workspace_bytes(int M, int N, int K, int block_
 // (waves of items) x (k-blocks per item) in MMA clocks, plus pipeline fill, the exposed last epilogue and, for
 // splits > 1, the fp32 partial round trip.  Picks the cheapest (block_n, splits): this is what removes the
 // wave-quantisation loss of the small-output wgrad problems (e.g. 192 tiles on 148 SMs -> 3 splits, 3.9 waves).
+static bool pair_enabled() {
+    static int ok = -1;
+    if (ok < 0) {
+        const char* e = getenv("B200_GEMM_CTA_PAIR");
+        ok = (e && e[0] == '0') ? 0 : 1;
+    }
+    return ok != 0;
+}
 static double plan_cost(int M, int N, int K, int block_n, int s, int sms) {
-    const double tiles = (double)((M + BLOCK_M - 1) / BLOCK_M) * ((N + block_n - 1) / block_n);
+    // CTA pairs (256-wide tiles, more than one row tile): the schedulable unit is a 256 x 256 tile pair on sms / 2 clusters
+    const bool pair = pair_enabled() && block_n == 256 && M > BLOCK_M;
+    const int rows = pair ? 2 * BLOCK_M : BLOCK_M;
+    const int workers = pair ? sms / 2 : sms;
+    const double tiles = (double)((M + rows - 1) / rows) * ((N + block_n - 1) / block_n);
     const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
     const int kb_per = (num_kb + s - 1) / s;
     const int s_eff = (num_kb + kb_per - 1) / kb_per;
     const double items = tiles * s_eff;
-    const double waves = ceil(items / sms);
+    const double waves = ceil(items / workers);
     // 4 UMMAs of 128 x block_n x 16 per k-block.  Measured on B200 (profiles/r1_*): 128-wide tiles top out near
     // 800 TFLOP/s (the 128x128x16 SS-mode UMMA re-reads 8 KB of smem operands per 64 clk = the 128 B/clk smem limit)
     // while 256-wide tiles reach 1.3-1.48 PFLOP/s, hence the 1.7x cost factor.
@@ -861,12 +873,7 @@ static int gemm_impl(const void* A, const void* B, void* C, const void* R, int M
     p.splits = splits;
     // CTA pairs (cta_group::2, 256-row tile pairs) for the 256-wide tiles: halves the B-operand shared-memory traffic per
     // MMA and the B bytes each CTA pulls through TMA.  B200_GEMM_CTA_PAIR=0 keeps one CTA per tile.
-    static int pair_ok = -1;
-    if (pair_ok < 0) {
-        const char* e = getenv("B200_GEMM_CTA_PAIR");
-        pair_ok = (e && e[0] == '0') ? 0 : 1;
-    }
-    const int cg = (pair_ok && block_n == 256 && M > BLOCK_M) ? 2 : 1;
+    const int cg = (pair_enabled() && block_n == 256 && M > BLOCK_M) ? 2 : 1;
     p.m_tiles = (M + BLOCK_M * cg - 1) / (BLOCK_M * cg);
     p.n_tiles = (N + block_n - 1) / block_n;
     p.mn_lbo = BLOCK_K * 128;

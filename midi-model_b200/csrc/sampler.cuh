@@ -189,12 +189,29 @@ __device__ int sample_logits_row(const bf16* __restrict__ logits, int V, float t
     constexpr int PER = SMP_MAXV / NT;                 // ids per thread (consecutive: thread t owns [t * PER, t * PER + PER))
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float mx = -INFINITY;
-    for (int i = tid; i < V; i += NT) {
-        const unsigned short raw = coherent_loads ? __ldcg(reinterpret_cast<const unsigned short*>(logits + i))
-                                                  : *reinterpret_cast<const unsigned short*>(logits + i);
-        const float x = bf16_round(__bfloat162float(__ushort_as_bfloat16(raw)) / temp);
-        s_p[i] = x;
-        mx = fmaxf(mx, x);
+    {
+        // the row's logits (<= PER per thread) requested together, then scaled / stored: one memory latency, not PER
+        unsigned short lraw[PER];
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int i = tid + k * NT;
+            lraw[k] = 0;
+            if (i < V) lraw[k] = coherent_loads ? __ldcg(reinterpret_cast<const unsigned short*>(logits + i))
+                                                : *reinterpret_cast<const unsigned short*>(logits + i);
+        }
+        const float inv_t = 1.f / temp;
+        const bool unit = temp == 1.f;
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int i = tid + k * NT;
+            if (i < V) {
+                const float l = __bfloat162float(__ushort_as_bfloat16(lraw[k]));
+                const float x = unit ? l : bf16_round(l / temp);
+                s_p[i] = x;
+                mx = fmaxf(mx, x);
+            }
+        }
+        (void)inv_t;
     }
     mx = warp_max(mx);
     if (lane == 0) s_red[warp] = mx;
@@ -229,11 +246,18 @@ __device__ int sample_logits_row(const bf16* __restrict__ logits, int V, float t
     // ---- fast path.  key = bf16 bit pattern of p (monotonic in p for p > 0), 0 = not a candidate
     unsigned key[PER];
     const int id0 = tid * PER;
+    unsigned char mk[PER];
+#pragma unroll
+    for (int j = 0; j < PER; j++) {                     // mask bytes of this thread's ids, requested together
+        const int id = id0 + j;
+        mk[j] = 1;
+        if (mrow != nullptr && id >= lo && id < hi && id < V) mk[j] = mrow[id];
+    }
 #pragma unroll
     for (int j = 0; j < PER; j++) {
         const int id = id0 + j;
         unsigned k = 0;
-        if (id >= lo && id < hi && id < V && (mrow == nullptr || mrow[id] != 0)) {
+        if (id >= lo && id < hi && id < V && mk[j] != 0) {
             const float pr = bf16_round(__expf(s_p[id] - mx) * inv);
             k = __float_as_uint(pr) >> 16;
         }
