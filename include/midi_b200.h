@@ -221,6 +221,7 @@ typedef struct b200_decode_desc {
                                    lm_head (11), sample (12), commit (13); [64 + 2i] / [65 + 2i] += the part of phase i
                                    spent staging activations / doing the phase's own work (the rest = barrier wait) */
 } b200_decode_desc;
+size_t b200_decode_desc_bytes(void);            /* sizeof(b200_decode_desc): lets a binding check its struct mirror */
 size_t b200_decode_events_workspace_bytes(const b200_decode_desc* d);
 int b200_decode_events(const b200_decode_desc* d, int n_events, void* workspace /*256-byte aligned*/,
                        size_t workspace_bytes, cudaStream_t s);

@@ -9,6 +9,11 @@
 // warp issues the loads of its first weight rows of the NEXT phase before it waits at the barrier (weights do not depend
 // on the previous phase), so the HBM latency of every phase hides behind the barrier.
 //
+// Measured notes (profiles/r2_decode_*): a bare grid barrier of 148 x 512 threads costs ~2 300 cycles
+// (tools/micro/gridbar_bench.cu) and waits for the issuing SM's outstanding loads, so a phase boundary is ~1.2 us, not the
+// L2 round trip; a variant with the phases as shared non-inlined routines (smaller instruction footprint) plus bulk L2
+// prefetch of the event-level weights was 25 % SLOWER at batch 1 (argument structs in local memory, calls) and was dropped.
+//
 // Arithmetic and rounding points are those of the launch-per-phase kernels in decode.cu (same per-row accumulation
 // order in the projections; attention differs only in how the context is cut into chunks).
 #include <cooperative_groups.h>
@@ -44,7 +49,6 @@ struct DD {                              // b200_decode_desc with typed pointers
     float temp, top_p;
     int top_k, batch;
     unsigned long long* prof;            // optional: per-phase clock64 totals of CTA 0 (tuning hook)
-    int l2_prefetch;                     // stream the event-level weights into L2 ahead of use
 };
 
 struct PD {                              // kernel parameters (device pointers resolved on the host)
@@ -570,122 +574,6 @@ __device__ __forceinline__ float rng_uniform(unsigned long long seed, unsigned l
     return (float)(z >> 40) * (1.0f / 16777216.0f);
 }
 
-// ---- one projection phase = staging of the activations + skinny GEMM, as TWO non-inlined routines shared by all eleven
-// projection phases of an event.  Code size matters here: every phase runs once and the next one evicts it, so with each
-// phase inlined (20 k instructions, 320 KB for batch 1) the kernel was instruction-fetch bound -- a 400-instruction staging
-// step measured 5 500 cycles.  Shared routines keep the token-step loop (~2 k instructions) resident in the instruction cache.
-struct StageArgs {
-    int kind;                  // 0: rows of a global buffer; 1: embed_tokens(event).sum(-2); 2: embedding of the previous token
-    const bf16* src;           // kind 0: [B][K]
-    const long long* ids;      // kind 2: ids[b] (token sampled at the previous step)
-    const bf16* norm_a;        // optional: RMSNorm applied first (final norm of the event-level stack -> `hidden`)
-    bf16* writeback;           // optional: CTA 0 stores the row here (it becomes the residual stream)
-    const bf16* norm_b;        // optional: the layer's RMSNorm
-    int K;
-};
-struct GemvArgs {
-    const bf16* W;
-    int K, N_out, swiglu;
-    const bf16* res;
-    bf16* y;
-    int ldy;
-    unsigned long long pol;
-};
-
-__device__ __noinline__ void stage_phase(const PD& p, const StageArgs& a, bf16* xs, const int* cur_ev, int B) {
-    const DD& d = p.d;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp < B) {
-        bf16* row = xs + (size_t)warp * a.K;
-        if (a.kind == 0) {
-            copy_row_from_global(row, a.src + (size_t)warp * a.K, a.K, lane);
-        } else if (a.kind == 1) {
-            // embed_tokens(x).sum(-2) (midi_model.py:145-146): fp32 accumulate over the 8 ids, one rounding
-            for (int v = lane; v < a.K / 8; v += 32) {
-                uint4 er[PD_T];
-#pragma unroll
-                for (int t = 0; t < PD_T; t++) {          // the 8 embedding rows of the event: loads in flight together
-                    const int id = cur_ev[warp * PD_T + t];
-                    er[t] = make_uint4(0, 0, 0, 0);
-                    if (id >= 0 && id < d.V) er[t] = *reinterpret_cast<const uint4*>(d.emb_outer + (size_t)id * a.K + v * 8);
-                }
-                float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-                for (int t = 0; t < PD_T; t++) {
-                    float f[8];
-                    unpack8(er[t], f);
-#pragma unroll
-                    for (int j = 0; j < 8; j++) acc[j] += f[j];
-                }
-                *reinterpret_cast<uint4*>(row + v * 8) = pack8(acc);
-            }
-        } else {
-            long long id = __ldcg(a.ids + warp);       // embedding of the token sampled at the previous step (midi_model.py:128)
-            if (id < 0 || id >= d.V) id = 0;
-            copy_row_from_global(row, d.emb_inner + (size_t)id * a.K, a.K, lane);
-        }
-        __syncwarp();
-        if (a.norm_a) {
-            norm_row_inplace(row, a.K, a.norm_a, d.eps, lane);
-            __syncwarp();
-        }
-        if (a.writeback && blockIdx.x == 0) copy_row_to_global(a.writeback + (size_t)warp * a.K, row, a.K, lane);
-        if (a.norm_b) norm_row_inplace(row, a.K, a.norm_b, d.eps, lane);
-    }
-    __syncthreads();
-}
-
-template <int BM>
-__device__ __noinline__ void gemv_phase(const GemvArgs& a, const bf16* xs, int B, int gwv, int ngwv, const Pre& pre) {
-    const int lane = threadIdx.x & 31;
-    if (a.swiglu) gemv_pairs<BM, true>(xs, a.K, a.W, a.K, a.N_out, B, nullptr, 0, a.y, a.ldy, gwv, ngwv, lane, pre, a.pol);
-    else gemv_pairs<BM, false>(xs, a.K, a.W, a.K, a.N_out, B, a.res, a.ldy, a.y, a.ldy, gwv, ngwv, lane, pre, a.pol);
-}
-
-__device__ __noinline__ void grid_sync_call(GridBar& gb) { grid_sync(gb); }
-
-__device__ __forceinline__ void prefetch_any(Pre& pre, const bf16* W, int K, int N_out, int swiglu, int gwv, int lane,
-                                             unsigned long long pol) {
-    if (swiglu) prefetch_rows<true>(pre, W, K, N_out, gwv, lane, pol);
-    else prefetch_rows<false>(pre, W, K, N_out, gwv, lane, pol);
-}
-
-// HBM -> L2 prefetch of this CTA's 1/gridDim slice of a weight matrix (fire and forget: no register, shared memory or
-// barrier involved, so a later release / barrier does not wait for it).  Issued one layer ahead: the one-shot register
-// prefetch in front of a grid barrier reaches only ~1.8 TB/s out of HBM (tools/micro/gridbar_bench.cu: 61 KB per SM take
-// ~10 000 cycles), a whole layer (33.5 MB) streamed in the background during the previous layer's phases does not.
-__device__ __forceinline__ void l2_prefetch_slice(const bf16* base, size_t elems) {
-    const size_t bytes = elems * 2;
-    size_t per = (bytes / gridDim.x + 127) & ~(size_t)127;
-    const size_t lo = (size_t)blockIdx.x * per;
-    if (lo >= bytes) return;
-    size_t n = bytes - lo < per ? bytes - lo : per;
-    n &= ~(size_t)15;
-    const char* ptr = reinterpret_cast<const char*>(base) + lo;
-    while (n > 0) {
-        const unsigned chunk = n > 65536 ? 65536u : (unsigned)n;
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(chunk) : "memory");
-        ptr += chunk;
-        n -= chunk;
-    }
-}
-// `part` 0: the attention projections (qkv, o; 8 MB), 1: the MLP (gate|up, down; 25 MB) of an event-level layer.  Issued two to
-// three phases ahead of their use, so at most ~35 MB of not-yet-used weights sit in L2 next to the 51 MB of token-level
-// weights (kept with evict_last) and the KV cache.
-__device__ __forceinline__ void l2_prefetch_layer(const PD& p, int layer, int part) {
-    const DD& d = p.d;
-    if (!d.l2_prefetch) return;
-    const LayerW w = layer_w(d.outer_w, layer);
-    const size_t H = d.H, I = d.I_outer;
-    if (part == 0) {
-        l2_prefetch_slice(w.qkv, 3 * H * H);
-        l2_prefetch_slice(w.o, H * H);
-    } else {
-        l2_prefetch_slice(w.gu, 2 * I * H);
-        l2_prefetch_slice(w.down, H * I);
-    }
-}
-
 // =================================================================================================================
 template <int BM>
 __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p) {
@@ -695,7 +583,7 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
     bf16* xs = reinterpret_cast<bf16*>(pd_smem);                                    // [BM][k_max]
     float* s_p = reinterpret_cast<float*>(pd_smem + (size_t)BM * p.k_max * 2);      // sampler: probabilities
     int* s_i = reinterpret_cast<int*>(s_p + smp::SMP_MAXV);
-    int* s_cnt = s_i + smp::SMP_MAXV;                                               // [PD_THREADS + 8]
+    int* s_cnt = s_i + smp::SMP_MAXV;                                               // [PD_THREADS + 1]
     float* s_red = reinterpret_cast<float*>(s_cnt + PD_THREADS + 8);                // [64]
     float* q_all = s_red + 64;                                                      // [PD_WARPS][64]
     bf16* kn_all = reinterpret_cast<bf16*>(q_all + PD_WARPS * 64);                  // [PD_WARPS][64]
@@ -716,63 +604,100 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
     int pos = __ldcg(d.pos);
     for (int i = threadIdx.x; i < B * PD_T; i += PD_THREADS) cur_ev[i] = (int)__ldcg(d.ev_in + i);
     const unsigned long long rng_c0 = d.rng_state[0], rng_seed = d.rng_state[1];
-    if (threadIdx.x == 32) l2_prefetch_layer(p, 0, 0);      // first projections of the first layer on their way into L2
     __syncthreads();
 
     int events_done = 0;
     Pre pre;
     Prof prof{d.prof, clock64(), clock64()};
-    StageArgs sa;
-    GemvArgs ga;
-    // one projection phase: [wait for the producers] stage the input rows, run this CTA's row pairs
-    auto project = [&](int ph, bool wait, int wait_ph) {
-        if (wait) {
-            grid_sync_call(gb);
-            prof.mark(wait_ph);
-        }
-        stage_phase(p, sa, xs, cur_ev, B);
-        prof.sub(ph, 0);
-        gemv_phase<BM>(ga, xs, B, gwv, ngwv, pre);
-        prof.sub(ph, 1);
-    };
     for (int e = 0; e < p.n_events; e++) {
         if (pos + 1 >= d.max_len) break;
         // =============================== event-level stack: one new position per row ===============================
         for (int l = 0; l < d.n_outer; l++) {
             const LayerW w = layer_w(d.outer_w, l);
-            if (threadIdx.x == 32) l2_prefetch_layer(p, l, 1);       // this layer's MLP weights: needed three phases from now
-            // ---- norm + QKV (layer 0 reads only this CTA's copy of the event: nothing to wait for)
-            sa = StageArgs{l == 0 ? 1 : 0, p.x, nullptr, nullptr, l == 0 ? p.x : nullptr, w.ln1, H};
-            ga = GemvArgs{w.qkv, H, 3 * H, 0, nullptr, p.qkv, 3 * H, pol_stream};
-            prefetch_any(pre, ga.W, ga.K, ga.N_out, ga.swiglu, gwv, lane, ga.pol);
-            project(PH_QKV_O, l > 0, PH_DOWN_O);
+            // ---- norm + QKV
+            prefetch_rows<false>(pre, w.qkv, H, 3 * H, gwv, lane, pol_stream);
+            if (l > 0) { grid_sync(gb); prof.mark(PH_DOWN_O); }   // layer 0 reads only this CTA's copy of the event: no wait
+            if (warp < B) {
+                bf16* row = xs + (size_t)warp * H;
+                if (l == 0) {
+                    // embed_tokens(x).sum(-2) (midi_model.py:145-146): fp32 accumulate over the 8 ids, one rounding
+                    for (int v = lane; v < H / 8; v += 32) {
+                        uint4 er[PD_T];
+#pragma unroll
+                        for (int t = 0; t < PD_T; t++) {      // the 8 embedding rows of the event: loads in flight together
+                            const int id = cur_ev[warp * PD_T + t];
+                            er[t] = make_uint4(0, 0, 0, 0);
+                            if (id >= 0 && id < d.V) er[t] = *reinterpret_cast<const uint4*>(d.emb_outer + (size_t)id * H + v * 8);
+                        }
+                        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+                        for (int t = 0; t < PD_T; t++) {
+                            float f[8];
+                            unpack8(er[t], f);
+#pragma unroll
+                            for (int j = 0; j < 8; j++) acc[j] += f[j];
+                        }
+                        *reinterpret_cast<uint4*>(row + v * 8) = pack8(acc);
+                    }
+                    __syncwarp();
+                    if (blockIdx.x == 0) copy_row_to_global(p.x + (size_t)warp * H, row, H, lane);
+                } else {
+                    copy_row_from_global(row, p.x + (size_t)warp * H, H, lane);
+                }
+                __syncwarp();
+                norm_row_inplace(row, H, w.ln1, d.eps, lane);
+            }
+            __syncthreads();
+            prof.sub(PH_QKV_O, 0);
+            gemv_pairs<BM, false>(xs, H, w.qkv, H, 3 * H, B, nullptr, 0, p.qkv, 3 * H, gwv, ngwv, lane, pre, pol_stream);
+            prof.sub(PH_QKV_O, 1);
             // ---- RoPE + KV append + attention over positions 0..pos
-            grid_sync_call(gb);
+            grid_sync(gb);
             prof.mark(PH_QKV_O);
             int n_chunks;
             outer_attention(p, l, pos, B, gw, ngw, lane, q_s, kn_s, vn_s, n_chunks);
             prof.sub(PH_ATT_O, 1);
             if (n_chunks > 1) {
-                grid_sync_call(gb);
+                grid_sync(gb);
                 prof.mark(PH_ATT_O);
                 outer_attention_combine(p, B, n_chunks, gw, ngw, lane);
+                prefetch_rows<false>(pre, w.o, H, H, gwv, lane, pol_stream);
+                grid_sync(gb);
+                prof.mark(PH_CMB_O);
+            } else {
+                prefetch_rows<false>(pre, w.o, H, H, gwv, lane, pol_stream);
+                grid_sync(gb);
+                prof.mark(PH_ATT_O);
             }
             // ---- o_proj + residual
-            sa = StageArgs{0, p.attn, nullptr, nullptr, nullptr, nullptr, H};
-            ga = GemvArgs{w.o, H, H, 0, p.x, p.h, H, pol_stream};
-            prefetch_any(pre, ga.W, ga.K, ga.N_out, ga.swiglu, gwv, lane, ga.pol);
-            project(PH_OPROJ_O, true, n_chunks > 1 ? PH_CMB_O : PH_ATT_O);
+            if (warp < B) copy_row_from_global(xs + (size_t)warp * H, p.attn + (size_t)warp * H, H, lane);
+            __syncthreads();
+            prof.sub(PH_OPROJ_O, 0);
+            gemv_pairs<BM, false>(xs, H, w.o, H, H, B, p.x, H, p.h, H, gwv, ngwv, lane, pre, pol_stream);
+            prof.sub(PH_OPROJ_O, 1);
             // ---- norm + gate|up + SwiGLU
-            if (threadIdx.x == 32 && l + 1 < d.n_outer) l2_prefetch_layer(p, l + 1, 0);   // next layer's attention projections
-            sa = StageArgs{0, p.h, nullptr, nullptr, nullptr, w.ln2, H};
-            ga = GemvArgs{w.gu, H, d.I_outer, 1, nullptr, p.act, d.I_outer, pol_stream};
-            prefetch_any(pre, ga.W, ga.K, ga.N_out, ga.swiglu, gwv, lane, ga.pol);
-            project(PH_GU_O, true, PH_OPROJ_O);
+            prefetch_rows<true>(pre, w.gu, H, d.I_outer, gwv, lane, pol_stream);
+            grid_sync(gb);
+            prof.mark(PH_OPROJ_O);
+            if (warp < B) {
+                copy_row_from_global(xs + (size_t)warp * H, p.h + (size_t)warp * H, H, lane);
+                __syncwarp();
+                norm_row_inplace(xs + (size_t)warp * H, H, w.ln2, d.eps, lane);
+            }
+            __syncthreads();
+            prof.sub(PH_GU_O, 0);
+            gemv_pairs<BM, true>(xs, H, w.gu, H, d.I_outer, B, nullptr, 0, p.act, d.I_outer, gwv, ngwv, lane, pre, pol_stream);
+            prof.sub(PH_GU_O, 1);
             // ---- down + residual
-            sa = StageArgs{0, p.act, nullptr, nullptr, nullptr, nullptr, d.I_outer};
-            ga = GemvArgs{w.down, d.I_outer, H, 0, p.h, p.x, H, pol_stream};
-            prefetch_any(pre, ga.W, ga.K, ga.N_out, ga.swiglu, gwv, lane, ga.pol);
-            project(PH_DOWN_O, true, PH_GU_O);
+            prefetch_rows<false>(pre, w.down, d.I_outer, H, gwv, lane, pol_stream);
+            grid_sync(gb);
+            prof.mark(PH_GU_O);
+            __syncthreads();
+            if (warp < B) copy_row_from_global(xs + (size_t)warp * d.I_outer, p.act + (size_t)warp * d.I_outer, d.I_outer, lane);
+            __syncthreads();
+            prof.sub(PH_DOWN_O, 0);
+            gemv_pairs<BM, false>(xs, d.I_outer, w.down, d.I_outer, H, B, p.h, H, p.x, H, gwv, ngwv, lane, pre, pol_stream);
+            prof.sub(PH_DOWN_O, 1);
         }
         // =============================== token-level stack: up to 8 steps =========================================
         int n_steps = PD_T;
@@ -780,14 +705,8 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
             if (i >= n_steps) break;
             for (int l = 0; l < d.n_inner; l++) {
                 const LayerW w = layer_w(d.inner_w, l);
-                // ---- norm + QKV.  Layer 0 builds the stack's input: `hidden` (final norm of the event-level stack, hf :421,
-                // midi_model.py:126) at step 0, the embedding of the previous token afterwards (midi_model.py:128)
-                if (l > 0) sa = StageArgs{0, p.x2, nullptr, nullptr, nullptr, w.ln1, H};
-                else if (i == 0) sa = StageArgs{0, p.x, nullptr, d.outer_norm, p.x2, w.ln1, H};
-                else sa = StageArgs{2, nullptr, p.ev_t + (size_t)(i - 1) * B, nullptr, p.x2, w.ln1, H};
-                ga = GemvArgs{w.qkv, H, 3 * H, 0, nullptr, p.qkv, 3 * H, pol_keep};
-                prefetch_any(pre, ga.W, ga.K, ga.N_out, ga.swiglu, gwv, lane, ga.pol);
-                grid_sync_call(gb);
+                prefetch_rows<false>(pre, w.qkv, H, 3 * H, gwv, lane, pol_keep);
+                grid_sync(gb);
                 prof.mark(l > 0 ? PH_DOWN_I : (i > 0 ? PH_SAMPLE : PH_DOWN_O));
                 if (i == 1 && l == 0) {
                     // how many token steps this event needs (midi_model.py:234-237: stop once every live row has all its
@@ -804,34 +723,78 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
                     }
                     n_steps = min(PD_T, need);
                 }
-                project(PH_QKV_I, false, 0);
-                grid_sync_call(gb);
+                if (warp < B) {
+                    bf16* row = xs + (size_t)warp * H;
+                    if (l == 0) {
+                        if (i == 0) {          // hidden = final norm of the event-level stack (hf :421), midi_model.py:126
+                            copy_row_from_global(row, p.x + (size_t)warp * H, H, lane);
+                            __syncwarp();
+                            norm_row_inplace(row, H, d.outer_norm, d.eps, lane);
+                        } else {               // embedding of the token sampled at the previous step (midi_model.py:128)
+                            long long id = __ldcg(p.ev_t + (size_t)(i - 1) * B + warp);
+                            if (id < 0 || id >= d.V) id = 0;
+                            copy_row_from_global(row, d.emb_inner + (size_t)id * H, H, lane);
+                        }
+                        __syncwarp();
+                        if (blockIdx.x == 0) copy_row_to_global(p.x2 + (size_t)warp * H, row, H, lane);
+                    } else {
+                        copy_row_from_global(row, p.x2 + (size_t)warp * H, H, lane);
+                    }
+                    __syncwarp();
+                    norm_row_inplace(row, H, w.ln1, d.eps, lane);
+                }
+                __syncthreads();
+                prof.sub(PH_QKV_I, 0);
+                gemv_pairs<BM, false>(xs, H, w.qkv, H, 3 * H, B, nullptr, 0, p.qkv, 3 * H, gwv, ngwv, lane, pre, pol_keep);
+                prof.sub(PH_QKV_I, 1);
+                grid_sync(gb);
                 prof.mark(PH_QKV_I);
                 inner_attention(p, l, i, B, gw, ngw, lane);
                 prof.sub(PH_ATT_I, 1);
-                // ---- o_proj + residual
-                sa = StageArgs{0, p.attn, nullptr, nullptr, nullptr, nullptr, H};
-                ga = GemvArgs{w.o, H, H, 0, p.x2, p.h2, H, pol_keep};
-                prefetch_any(pre, ga.W, ga.K, ga.N_out, ga.swiglu, gwv, lane, ga.pol);
-                project(PH_OPROJ_I, true, PH_ATT_I);
-                // ---- norm + gate|up + SwiGLU
-                sa = StageArgs{0, p.h2, nullptr, nullptr, nullptr, w.ln2, H};
-                ga = GemvArgs{w.gu, H, d.I_inner, 1, nullptr, p.act, d.I_inner, pol_keep};
-                prefetch_any(pre, ga.W, ga.K, ga.N_out, ga.swiglu, gwv, lane, ga.pol);
-                project(PH_GU_I, true, PH_OPROJ_I);
-                // ---- down + residual
-                sa = StageArgs{0, p.act, nullptr, nullptr, nullptr, nullptr, d.I_inner};
-                ga = GemvArgs{w.down, d.I_inner, H, 0, p.h2, p.x2, H, pol_keep};
-                prefetch_any(pre, ga.W, ga.K, ga.N_out, ga.swiglu, gwv, lane, ga.pol);
-                project(PH_DOWN_I, true, PH_GU_I);
+                prefetch_rows<false>(pre, w.o, H, H, gwv, lane, pol_keep);
+                grid_sync(gb);
+                prof.mark(PH_ATT_I);
+                if (warp < B) copy_row_from_global(xs + (size_t)warp * H, p.attn + (size_t)warp * H, H, lane);
+                __syncthreads();
+                prof.sub(PH_OPROJ_I, 0);
+                gemv_pairs<BM, false>(xs, H, w.o, H, H, B, p.x2, H, p.h2, H, gwv, ngwv, lane, pre, pol_keep);
+                prof.sub(PH_OPROJ_I, 1);
+                prefetch_rows<true>(pre, w.gu, H, d.I_inner, gwv, lane, pol_keep);
+                grid_sync(gb);
+                prof.mark(PH_OPROJ_I);
+                if (warp < B) {
+                    copy_row_from_global(xs + (size_t)warp * H, p.h2 + (size_t)warp * H, H, lane);
+                    __syncwarp();
+                    norm_row_inplace(xs + (size_t)warp * H, H, w.ln2, d.eps, lane);
+                }
+                __syncthreads();
+                prof.sub(PH_GU_I, 0);
+                gemv_pairs<BM, true>(xs, H, w.gu, H, d.I_inner, B, nullptr, 0, p.act, d.I_inner, gwv, ngwv, lane, pre, pol_keep);
+                prof.sub(PH_GU_I, 1);
+                prefetch_rows<false>(pre, w.down, d.I_inner, H, gwv, lane, pol_keep);
+                grid_sync(gb);
+                prof.mark(PH_GU_I);
+                if (warp < B) copy_row_from_global(xs + (size_t)warp * d.I_inner, p.act + (size_t)warp * d.I_inner, d.I_inner, lane);
+                __syncthreads();
+                prof.sub(PH_DOWN_I, 0);
+                gemv_pairs<BM, false>(xs, d.I_inner, w.down, d.I_inner, H, B, p.h2, H, p.x2, H, gwv, ngwv, lane, pre, pol_keep);
+                prof.sub(PH_DOWN_I, 1);
             }
             // ---- final norm + lm_head
-            sa = StageArgs{0, p.x2, nullptr, nullptr, nullptr, d.inner_norm, H};
-            ga = GemvArgs{d.lm_head, H, d.V, 0, nullptr, p.logits, d.pitch, pol_keep};
-            prefetch_any(pre, ga.W, ga.K, ga.N_out, ga.swiglu, gwv, lane, ga.pol);
-            project(PH_LMHEAD, true, PH_DOWN_I);
+            prefetch_rows<false>(pre, d.lm_head, H, d.V, gwv, lane, pol_keep);
+            grid_sync(gb);
+            prof.mark(PH_DOWN_I);
+            if (warp < B) {
+                copy_row_from_global(xs + (size_t)warp * H, p.x2 + (size_t)warp * H, H, lane);
+                __syncwarp();
+                norm_row_inplace(xs + (size_t)warp * H, H, d.inner_norm, d.eps, lane);
+            }
+            __syncthreads();
+            prof.sub(PH_LMHEAD, 0);
+            gemv_pairs<BM, false>(xs, H, d.lm_head, H, d.V, B, nullptr, 0, p.logits, d.pitch, gwv, ngwv, lane, pre, pol_keep);
+            prof.sub(PH_LMHEAD, 1);
             // ---- sample (one CTA per row): temperature softmax, grammar range, top-p / top-k, draw
-            grid_sync_call(gb);
+            grid_sync(gb);
             prof.mark(PH_LMHEAD);
             if ((int)blockIdx.x < B) {
                 const int b = blockIdx.x;
@@ -843,8 +806,9 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
             prof.sub(PH_SAMPLE, 1);
         }
         // =============================== commit the event ========================================================
-        grid_sync_call(gb);                              // every row's tokens are visible
+        grid_sync(gb);                                   // every row's tokens are visible
         prof.mark(PH_SAMPLE);
+        __syncthreads();
         for (int k = threadIdx.x; k < B * PD_T; k += PD_THREADS) {
             const int b = k / PD_T, t = k % PD_T;
             const long long v = (t < n_steps) ? __ldcg(p.ev_t + (size_t)t * B + b) : (long long)d.pad_id;
@@ -856,7 +820,6 @@ __global__ void __launch_bounds__(PD_THREADS, 1) decode_events_kernel(const PD p
         }
         __syncthreads();
         prof.mark(PH_COMMIT);
-        if (threadIdx.x == 32 && e + 1 < p.n_events) l2_prefetch_layer(p, 0, 0);        // next event's first projections
         pos++;
         events_done++;
     }
@@ -892,6 +855,7 @@ WsLayout ws_layout(const b200_decode_desc& d) {
 }   // namespace
 
 extern "C" size_t b200_decode_events_workspace_bytes(const b200_decode_desc* d) { return ws_layout(*d).total; }
+extern "C" size_t b200_decode_desc_bytes(void) { return sizeof(b200_decode_desc); }
 
 extern "C" int b200_decode_events(const b200_decode_desc* desc, int n_events, void* workspace, size_t workspace_bytes,
                                   cudaStream_t stream) {
@@ -922,14 +886,6 @@ extern "C" int b200_decode_events(const b200_decode_desc* desc, int n_events, vo
     t.dense_mask = d.dense_mask; t.lut = d.lut; t.n_event_types = d.n_event_types; t.eos_id = d.eos_id; t.pad_id = d.pad_id;
     t.temp = d.temp; t.top_p = d.top_p; t.top_k = d.top_k; t.batch = d.batch;
     t.prof = d.prof;
-    {
-        static int l2pf = -1;
-        if (l2pf < 0) {
-            const char* e = getenv("B200_DECODE_L2_PREFETCH");
-            l2pf = (e && e[0] == '0') ? 0 : 1;
-        }
-        t.l2_prefetch = l2pf;
-    }
     p.bar = (unsigned int*)(ws + L.bar);
     p.x = (bf16*)(ws + L.x); p.h = (bf16*)(ws + L.h); p.x2 = (bf16*)(ws + L.x2); p.h2 = (bf16*)(ws + L.h2);
     p.qkv = (bf16*)(ws + L.qkv); p.attn = (bf16*)(ws + L.attn); p.act = (bf16*)(ws + L.act);

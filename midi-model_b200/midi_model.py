@@ -710,7 +710,10 @@ class MIDIModel(PreTrainedModel):
                 hi = [rt.inner.seg_start]
 
                 def layer_done(li):
-                    if li % 3 == 0:
+                    # groups of three layers while a lot of backward is still ahead (fewer, larger collectives); the last
+                    # three layers one by one, so that only the first layer (33.5 MB) and the embedding table are still
+                    # to be reduced when the backward pass ends
+                    if li % 3 == 0 or li < 3:
                         lo = rt.outer.layer_range(li)[0]
                         grad_ready(lo, hi[0])
                         hi[0] = lo

@@ -314,3 +314,29 @@ def test_synth_batch_is_grammar_valid():
     for row in b[:, 1:-4].reshape(-1, 8).tolist():
         assert tok.tokens2event(row) != []
     assert torch.equal(b, synth_batch(tok, 3, 50, seed=1, pad_tail=4))
+
+
+def test_decode_descriptor_mirror_matches_the_header():
+    """The ctypes mirror of b200_decode_desc (persistent generate kernel) has the size the C compiler gives the struct, and
+    every field the header declares, in order."""
+    import ctypes
+    import re
+    from midi_b200 import lib
+    assert ctypes.sizeof(lib.DecodeDesc) == lib.query("b200_decode_desc_bytes")
+    hdr = open(os.path.join(ROOT, "include", "midi_b200.h")).read()
+    body = hdr[hdr.index("typedef struct b200_decode_desc {"):hdr.index("} b200_decode_desc;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for stmt in body.split("{", 1)[1].split(";"):
+        stmt = stmt.strip()
+        if not stmt:
+            continue
+        for part in stmt.split(","):
+            names.append(re.findall(r"[A-Za-z_][A-Za-z_0-9]*", part)[-1])
+    assert names == [f[0] for f in lib.DecodeDesc._fields_]
+
+
+def test_generate_loop_modes():
+    import midi_model as mm
+    assert mm._loop_mode("persist") == "persist"
+    assert mm._loop_mode("graph") is True and mm._loop_mode("nograph") is False and mm._loop_mode("eager") is False
