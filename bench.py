@@ -47,8 +47,9 @@ for p in (os.path.join(ROOT, "midi-model_b200"), ROOT):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the single JSON line
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ.pop("NCCL_DEBUG")           # (NCCL prints its version banner to stdout at VERSION and above: keep stdout
+                                           #  to the single JSON line; an explicitly requested WARN / INFO is left alone)
 
 import torch  # noqa: E402
 

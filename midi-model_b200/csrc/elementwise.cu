@@ -329,8 +329,11 @@ rmsnorm_fwd_warp_kernel(const bf16* __restrict__ x, const bf16* __restrict__ res
     }
 }
 
+// (Same register diet as the forward kernel: x and dy stay packed between the two passes and n = x*rstd, dn = dy*w are
+// recomputed -- identical fp32 operations -- instead of living in 64 fp32 registers; the norm weight is re-read from L1.
+// 157 -> ~100 registers, 3 -> 5 CTAs of 4 warps per SM.)
 template <int VPT>
-__global__ void __launch_bounds__(WRB_WARPS * 32)
+__global__ void __launch_bounds__(WRB_WARPS * 32, (VPT <= 4) ? 4 : 2)
 rmsnorm_bwd_warp_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
                         const float* __restrict__ rstd_in, const bf16* __restrict__ dres, bf16* __restrict__ dx,
                         float* __restrict__ dw_partial, int M) {
@@ -338,41 +341,53 @@ rmsnorm_bwd_warp_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
     extern __shared__ float wr_smem[];   // [WRB_WARPS][H]
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    float wv[VPT][8], dwacc[VPT][8];
+    float dwacc[VPT][8];
 #pragma unroll
-    for (int k = 0; k < VPT; k++) {
-        unpack8(*reinterpret_cast<const uint4*>(w + (lane + k * 32) * 8), wv[k]);
+    for (int k = 0; k < VPT; k++)
 #pragma unroll
         for (int j = 0; j < 8; j++) dwacc[k][j] = 0.f;
-    }
     for (int m = blockIdx.x * WRB_WARPS + warp; m < M; m += gridDim.x * WRB_WARPS) {
+        uint4 xp[VPT], dyp[VPT], rp[VPT];
+#pragma unroll
+        for (int k = 0; k < VPT; k++) {
+            xp[k] = ld_nc16(x + (size_t)m * H + (lane + k * 32) * 8);
+            dyp[k] = ld_nc16(dy + (size_t)m * H + (lane + k * 32) * 8);
+            if (dres) rp[k] = ld_nc16(dres + (size_t)m * H + (lane + k * 32) * 8);
+        }
         const float rstd = rstd_in[m];
-        float nn[VPT][8], dn[VPT][8];
         float dot = 0.f;
 #pragma unroll
         for (int k = 0; k < VPT; k++) {
-            float xv[8], dyv[8];
-            unpack8(ld_nc16(x + (size_t)m * H + (lane + k * 32) * 8), xv);
-            unpack8(ld_nc16(dy + (size_t)m * H + (lane + k * 32) * 8), dyv);
+            float xv[8], dyv[8], wv[8];
+            unpack8(xp[k], xv);
+            unpack8(dyp[k], dyv);
+            unpack8(*reinterpret_cast<const uint4*>(w + (lane + k * 32) * 8), wv);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                nn[k][j] = xv[j] * rstd;
-                dn[k][j] = dyv[j] * wv[k][j];
-                dot = fmaf(dn[k][j], nn[k][j], dot);
-                dwacc[k][j] = fmaf(dyv[j], nn[k][j], dwacc[k][j]);
+                const float nn = xv[j] * rstd;
+                const float dn = dyv[j] * wv[j];
+                dot = fmaf(dn, nn, dot);
+                dwacc[k][j] = fmaf(dyv[j], nn, dwacc[k][j]);
             }
         }
         dot = warp_sum(dot) / (float)H;
 #pragma unroll
         for (int k = 0; k < VPT; k++) {
-            float o[8];
-            if (dres) unpack8(ld_nc16(dres + (size_t)m * H + (lane + k * 32) * 8), o);
+            float o[8], xv[8], dyv[8], wv[8];
+            if (dres) unpack8(rp[k], o);
             else {
 #pragma unroll
                 for (int j = 0; j < 8; j++) o[j] = 0.f;
             }
+            unpack8(xp[k], xv);
+            unpack8(dyp[k], dyv);
+            unpack8(*reinterpret_cast<const uint4*>(w + (lane + k * 32) * 8), wv);
 #pragma unroll
-            for (int j = 0; j < 8; j++) o[j] += rstd * (dn[k][j] - nn[k][j] * dot);
+            for (int j = 0; j < 8; j++) {
+                const float nn = xv[j] * rstd;
+                const float dn = dyv[j] * wv[j];
+                o[j] += rstd * (dn - nn * dot);
+            }
             *reinterpret_cast<uint4*>(dx + (size_t)m * H + (lane + k * 32) * 8) = pack8(o);
         }
     }
@@ -641,7 +656,7 @@ static int rmsnorm_fwd_impl(const void* x, const void* res, const void* w, void*
     return B200_OK;
 }
 
-extern "C" int b200_rmsnorm_bwd_parts(void) { return b200_num_sms() * 3; }
+extern "C" int b200_rmsnorm_bwd_parts(void) { return b200_num_sms() * 4; }
 
 // workspace: float[b200_rmsnorm_bwd_parts() * H]
 extern "C" int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres,
