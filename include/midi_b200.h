@@ -60,7 +60,9 @@ int b200_rmsnorm_fwd(const void* x, const void* w, void* y, float* rstd /*may be
 int b200_add_rmsnorm_fwd(const void* x, const void* res, const void* w, void* h_out, void* y, float* rstd /*may be NULL*/,
                          int M, int H, float eps, cudaStream_t s);
 int b200_rmsnorm_bwd_parts(void);
-/* dx = dres + d(norm)/dx ; dw (+)= column sums.  workspace: float[b200_rmsnorm_bwd_parts() * H] */
+/* dx = dres + d(norm)/dx ; dw (+)= column sums.  workspace: float[b200_rmsnorm_bwd_parts() * H]; its first H + 1 words
+ * (fp32 accumulator row + arrival ticket of the fused column sum) must be ZERO when first handed in -- the kernel hands
+ * them back zeroed, so one cudaMemset at allocation is enough */
 int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres /*may be NULL*/,
                      void* dx, void* dw /*may be NULL*/, int M, int H, int accumulate_dw, void* workspace,
                      size_t workspace_bytes, cudaStream_t s);

@@ -336,7 +336,8 @@ template <int VPT>
 __global__ void __launch_bounds__(WRB_WARPS * 32, (VPT <= 4) ? 4 : 2)
 rmsnorm_bwd_warp_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
                         const float* __restrict__ rstd_in, const bf16* __restrict__ dres, bf16* __restrict__ dx,
-                        float* __restrict__ dw_partial, int M) {
+                        float* __restrict__ dw_acc, unsigned int* __restrict__ dw_ticket, bf16* __restrict__ dw,
+                        int accumulate_dw, int M) {
     constexpr int H = 256 * VPT;
     extern __shared__ float wr_smem[];   // [WRB_WARPS][H]
     const int lane = threadIdx.x & 31;
@@ -391,7 +392,11 @@ rmsnorm_bwd_warp_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
             *reinterpret_cast<uint4*>(dx + (size_t)m * H + (lane + k * 32) * 8) = pack8(o);
         }
     }
-    // block-level reduction of the per-warp dw partials, one partial row per CTA
+    // weight gradient: the warps' partials meet in shared memory, the CTA adds its column sums to ONE fp32 accumulator row
+    // in global memory (red.add), and the last CTA to finish (atomic ticket) rounds the row into dw and hands the
+    // accumulator back zeroed -- no second launch for the column sum (it was 32 launches, 0.35 ms per step).  The
+    // accumulation order over CTAs is not fixed; dw is a [H] vector whose fp32 sum is rounded to bf16 once.
+    if (dw == nullptr) return;
 #pragma unroll
     for (int k = 0; k < VPT; k++)
 #pragma unroll
@@ -401,7 +406,22 @@ rmsnorm_bwd_warp_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
         float t = 0.f;
 #pragma unroll
         for (int wi = 0; wi < WRB_WARPS; wi++) t += wr_smem[wi * H + c];
-        dw_partial[(size_t)blockIdx.x * H + c] = t;
+        atomicAdd(dw_acc + c, t);
+    }
+    __threadfence();
+    __syncthreads();
+    __shared__ int s_last;
+    if (threadIdx.x == 0) s_last = (atomicAdd(dw_ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        for (int c = threadIdx.x; c < H; c += blockDim.x) {
+            float t = __ldcg(dw_acc + c);
+            if (accumulate_dw) t = bf16_round(t) + __bfloat162float(dw[c]);
+            dw[c] = __float2bfloat16_rn(t);
+            dw_acc[c] = 0.f;
+        }
+        if (threadIdx.x == 0) *dw_ticket = 0u;
     }
 }
 
@@ -680,16 +700,12 @@ extern "C" int b200_rmsnorm_bwd(const void* dy, const void* x, const void* w, co
         }                                                                                                             \
         rmsnorm_bwd_warp_kernel<V><<<g, WRB_WARPS * 32, smem, stream>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, \
                                                                        rstd, (const bf16*)dres, (bf16*)dx,            \
-                                                                       (float*)workspace, M);                         \
+                                                                       (float*)workspace, (unsigned int*)((float*)workspace + H), \
+                                                                       (bf16*)dw, accumulate_dw, M);                  \
     } while (0)
         if (H == 256) B200_RMS_BWDW(1); else if (H == 512) B200_RMS_BWDW(2); else B200_RMS_BWDW(4);
 #undef B200_RMS_BWDW
         B200_CHECK_LAUNCH("rmsnorm_bwd");
-        if (dw) {
-            colsum_partial_kernel<<<(H + 31) / 32, dim3(32, 8), 0, stream>>>((const float*)workspace, g, H, (bf16*)dw,
-                                                                            accumulate_dw);
-            B200_CHECK_LAUNCH("rmsnorm_bwd_dw");
-        }
         return B200_OK;
     }
     const int vpt = (H / 8 + ROW_THREADS - 1) / ROW_THREADS;

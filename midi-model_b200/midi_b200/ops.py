@@ -17,12 +17,14 @@ _ws_cache: dict = {}
 GEMM_PROFILE = None   # bench.py sets this to a list: (start_event, end_event, flops) per tensor-core GEMM launch
 
 
-def _ws(key, nbytes: int, device) -> torch.Tensor:
-    """Per-(key, device, stream) byte workspace, grown on demand (kernels are stream-ordered)."""
+def _ws(key, nbytes: int, device, zero: bool = False) -> torch.Tensor:
+    """Per-(key, device, stream) byte workspace, grown on demand (kernels are stream-ordered).  `zero`: zero-filled when
+    (re)allocated, for kernels that keep a self-cleaning accumulator / ticket in it."""
     k = (key, device.index, torch.cuda.current_stream().cuda_stream)
     t = _ws_cache.get(k)
     if t is None or t.numel() < nbytes:
-        t = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        alloc = torch.zeros if zero else torch.empty
+        t = alloc(max(nbytes, 256), dtype=torch.uint8, device=device)
         _ws_cache[k] = t
     return t
 
@@ -103,7 +105,7 @@ def rmsnorm_bwd(dy, x, w, rstd, dres, dw, accumulate_dw: bool) -> torch.Tensor:
     M, H = x.shape
     dx = torch.empty_like(x)
     parts = lib.query("b200_rmsnorm_bwd_parts")
-    ws = _ws("rms_bwd", parts * H * 4, x.device)
+    ws = _ws("rms_bwd", parts * H * 4, x.device, zero=True)
     lib.call("b200_rmsnorm_bwd", dy.data_ptr(), x.data_ptr(), w.data_ptr(), rstd.data_ptr(), lib.ptr(dres), dx.data_ptr(),
              lib.ptr(dw), M, H, int(accumulate_dw), ws.data_ptr(), ws.numel(), lib.stream())
     return dx
