@@ -847,6 +847,38 @@ def check_model_peaked_greedy():
     out["stream_masked_differs_from_plain"] = float((ids_masked[:, :min(ids_masked.shape[1], ids_stream.shape[1])]
                                                      != ids_stream[:, :min(ids_masked.shape[1], ids_stream.shape[1])]).sum())
     print("stream: disabled channels", chans, "masked events", ids_masked.shape[1], "plain events", ids_stream.shape[1])
+    # two generations streaming concurrently from two threads on ONE model (gradio serves app.generate from worker threads,
+    # app.py:496): each owns its loop state, so both must reproduce their sequential results; a generator resumed from
+    # another thread than the one that created it must work too
+    import threading
+    prompt_b = _song_batch(tok, 4, 9, seed=321).numpy()
+    seq_a = np.stack(list(model.generate_stream(prompt=prompt, batch_size=4, max_len=30, top_k=1)), axis=1)
+    seq_b = np.stack(list(model.generate_stream(prompt=prompt_b, batch_size=4, max_len=30, top_k=1)), axis=1)
+    got, errs = {}, []
+
+    def drive(name, pr):
+        try:
+            got[name] = np.stack(list(model.generate_stream(prompt=pr, batch_size=4, max_len=30, top_k=1)), axis=1)
+        except Exception as e:     # noqa: BLE001
+            errs.append(repr(e))
+    th = [threading.Thread(target=drive, args=("a", prompt)), threading.Thread(target=drive, args=("b", prompt_b))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    out["stream_concurrent_errors"] = float(len(errs))
+    out["stream_concurrent_mismatch"] = (float((got["a"] != seq_a).sum() + (got["b"] != seq_b).sum())
+                                         if not errs and got["a"].shape == seq_a.shape and got["b"].shape == seq_b.shape else 1e9)
+    gen = model.generate_stream(prompt=prompt, batch_size=4, max_len=30, top_k=1)
+    first = next(gen)
+    rest = []
+    t2 = threading.Thread(target=lambda: rest.extend(list(gen)))
+    t2.start()
+    t2.join()
+    moved = np.stack([first] + rest, axis=1)
+    out["stream_resumed_on_other_thread_mismatch"] = float((moved != seq_a).sum()) if moved.shape == seq_a.shape else 1e9
+    if errs:
+        print("concurrent stream errors:", errs)
     ids_after = model.generate(prompt=prompt, batch_size=4, max_len=40, top_k=1)      # the mask must not leak into generate()
     out["stream_mask_leak_mismatch"] = float((ids_after != ids_new).sum()) if ids_after.shape == ids_new.shape else 1e9
     # the generated continuation is itself grammar-valid
@@ -1311,7 +1343,8 @@ THRESH = [
     ("autograd_grad_global_rel", 6e-2),
     ("cached_vs_full_hidden", 3e-2), ("inner_cached_vs_full_logits", 3e-2), ("min:greedy_token_agree", 0.6),
     ("min:lazy_ce_hits", 1.0), ("xy_split_mismatch", 0.0), ("prefetch_mismatch", 0.0), ("int16_path_loss_mismatch", 0.0), ("int16_path_grad_rel", 1e-3), ("stream_vs_generate_mismatch", 0.0), ("stream_masked_mismatch", 0.0), ("stream_denied_ids_emitted", 0.0),
-    ("stream_mask_leak_mismatch", 0.0), ("peaked_greedy_mismatch", 0.0), ("peaked_eager_vs_graph_mismatch", 0.0), ("peaked_invalid_events", 0.0), ("peaked_loss_last", 1.5),
+    ("stream_mask_leak_mismatch", 0.0), ("stream_concurrent_errors", 0.0), ("stream_concurrent_mismatch", 0.0),
+    ("stream_resumed_on_other_thread_mismatch", 0.0), ("peaked_greedy_mismatch", 0.0), ("peaked_eager_vs_graph_mismatch", 0.0), ("peaked_invalid_events", 0.0), ("peaked_loss_last", 1.5),
     ("peaked_argmax_mismatch_vs_fp32", 0.0), ("peaked_logits_vs_fp32", 3e-2),
     ("sampled_invalid_events", 0.0), ("greedy_graph_vs_nograph_mismatch", 0.0), ("fused_decode_mismatch", 0.0), ("fused_lm_head_mismatch", 0.0),
 ]

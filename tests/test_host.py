@@ -340,3 +340,32 @@ def test_generate_loop_modes():
     import midi_model as mm
     assert mm._loop_mode("persist") == "persist"
     assert mm._loop_mode("graph") is True and mm._loop_mode("nograph") is False and mm._loop_mode("eager") is False
+
+
+def test_paged_kv_grow_keeps_cached_positions():
+    """PagedKV.grow (contexts past max_position_embeddings: app.py's prompt + 4096 new events): after re-allocation every
+    cached (row, head, position) is found through the new block table where it was before."""
+    import torch
+    from midi_b200.decode import PagedKV
+    from midi_b200.engine import StackCfg
+    cfg = StackCfg("net", 2, 4, 32, 64, 1e-6)          # 2 layers, 4 heads of 8
+    kv = PagedKV(cfg, batch=3, capacity=20, page=8, device="cpu")
+    assert kv.capacity == 24 and kv.max_pages == 3
+    g = torch.Generator().manual_seed(0)
+    for pools in (kv.k, kv.v):
+        for li in range(cfg.n_layer):
+            pools[li].copy_(torch.randn(pools[li].shape, generator=g).to(torch.bfloat16))
+
+    def gather(pool, bt, page, b, h, t):
+        return pool[int(bt[b, t // page]), h, t % page].clone()
+
+    before = {(li, b, h, t): (gather(kv.k[li], kv.block_table, 8, b, h, t), gather(kv.v[li], kv.block_table, 8, b, h, t))
+              for li in range(2) for b in range(3) for h in range(4) for t in (0, 7, 8, 19)}
+    kv.length = 20
+    kv.grow(25)
+    assert kv.capacity >= 48 and kv.capacity % 8 == 0 and kv.block_table.shape == (3, kv.max_pages) and kv.length == 20
+    for (li, b, h, t), (k0, v0) in before.items():
+        assert torch.equal(gather(kv.k[li], kv.block_table, 8, b, h, t), k0)
+        assert torch.equal(gather(kv.v[li], kv.block_table, 8, b, h, t), v0)
+    kv.grow(10)                                          # no-op
+    assert kv.capacity >= 48
