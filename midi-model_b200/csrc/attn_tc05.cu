@@ -45,6 +45,7 @@ struct FwdParams {
     bf16* o;
     float* lse;
     long long o_b, o_r;          // element strides of the output: batch, row (heads are contiguous blocks of 64)
+    int batch;
     int n_heads, Sq, Sk, H;      // H = columns between the q, k and v thirds when packed (used for TMA column coords)
     int q_col0, k_col0, v_col0;  // first column of head 0 in each tensor map
     float scale;
@@ -268,6 +269,7 @@ constexpr int F2_SMEM = F2_BAR + 256;
 __global__ void __launch_bounds__(F2_THREADS, 1)
 attn_fwd_tc05_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
+    B200_PDL_TRIGGER();
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F2_BAR);
     uint64_t* q_full = bars + 0;
@@ -460,6 +462,320 @@ attn_fwd_tc05_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         tmem_dealloc(tmem_base, 512);
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// forward, third generation (default): persistent, two query tiles per CTA, thread = one query row.
+//   * grid = one CTA per SM; every CTA walks a static, length-balanced list of work items (snake order over the items sorted
+//     longest first).  An item = two adjacent 128-row query tiles of one (batch, head); both tiles consume the same K/V
+//     stream, so every K/V tile is staged once for 256 query rows.
+//   * two softmax groups of 4 warps (one per query tile); a thread owns a whole row of the 128-key score tile, so the row
+//     maximum and the row sum never leave its registers (no shared-memory exchange, no named barriers).  The two groups
+//     sit pairwise on the four SM sub-partitions and drift out of phase, so one group's MUFU burst overlaps the other's
+//     max / convert / store work.
+//   * the output accumulates in TMEM (P.V with the accumulate flag); it is rescaled in place only when a row's maximum has
+//     grown by more than 2^8 since the reference maximum was taken (lazy rescale: with a stale maximum the probabilities
+//     are at most 256, exact in fp32 and harmless in bf16), which in practice happens on the first tiles of a row only.
+//   * one MMA-issuing warp per group: S_{j+1} = Q.K^T is issued as soon as the group has read S_j out of TMEM, P.V_j when
+//     P_j is in shared memory.  K/V stages are released when both groups' MMAs on them have retired.
+//   warp 0: TMA producer   warps 1, 2: MMA issuers of group 0 / 1   warp 3: TMEM allocator   warps 4..7 / 8..11: softmax
+// ---------------------------------------------------------------------------------------------
+constexpr int F3_THREADS = 384;
+constexpr int F3_KVS = 4;                                 // K/V stages
+constexpr int F3_Q = 0;                                   // 2 x 16 KB
+constexpr int F3_P = 32768;                               // 2 x 32 KB (one P tile per group)
+constexpr int F3_KV = F3_P + 2 * 32768;                   // F3_KVS x (K 16 KB + V 16 KB)
+constexpr int F3_BAR = F3_KV + F3_KVS * 32768;
+constexpr int F3_SMEM = F3_BAR + 256;
+constexpr float F3_RESCALE_LOG2 = 8.f;
+
+struct F3Item {
+    int b, h;
+    int q0[2], n[2], nt;      // first query row and number of K/V tiles of each group (0 = group idle), max of the two
+};
+
+__device__ __forceinline__ bool f3_item(const FwdParams& p, int round, F3Item& it) {
+    const int n_qt = (p.Sq + BQ - 1) / BQ, n_pairs = (n_qt + 1) >> 1;
+    const int n_bh = p.batch * p.n_heads;
+    const int G = gridDim.x, c = blockIdx.x;
+    const long long idx = (long long)round * G + ((round & 1) ? G - 1 - c : c);
+    if (idx >= (long long)n_pairs * n_bh) return false;
+    const int pt = n_pairs - 1 - (int)(idx / n_bh);           // long (late) tile pairs first
+    const int bh = (int)(idx % n_bh);
+    it.b = bh / p.n_heads; it.h = bh % p.n_heads;
+    const int off = p.Sk - p.Sq;
+    it.nt = 0;
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+        const int qt = 2 * pt + g;
+        it.q0[g] = qt * BQ;
+        int n = 0;
+        if (qt < n_qt) {
+            n = min((p.Sk + BK - 1) / BK, (it.q0[g] + BQ - 1 + off) / BK + 1);
+            if (n < 1) n = 1;
+        }
+        it.n[g] = n;
+        it.nt = max(it.nt, n);
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(F3_THREADS, 1)
+attn_fwd_tc05_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
+    B200_PDL_TRIGGER();
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F3_BAR);
+    uint64_t* kv_full = bars + 0;      // [F3_KVS]
+    uint64_t* kv_empty = bars + 4;     // [F3_KVS]  one arrival per MMA warp
+    uint64_t* q_full = bars + 8;       // [2]
+    uint64_t* q_empty = bars + 10;     // [2]
+    uint64_t* s_full = bars + 12;      // [2]
+    uint64_t* s_empty = bars + 14;     // [2]  4 softmax warps
+    uint64_t* p_full = bars + 16;      // [2]  4 softmax warps
+    uint64_t* pv_done = bars + 18;     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_rounds = (int)(((long long)((p.Sq + BQ - 1) / BQ + 1) / 2 * p.batch * p.n_heads + gridDim.x - 1) / gridDim.x);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
+        for (int s = 0; s < F3_KVS; s++) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }
+        for (int g = 0; g < 2; g++) {
+            mbar_init(&q_full[g], 1); mbar_init(&q_empty[g], 1); mbar_init(&s_full[g], 1); mbar_init(&s_empty[g], 4);
+            mbar_init(&p_full[g], 4); mbar_init(&pv_done[g], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 3) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t T = 0, cq[2] = {0, 0};
+            F3Item it;
+            for (int r = 0; r < n_rounds; r++) {
+                if (!f3_item(p, r, it)) continue;
+#pragma unroll
+                for (int g = 0; g < 2; g++) {
+                    if (it.n[g] == 0) continue;
+                    mbar_wait(&q_empty[g], (cq[g] & 1) ^ 1);
+                    mbar_expect_tx(&q_full[g], BQ * D * 2);
+                    tma_load_3d(smem + F3_Q + g * 16384, &tmQ, &q_full[g], p.q_col0 + it.h * D, it.q0[g], it.b);
+                    cq[g]++;
+                }
+                for (int j = 0; j < it.nt; j++, T++) {
+                    const int st = T % F3_KVS;
+                    mbar_wait(&kv_empty[st], ((T / F3_KVS) & 1) ^ 1);
+                    uint8_t* sK = smem + F3_KV + st * 32768;
+                    mbar_expect_tx(&kv_full[st], 2 * BK * D * 2);
+                    tma_load_3d(sK, &tmK, &kv_full[st], p.k_col0 + it.h * D, j * BK, it.b);
+                    tma_load_3d(sK + 16384, &tmV, &kv_full[st], p.v_col0 + it.h * D, j * BK, it.b);
+                }
+            }
+        }
+    } else if (warp == 1 || warp == 2) {
+        if (lane == 0) {
+            const int g = warp - 1;
+            constexpr uint32_t idesc_s = make_idesc(BQ, BK, false, false);    // S[128 x 128] = Q . K^T
+            constexpr uint32_t idesc_pv = make_idesc(BQ, D, false, true);     // O[128 x 64] += P . V (V is [keys, d]: MN-major B)
+            const uint32_t tS = tmem_base + g * 128, tO = tmem_base + 256 + g * 64;
+            const uint64_t dQ0 = make_smem_desc(smem_u32(smem + F3_Q + g * 16384), 16, 1024);
+            const uint64_t dP0 = make_smem_desc(smem_u32(smem + F3_P + g * 32768), 16, 1024);
+            uint32_t T = 0, tg = 0, cq = 0;
+            auto issue_s = [&](uint32_t Tj) {               // S = Q . K_j^T of the K/V tile with running index Tj
+                const int st = Tj % F3_KVS;
+                mbar_wait(&kv_full[st], (Tj / F3_KVS) & 1);
+                const uint64_t dK0 = make_smem_desc(smem_u32(smem + F3_KV + st * 32768), 16, 1024);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < D / 16; k++) umma_f16(tS, desc_adv(dQ0, k * 32), desc_adv(dK0, k * 32), idesc_s, k > 0);
+                umma_commit(&s_full[g]);
+            };
+            F3Item it;
+            for (int r = 0; r < n_rounds; r++) {
+                if (!f3_item(p, r, it)) continue;
+                const int n = it.n[g];
+                if (n > 0) { mbar_wait(&q_full[g], cq & 1); cq++; }
+                for (int j = 0; j < it.nt; j++, T++) {
+                    const int st = T % F3_KVS;
+                    if (j < n) {
+                        if (j == 0) {
+                            if (tg > 0) mbar_wait(&s_empty[g], (tg - 1) & 1);      // last tile of the previous item read out
+                            issue_s(T);
+                            if (n == 1) umma_commit(&q_empty[g]);
+                        }
+                        if (j + 1 < n) {                                           // S_{j+1} first: the group never waits for it
+                            mbar_wait(&s_empty[g], tg & 1);
+                            issue_s(T + 1);
+                            if (j + 2 == n) umma_commit(&q_empty[g]);
+                        }
+                        mbar_wait(&p_full[g], tg & 1);
+                        tc_fence_after();
+                        const uint64_t dV0 = make_smem_desc(smem_u32(smem + F3_KV + st * 32768 + 16384), 16384, 1024);
+#pragma unroll
+                        for (int kk = 0; kk < BK / 16; kk++)
+                            umma_f16(tO, desc_adv(dP0, (kk >> 2) * 16384 + (kk & 3) * 32), desc_adv(dV0, kk * 2048), idesc_pv,
+                                     (j > 0 || kk > 0) ? 1u : 0u);
+                        umma_commit(&pv_done[g]);
+                        umma_commit(&kv_empty[st]);
+                        tg++;
+                    } else {
+                        mbar_wait(&kv_full[st], (T / F3_KVS) & 1);                 // the other group's tile: just pass the stage on
+                        mbar_arrive(&kv_empty[st]);
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        const int g = (warp - 4) >> 2;
+        const int quarter = warp & 3;
+        const int row_t = quarter * 32 + lane;            // row inside the tile == TMEM lane
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        const uint32_t tS = tmem_base + g * 128 + lane_addr, tO = tmem_base + 256 + g * 64 + lane_addr;
+        const float sl2 = p.scale * LOG2E;
+        const int off = p.Sk - p.Sq;
+        uint8_t* sP = smem + F3_P + g * 32768;
+        uint32_t tg = 0;
+        F3Item it;
+        for (int r = 0; r < n_rounds; r++) {
+            if (!f3_item(p, r, it)) continue;
+            const int n = it.n[g];
+            if (n == 0) continue;
+            const int q0 = it.q0[g], row = q0 + row_t;
+            float m_ref = -INFINITY, l_i = 0.f;
+            for (int j = 0; j < n; j++, tg++) {
+                const int k0 = j * BK;
+                const bool need_mask = (k0 + BK - 1 > q0 + off) || (k0 + BK > p.Sk);
+                const int lim0 = min(row + off, p.Sk - 1) - k0;     // last visible column of this row in the tile
+                mbar_wait(&s_full[g], tg & 1);
+                tc_fence_after();
+                uint32_t rr[2][32];
+                // ---- pass 1: row maximum
+                float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                tmem_ld32(tS, rr[0]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    if (c < 3) tmem_ld32(tS + (c + 1) * 32, rr[(c + 1) & 1]);
+                    if (need_mask) {
+                        const int lim = lim0 - c * 32;
+#pragma unroll
+                        for (int i = 0; i < 32; i++)
+                            mx4[i & 3] = fmaxf(mx4[i & 3], (i > lim) ? -INFINITY : __uint_as_float(rr[c & 1][i]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i++) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(rr[c & 1][i]));
+                    }
+                    if (c < 3) tmem_ld_wait();
+                }
+                const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+                // ---- reference maximum; P buffer and O are free / stable once P.V of the previous tile has retired
+                const bool need = (mx - m_ref) * sl2 > F3_RESCALE_LOG2;       // true on the first tile (m_ref = -inf)
+                if (j > 0) {
+                    mbar_wait(&pv_done[g], (tg - 1) & 1);
+                    tc_fence_after();
+                }
+                if (__any_sync(0xffffffffu, need)) {
+                    const float m_new = need ? mx : m_ref;
+                    if (j > 0) {
+                        const float alpha = need ? exp2f((m_ref - m_new) * sl2) : 1.f;
+#pragma unroll
+                        for (int c = 0; c < 2; c++) {
+                            tmem_ld32(tO + c * 32, rr[0]);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; i++) rr[0][i] = __float_as_uint(__uint_as_float(rr[0][i]) * alpha);
+                            tmem_st32(tO + c * 32, rr[0]);
+                        }
+                        tmem_st_wait();
+                        l_i *= alpha;
+                    }
+                    m_ref = m_new;
+                }
+                const float msc = m_ref * sl2;
+                // ---- pass 2: probabilities -> bf16 -> swizzled P tile in shared memory
+                float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+                tmem_ld32(tS, rr[0]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    if (c < 3) tmem_ld32(tS + (c + 1) * 32, rr[(c + 1) & 1]);
+                    uint32_t pk[16];
+                    if (need_mask) {
+                        const int lim = lim0 - c * 32;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            const float p0 = (i > lim) ? 0.f : ex2_approx(fmaf(__uint_as_float(rr[c & 1][i]), sl2, -msc));
+                            const float p1 = (i + 1 > lim) ? 0.f : ex2_approx(fmaf(__uint_as_float(rr[c & 1][i + 1]), sl2, -msc));
+                            rs4[(i >> 1) & 3] += p0 + p1;
+                            pk[i >> 1] = pack2(p0, p1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            const float p0 = ex2_approx(fmaf(__uint_as_float(rr[c & 1][i]), sl2, -msc));
+                            const float p1 = ex2_approx(fmaf(__uint_as_float(rr[c & 1][i + 1]), sl2, -msc));
+                            rs4[(i >> 1) & 3] += p0 + p1;
+                            pk[i >> 1] = pack2(p0, p1);
+                        }
+                    }
+                    // keys c*32 .. +31 of this row: atom (c >> 1), 16-byte chunks (c & 1) * 4 .. + 3
+                    uint8_t* rowp = sP + (c >> 1) * 16384 + row_t * 128;
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+                        const int chunk = (c & 1) * 4 + v;
+                        *reinterpret_cast<uint4*>(rowp + ((chunk ^ (row_t & 7)) << 4)) =
+                            make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+                    }
+                    if (c < 3) tmem_ld_wait();
+                    if (c == 2) {                      // the whole S tile is in registers: the tensor pipe may overwrite it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&s_empty[g]);
+                    }
+                }
+                l_i += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[g]);
+            }
+            // ---- epilogue of the item: O / l -> bf16
+            mbar_wait(&pv_done[g], (tg - 1) & 1);
+            tc_fence_after();
+            const float inv = l_i > 0.f ? 1.f / l_i : 0.f;
+            bf16* dst = p.o + it.b * p.o_b + (long long)row * p.o_r + it.h * D;
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                uint32_t r[32];
+                tmem_ld32(tO + c * 32, r);
+                tmem_ld_wait();
+                if (row < p.Sq) {
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+                        float f[8];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) f[i] = __uint_as_float(r[v * 8 + i]) * inv;
+                        *reinterpret_cast<uint4*>(dst + c * 32 + v * 8) = pack8(f);
+                    }
+                }
+            }
+            if (p.lse && row < p.Sq) p.lse[((long long)it.b * p.n_heads + it.h) * p.Sq + row] = m_ref * p.scale + logf(l_i);
+            // the next item's first P.V (accumulate = 0) overwrites O only after this thread's p_full arrival: ordered
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 3) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
 }   // namespace
 
 // 3-D bf16 tensor map {cols, rows per sequence, batch} with 128B swizzle: rows outside a sequence are zero-filled
@@ -485,18 +801,26 @@ extern "C" int b200_attn_causal_fwd_tc(const void* q, const void* k, const void*
     if ((rc = tc05_make_tmap_3d(&tmV, v, W, Sk, batch, strides[7], strides[6], D, BK))) return rc;
     FwdParams p;
     p.o = (bf16*)o; p.lse = lse; p.o_b = strides[9]; p.o_r = strides[10];
-    p.n_heads = n_heads; p.Sq = Sq; p.Sk = Sk; p.H = (int)W;
+    p.batch = batch; p.n_heads = n_heads; p.Sq = Sq; p.Sk = Sk; p.H = (int)W;
     p.q_col0 = p.k_col0 = p.v_col0 = 0;
     p.scale = scale;
     static int gen = 0;
     if (!gen) {
-        // B200_ATTN_FWD_TC=v1 selects the first-generation kernel (4 softmax warps, 2 CTAs per SM)
+        // B200_ATTN_FWD_TC=v1 / v2 select the earlier generations (see the file header)
         const char* e = getenv("B200_ATTN_FWD_TC");
-        gen = (e && !strcmp(e, "v1")) ? 1 : 2;
+        gen = (e && !strcmp(e, "v1")) ? 1 : (e && !strcmp(e, "v2")) ? 2 : 3;
         B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES), "attn_tc smem");
         B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc05_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                        cudaSharedmemCarveoutMaxShared), "attn_tc carveout");
         B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc05_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM), "attn_tc v2 smem");
+        B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc05_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM), "attn_tc v3 smem");
+    }
+    if (gen == 3) {
+        const long long items = (long long)(((Sq + BQ - 1) / BQ + 1) / 2) * batch * n_heads;
+        const int g3 = (int)(items < b200_num_sms() ? items : b200_num_sms());
+        attn_fwd_tc05_v3_kernel<<<g3, F3_THREADS, F3_SMEM, stream>>>(tmQ, tmK, tmV, p);
+        B200_CHECK_LAUNCH("attn_causal_fwd_tc");
+        return B200_OK;
     }
     dim3 grid(batch * n_heads, (Sq + BQ - 1) / BQ);   // tiles on the slow index: longest first across all heads
     if (gen == 2) attn_fwd_tc05_v2_kernel<<<grid, F2_THREADS, F2_SMEM, stream>>>(tmQ, tmK, tmV, p);
@@ -1105,6 +1429,7 @@ attn_bwd_dq_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 __global__ void attn_bwd_dq_finalize_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, long long rows, int W, int ld,
                                             int S, float scale, const bf16* __restrict__ rope_cos,
                                             const bf16* __restrict__ rope_sin) {
+    B200_PDL_TRIGGER();
     // one thread = 8 columns d0..d0+7 of the first half of a head and the matching 8 of the second half
     const long long n = rows * (W / 16);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {

@@ -88,6 +88,7 @@ template <int L>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 tiny_attn_fwd_kernel(bf16* __restrict__ qkv, bf16* __restrict__ out, int n_events, int n_heads, int ld_qkv, int ld_out,
                      float scale, const bf16* __restrict__ rope_cos, const bf16* __restrict__ rope_sin) {
+    B200_PDL_TRIGGER();
     const int wid = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
     if (wid >= n_events * n_heads) return;
     const int lane = threadIdx.x & 31;
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 tiny_attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_out, bf16* __restrict__ dqkv, int n_events,
                      int n_heads, int ld_qkv, int ld_out, float scale, const bf16* __restrict__ rope_cos,
                      const bf16* __restrict__ rope_sin) {
+    B200_PDL_TRIGGER();
     const int wid = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
     if (wid >= n_events * n_heads) return;
     const int lane = threadIdx.x & 31;

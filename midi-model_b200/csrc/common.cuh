@@ -55,6 +55,14 @@ void b200_count_launches(int n);
 
 int b200_num_sms();
 
+// Programmatic dependent launch (PDL).  Kernels that run right before a tensor-core GEMM execute
+// `griddepcontrol.launch_dependents` first thing: a GEMM launched with the programmatic-serialization attribute may then be
+// scheduled onto SMs as they drain and run its prologue (barrier init, TMEM allocation, tensor-map prefetch) under this
+// kernel's tail; it touches no memory before its own `griddepcontrol.wait`, which returns only once this grid has completed
+// and flushed.  Without the launch attribute on the next kernel both instructions are no-ops.
+#define B200_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define B200_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+
 // ---------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------

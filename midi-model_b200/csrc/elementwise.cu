@@ -288,6 +288,7 @@ template <int VPT>
 __global__ void __launch_bounds__(WR_WARPS * 32, (VPT <= 4) ? 4 : 2)
 rmsnorm_fwd_warp_kernel(const bf16* __restrict__ x, const bf16* __restrict__ res, const bf16* __restrict__ w,
                         bf16* __restrict__ h_out, bf16* __restrict__ y, float* __restrict__ rstd_out, int M, float eps) {
+    B200_PDL_TRIGGER();
     constexpr int H = 256 * VPT;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -338,6 +339,7 @@ rmsnorm_bwd_warp_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                         const float* __restrict__ rstd_in, const bf16* __restrict__ dres, bf16* __restrict__ dx,
                         float* __restrict__ dw_acc, unsigned int* __restrict__ dw_ticket, bf16* __restrict__ dw,
                         int accumulate_dw, int M) {
+    B200_PDL_TRIGGER();
     constexpr int H = 256 * VPT;
     extern __shared__ float wr_smem[];   // [WRB_WARPS][H]
     const int lane = threadIdx.x & 31;
@@ -519,6 +521,7 @@ __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict_
 // dg = dact * u * silu'(g), du = dact * silu(g)
 __global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, const bf16* __restrict__ dact, bf16* __restrict__ dgu,
                                   size_t rows, int I) {
+    B200_PDL_TRIGGER();
     const size_t nvec = rows * (size_t)(I / 8);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
         const size_t r = i / (I / 8);

@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(num_threads(EG), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
     using L = SmemLayout<BLOCK_N, CG>;
+    B200_PDL_TRIGGER();
     // CTA pair: this CTA's rank in its 2-CTA cluster (0 = leader: issues the MMAs, owns the full / tmem-empty barriers)
     const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
     const bool leader_cta = rank == 0;
@@ -137,6 +138,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (CG == 2) cluster_sync_all();             // the peer's barriers exist before anything arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above (barriers, TMEM, tensor-map prefetch) may have run under the previous kernel's tail (PDL); from
+    // here on this kernel reads and writes global memory
+    B200_PDL_WAIT();
 
     const int total_items = p.total_items;
 
@@ -602,27 +606,40 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
         configured = true;
     }
     const int items = p.total_items;
+    static int pdl = -1;
+    if (pdl < 0) {
+        // B200_PDL=1: programmatic dependent launch of the GEMMs.  Measured neutral on the train step (51.1/51.8 ms off,
+        // 51.3/51.8 ms on, same box, profiles/r2_pdl_ab.txt): the GEMM prologue is ~2 us of a >=100 us kernel and the
+        // producer kernels' tails are short, so it stays off by default.
+        const char* e = getenv("B200_PDL");
+        pdl = (e && e[0] == '1') ? 1 : 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(num_threads(EG));
+    cfg.dynamicSmemBytes = L::TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int n_attr = 0;
     if (CG == 1) {
-        const int grid = items < b200_num_sms() ? items : b200_num_sms();
-        kern<<<grid, num_threads(EG), L::TOTAL, stream>>>(tmA, tmB, tmC, tmD, p);
+        cfg.gridDim = dim3(items < b200_num_sms() ? items : b200_num_sms());
     } else {
         // CTA pairs: clusters of two CTAs (same TPC), one 256-row tile pair per cluster at a time
         const int pairs = b200_num_sms() / 2;
-        const int grid = 2 * (items < pairs ? items : pairs);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(num_threads(EG));
-        cfg.dynamicSmemBytes = L::TOTAL;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        B200_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmD, p), "gemm pair launch");
+        cfg.gridDim = dim3(2 * (items < pairs ? items : pairs));
+        attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+        attr[n_attr].val.clusterDim.x = 2;
+        attr[n_attr].val.clusterDim.y = 1;
+        attr[n_attr].val.clusterDim.z = 1;
+        n_attr++;
     }
+    if (pdl) {
+        attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+        n_attr++;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n_attr;
+    B200_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmD, p), "gemm launch");
     B200_CHECK_LAUNCH("gemm_tcgen05");
     return B200_OK;
 }

@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(CE_THREADS)
 ce_bwd_kernel(bf16* __restrict__ logits, const long long* __restrict__ targets, const float* __restrict__ lse_in,
               const float* __restrict__ loss_and_count, int V, int ld, int n_cols_store, long long ignore_index,
               float gscale, const void* __restrict__ gscale_dev, int gscale_is_bf16) {
+    B200_PDL_TRIGGER();
     // upstream d(loss) as a device scalar (autograd hands it over as a tensor: no host sync to read it)
     if (gscale_dev) gscale *= gscale_is_bf16 ? __bfloat162float(*reinterpret_cast<const bf16*>(gscale_dev))
                                              : *reinterpret_cast<const float*>(gscale_dev);
