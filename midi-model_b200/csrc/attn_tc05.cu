@@ -1,11 +1,14 @@
 // Causal attention for the event-level stack on the 5th-gen tensor cores (head_dim 64), forward and backward:
 // every matmul is tcgen05.mma with accumulators in TMEM, Q / K / V / dO tiles are staged by TMA (cp.async.bulk.tensor.3d,
 // 128B swizzle, zero fill outside the sequence) straight from the packed [rows, 3*hidden] QKV activation, and the
-// fp32 softmax math runs on 16 warps that exchange tiles with the single MMA-issuing thread through mbarriers.
-//   warp 0 : TMA producer      warp 1 : TMEM allocator + MMA issuer      warps 2..17 : math / epilogue
-// Kernels, in file order:
-//   attn_fwd_tc05_kernel      first-generation forward (4 softmax warps, thread = query row, 2 CTAs/SM); B200_ATTN_FWD_TC=v1
-//   attn_fwd_tc05_v2_kernel   default forward: 1 CTA/SM, thread = row x 32 keys, S / P / PV double-buffered
+// fp32 softmax math runs on dedicated warps that exchange tiles with the MMA-issuing thread(s) through mbarriers.
+// Kernels, in file order (forward generations are selected with B200_ATTN_FWD_TC=v1|v2|v3|v4, default v3):
+//   attn_fwd_tc05_kernel      v1: 4 softmax warps, thread = query row, 2 CTAs/SM
+//   attn_fwd_tc05_v2_kernel   v2: 1 CTA/SM, thread = row x 32 keys, S / P / PV double-buffered, output folded in registers (0.190 ms)
+//   attn_fwd_tc05_v3_kernel   v3 (default): persistent, two query tiles per CTA, thread = row, O in TMEM with a lazy rescale,
+//                             ping-pong between the two softmax groups (0.147-0.155 ms per layer at B=8, S=2048)
+//   attn_fwd_tc05_v4_kernel   v4: v3 with two threads per row (16 softmax warps, setmaxnreg); measured equal to v3, kept as
+//                             the record of that experiment
 //   attn_bwd_tc05_kernel<M>   default backward (dK, dV and -- M = 2 -- dQ through a TMA reduce-add), half-tile pipeline
 //   attn_bwd_dq_tc05_kernel   atomic-free dQ for the `split` variant;  attn_bwd_dq_finalize_kernel: fp32 dQ -> bf16
 // Semantics = hf sdpa_attention.py:92-101 (causal, scale d^-1/2): online softmax in fp32, P rounded to bf16
@@ -49,6 +52,7 @@ struct FwdParams {
     int n_heads, Sq, Sk, H;      // H = columns between the q, k and v thirds when packed (used for TMA column coords)
     int q_col0, k_col0, v_col0;  // first column of head 0 in each tensor map
     float scale;
+    long long* dbg;              // forward v3 phase profile (NULL = off)
 };
 
 __global__ void __launch_bounds__(NTHREADS, 2)
@@ -463,6 +467,7 @@ attn_fwd_tc05_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
 }
 
+
 // ---------------------------------------------------------------------------------------------
 // forward, third generation (default): persistent, two query tiles per CTA, thread = one query row.
 //   * grid = one CTA per SM; every CTA walks a static, length-balanced list of work items (snake order over the items sorted
@@ -519,6 +524,10 @@ __device__ __forceinline__ bool f3_item(const FwdParams& p, int round, F3Item& i
     return true;
 }
 
+// PINGPONG: the two softmax warps that share an SM sub-partition (same row quarter, different group) take turns in the
+// MUFU-bound half of a tile (pass 2) through a pair of 64-thread named barriers, so that one warp's exponentials run
+// against the other's tile-load / row-maximum / barrier work instead of against its exponentials.
+template <bool PINGPONG, bool PROF>
 __global__ void __launch_bounds__(F3_THREADS, 1)
 attn_fwd_tc05_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
@@ -598,7 +607,7 @@ attn_fwd_tc05_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             F3Item it;
             for (int r = 0; r < n_rounds; r++) {
                 if (!f3_item(p, r, it)) continue;
-                const int n = it.n[g];
+                const int n = g ? it.n[1] : it.n[0];
                 if (n > 0) { mbar_wait(&q_full[g], cq & 1); cq++; }
                 for (int j = 0; j < it.nt; j++, T++) {
                     const int st = T % F3_KVS;
@@ -640,19 +649,36 @@ attn_fwd_tc05_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         const int off = p.Sk - p.Sq;
         uint8_t* sP = smem + F3_P + g * 32768;
         uint32_t tg = 0;
+        // ping-pong token of this sub-partition: barrier 1 + 2*quarter + g is the one this warp waits on
+        const int bar_mine = 1 + 2 * quarter + g, bar_other = 1 + 2 * quarter + (g ^ 1);
+        if (PINGPONG && g == 1) asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory");    // group 0 goes first
+        long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = 0;      // PROF: cycles per phase (lane 0), tiles
+        const long long pstart = PROF ? clock64() : 0;
+        auto mark = [&](int k) {
+            if (PROF) { const long long t = clock64(); pf[k] += t - pt; pt = t; }
+        };
+        pt = pstart;
         F3Item it;
         for (int r = 0; r < n_rounds; r++) {
             if (!f3_item(p, r, it)) continue;
-            const int n = it.n[g];
-            if (n == 0) continue;
-            const int q0 = it.q0[g], row = q0 + row_t;
+            const int n = g ? it.n[1] : it.n[0];
+            const int q0 = g ? it.q0[1] : it.q0[0], row = q0 + row_t;
             float m_ref = -INFINITY, l_i = 0.f;
-            for (int j = 0; j < n; j++, tg++) {
+            for (int j = 0; j < it.nt; j++) {
+                if (j >= n) {            // the other group's extra tile: keep the token moving
+                    if (PINGPONG) {
+                        asm volatile("bar.sync %0, 64;" ::"r"(bar_mine) : "memory");
+                        asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory");
+                    }
+                    continue;
+                }
                 const int k0 = j * BK;
                 const bool need_mask = (k0 + BK - 1 > q0 + off) || (k0 + BK > p.Sk);
                 const int lim0 = min(row + off, p.Sk - 1) - k0;     // last visible column of this row in the tile
+                mark(6);
                 mbar_wait(&s_full[g], tg & 1);
                 tc_fence_after();
+                mark(0);
                 uint32_t rr[2][32];
                 // ---- pass 1: row maximum
                 float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -675,6 +701,7 @@ attn_fwd_tc05_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                 const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
                 // ---- reference maximum; P buffer and O are free / stable once P.V of the previous tile has retired
                 const bool need = (mx - m_ref) * sl2 > F3_RESCALE_LOG2;       // true on the first tile (m_ref = -inf)
+                mark(1);
                 if (j > 0) {
                     mbar_wait(&pv_done[g], (tg - 1) & 1);
                     tc_fence_after();
@@ -698,6 +725,9 @@ attn_fwd_tc05_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                 }
                 const float msc = m_ref * sl2;
                 // ---- pass 2: probabilities -> bf16 -> swizzled P tile in shared memory
+                mark(2);
+                if (PINGPONG) asm volatile("bar.sync %0, 64;" ::"r"(bar_mine) : "memory");
+                mark(3);
                 float rs4[4] = {0.f, 0.f, 0.f, 0.f};
                 tmem_ld32(tS, rr[0]);
                 tmem_ld_wait();
@@ -738,12 +768,17 @@ attn_fwd_tc05_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                         if (lane == 0) mbar_arrive(&s_empty[g]);
                     }
                 }
+                if (PINGPONG) asm volatile("bar.arrive %0, 64;" ::"r"(bar_other) : "memory");
+                mark(4);
                 l_i += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
                 tc_fence_before();
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&p_full[g]);
+                tg++;
+                mark(5);
             }
+            if (n == 0) continue;
             // ---- epilogue of the item: O / l -> bf16
             mbar_wait(&pv_done[g], (tg - 1) & 1);
             tc_fence_after();
@@ -768,6 +803,14 @@ attn_fwd_tc05_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             // the next item's first P.V (accumulate = 0) overwrites O only after this thread's p_full arrival: ordered
             tc_fence_before();
         }
+        if (PINGPONG && g == 0) asm volatile("bar.sync %0, 64;" ::"r"(bar_mine) : "memory");    // consume the last token
+        if (PROF && lane == 0 && p.dbg) {
+            mark(6);                                   // [6] = epilogues + item bookkeeping + dummy token passes
+            for (int k = 0; k < 7; k++) atomicAdd((unsigned long long*)&p.dbg[g * 16 + k], (unsigned long long)pf[k]);
+            atomicAdd((unsigned long long*)&p.dbg[g * 16 + 7], (unsigned long long)(clock64() - pstart));
+            atomicAdd((unsigned long long*)&p.dbg[g * 16 + 8], (unsigned long long)tg);
+            atomicAdd((unsigned long long*)&p.dbg[g * 16 + 9], 1ull);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -776,7 +819,338 @@ attn_fwd_tc05_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         tmem_dealloc(tmem_base, 512);
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// forward, fourth generation: the v3 skeleton (persistent CTAs, two query tiles per CTA, O accumulated in TMEM with a lazy
+// rescale, one MMA-issuing warp per group) with TWO threads per query row: 16 softmax warps, four per SM sub-partition.
+// A single warp cannot keep the MUFU pipe busy through the softmax instruction mix (tools/micro/mufu_bench.cu: 13.4 cycles per
+// warp-exponential with one warp per sub-partition, 9.5 with four; the pipe's floor is 8), and with only two warps per
+// sub-partition every barrier wait of one warp idles half of the issue slots.  A thread owns 64 of the 128 keys of a row; the
+// two halves of a row agree on the exact row maximum through 4 bytes of shared memory and a 64-thread named barrier per tile
+// (the two warps involved sit on the same sub-partition), write their own 64-key atom of the P tile, rescale / emit their own
+// 32 output columns and meet once more per item for the row sum.
+//   warp 0: TMA producer   warps 1, 2: MMA issuers of group 0 / 1   warp 3: TMEM allocator
+//   warps 4..19: softmax; warp w -> row quarter w & 3, group (w - 4) >> 3, key half ((w - 4) >> 2) & 1
+// ---------------------------------------------------------------------------------------------
+constexpr int F4_THREADS = 640;
+constexpr int F4_KVS = 3;                                 // K/V stages (one fewer than v3: the exchange area needs 4 KB)
+constexpr int F4_BAR = F3_KV + F4_KVS * 32768;
+constexpr int F4_MX = F4_BAR + 256;                       // float [2 groups][2 slots][2 halves][128 rows]: row-maximum exchange
+constexpr int F4_SMEM = F4_MX + 4096;
+static_assert(F4_SMEM <= 232448 && F3_SMEM <= 232448, "dynamic shared memory of the forward kernels exceeds 227 KB");
+
+template <bool PROF>
+__global__ void __launch_bounds__(F4_THREADS, 1)
+attn_fwd_tc05_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
+    B200_PDL_TRIGGER();
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F4_BAR);
+    uint64_t* kv_full = bars + 0;      // [F4_KVS]
+    uint64_t* kv_empty = bars + 4;     // [F4_KVS]  one arrival per MMA warp
+    uint64_t* q_full = bars + 8;       // [2]
+    uint64_t* q_empty = bars + 10;     // [2]
+    uint64_t* s_full = bars + 12;      // [2]
+    uint64_t* s_empty = bars + 14;     // [2]  8 softmax warps
+    uint64_t* p_full = bars + 16;      // [2]  8 softmax warps
+    uint64_t* pv_done = bars + 18;     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    float* mx_s = reinterpret_cast<float*>(smem + F4_MX);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_rounds = (int)(((long long)((p.Sq + BQ - 1) / BQ + 1) / 2 * p.batch * p.n_heads + gridDim.x - 1) / gridDim.x);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
+        for (int s = 0; s < F4_KVS; s++) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }
+        for (int g = 0; g < 2; g++) {
+            mbar_init(&q_full[g], 1); mbar_init(&q_empty[g], 1); mbar_init(&s_full[g], 1); mbar_init(&s_empty[g], 8);
+            mbar_init(&p_full[g], 8); mbar_init(&pv_done[g], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 3) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // register budget: 640 threads start with 96 registers each (a pool of 61 440 for the CTA); the four housekeeping warps drop
+    // to 56 so that the sixteen softmax warps can take 104 (16 x 32 x 104 + 4 x 32 x 56 = 60 416 <= 61 440 -- a larger request
+    // than the CTA's own pool never succeeds) and hold both 32-column chunks of their half tile across the two passes
+    if (warp < 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+      if (warp == 0) {
+        if (lane == 0) {
+            uint32_t T = 0, cq0 = 0, cq1 = 0;
+            F3Item it;
+            for (int r = 0; r < n_rounds; r++) {
+                if (!f3_item(p, r, it)) continue;
+                if (it.n[0] > 0) {
+                    mbar_wait(&q_empty[0], (cq0 & 1) ^ 1);
+                    mbar_expect_tx(&q_full[0], BQ * D * 2);
+                    tma_load_3d(smem + F3_Q, &tmQ, &q_full[0], p.q_col0 + it.h * D, it.q0[0], it.b);
+                    cq0++;
+                }
+                if (it.n[1] > 0) {
+                    mbar_wait(&q_empty[1], (cq1 & 1) ^ 1);
+                    mbar_expect_tx(&q_full[1], BQ * D * 2);
+                    tma_load_3d(smem + F3_Q + 16384, &tmQ, &q_full[1], p.q_col0 + it.h * D, it.q0[1], it.b);
+                    cq1++;
+                }
+                for (int j = 0; j < it.nt; j++, T++) {
+                    const int st = T % F4_KVS;
+                    mbar_wait(&kv_empty[st], ((T / F4_KVS) & 1) ^ 1);
+                    uint8_t* sK = smem + F3_KV + st * 32768;
+                    mbar_expect_tx(&kv_full[st], 2 * BK * D * 2);
+                    tma_load_3d(sK, &tmK, &kv_full[st], p.k_col0 + it.h * D, j * BK, it.b);
+                    tma_load_3d(sK + 16384, &tmV, &kv_full[st], p.v_col0 + it.h * D, j * BK, it.b);
+                }
+            }
+        }
+      } else if (warp == 1 || warp == 2) {
+        if (lane == 0) {
+            const int g = warp - 1;
+            constexpr uint32_t idesc_s = make_idesc(BQ, BK, false, false);    // S[128 x 128] = Q . K^T
+            constexpr uint32_t idesc_pv = make_idesc(BQ, D, false, true);     // O[128 x 64] += P . V (V is [keys, d]: MN-major B)
+            const uint32_t tS = tmem_base + g * 128, tO = tmem_base + 256 + g * 64;
+            const uint64_t dQ0 = make_smem_desc(smem_u32(smem + F3_Q + g * 16384), 16, 1024);
+            const uint64_t dP0 = make_smem_desc(smem_u32(smem + F3_P + g * 32768), 16, 1024);
+            uint32_t T = 0, tg = 0, cq = 0;
+            auto issue_s = [&](uint32_t Tj) {               // S = Q . K_j^T of the K/V tile with running index Tj
+                const int st = Tj % F4_KVS;
+                mbar_wait(&kv_full[st], (Tj / F4_KVS) & 1);
+                const uint64_t dK0 = make_smem_desc(smem_u32(smem + F3_KV + st * 32768), 16, 1024);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < D / 16; k++) umma_f16(tS, desc_adv(dQ0, k * 32), desc_adv(dK0, k * 32), idesc_s, k > 0);
+                umma_commit(&s_full[g]);
+            };
+            F3Item it;
+            for (int r = 0; r < n_rounds; r++) {
+                if (!f3_item(p, r, it)) continue;
+                const int n = g ? it.n[1] : it.n[0];
+                if (n > 0) { mbar_wait(&q_full[g], cq & 1); cq++; }
+                for (int j = 0; j < it.nt; j++, T++) {
+                    const int st = T % F4_KVS;
+                    if (j < n) {
+                        if (j == 0) {
+                            if (tg > 0) mbar_wait(&s_empty[g], (tg - 1) & 1);      // last tile of the previous item read out
+                            issue_s(T);
+                            if (n == 1) umma_commit(&q_empty[g]);
+                        }
+                        if (j + 1 < n) {                                           // S_{j+1} first: the group never waits for it
+                            mbar_wait(&s_empty[g], tg & 1);
+                            issue_s(T + 1);
+                            if (j + 2 == n) umma_commit(&q_empty[g]);
+                        }
+                        mbar_wait(&p_full[g], tg & 1);
+                        tc_fence_after();
+                        const uint64_t dV0 = make_smem_desc(smem_u32(smem + F3_KV + st * 32768 + 16384), 16384, 1024);
+#pragma unroll
+                        for (int kk = 0; kk < BK / 16; kk++)
+                            umma_f16(tO, desc_adv(dP0, (kk >> 2) * 16384 + (kk & 3) * 32), desc_adv(dV0, kk * 2048), idesc_pv,
+                                     (j > 0 || kk > 0) ? 1u : 0u);
+                        umma_commit(&pv_done[g]);
+                        umma_commit(&kv_empty[st]);
+                        tg++;
+                    } else {
+                        mbar_wait(&kv_full[st], (T / F4_KVS) & 1);                 // the other group's tile: just pass the stage on
+                        mbar_arrive(&kv_empty[st]);
+                    }
+                }
+            }
+        }
+      }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        const int g = (warp - 4) >> 3;
+        const int half = ((warp - 4) >> 2) & 1;           // keys half*64 .. +63 of every tile, output columns half*32 .. +31
+        const int quarter = warp & 3;
+        const int row_t = quarter * 32 + lane;            // row inside the tile == TMEM lane
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        const uint32_t tS = tmem_base + g * 128 + half * 64 + lane_addr, tO = tmem_base + 256 + g * 64 + half * 32 + lane_addr;
+        const float sl2 = p.scale * LOG2E;
+        const int off = p.Sk - p.Sq;
+        uint8_t* sP = smem + F3_P + g * 32768 + half * 16384 + row_t * 128;      // this thread's 128-byte row of its 64-key atom
+        float* mxg = mx_s + g * 512;                      // [slot][half][row]
+        const int pair_bar = 1 + g * 4 + quarter;         // named barrier of the two warps that share this row quarter
+        uint32_t tg = 0;
+        long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = 0;      // PROF: cycles per phase (lane 0)
+        const long long pstart = PROF ? clock64() : 0;
+        auto mark = [&](int k) {
+            if (PROF) { const long long t = clock64(); pf[k] += t - pt; pt = t; }
+        };
+        pt = pstart;
+        F3Item it;
+        for (int r = 0; r < n_rounds; r++) {
+            if (!f3_item(p, r, it)) continue;
+            const int n = g ? it.n[1] : it.n[0];
+            if (n == 0) continue;
+            const int q0 = g ? it.q0[1] : it.q0[0], row = q0 + row_t;
+            float m_ref = -INFINITY, l_i = 0.f;
+            for (int j = 0; j < n; j++, tg++) {
+                const int k0 = j * BK + half * 64;
+                const bool need_mask = (j * BK + BK - 1 > q0 + off) || (j * BK + BK > p.Sk);
+                const int lim0 = min(row + off, p.Sk - 1) - k0;     // last visible column of this row in this thread's half tile
+                mark(6);
+                mbar_wait(&s_full[g], tg & 1);
+                tc_fence_after();
+                mark(0);
+                uint32_t rr[2][32];
+                // ---- pass 1: row maximum over this thread's 64 keys, then the exact row maximum with the other half
+                float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                tmem_ld32(tS, rr[0]);
+                tmem_ld32(tS + 32, rr[1]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    if (need_mask) {
+                        const int lim = lim0 - c * 32;
+#pragma unroll
+                        for (int i = 0; i < 32; i++)
+                            mx4[i & 3] = fmaxf(mx4[i & 3], (i > lim) ? -INFINITY : __uint_as_float(rr[c][i]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i++) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(rr[c][i]));
+                    }
+                }
+                float* mslot = mxg + (tg & 1) * 256;
+                mslot[half * 128 + row_t] = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+                const float mx = fmaxf(mslot[row_t], mslot[128 + row_t]);
+                // ---- reference maximum; P buffer and O are free / stable once P.V of the previous tile has retired
+                const bool need = (mx - m_ref) * sl2 > F3_RESCALE_LOG2;       // true on the first tile (m_ref = -inf)
+                mark(1);
+                if (j > 0) {
+                    mbar_wait(&pv_done[g], (tg - 1) & 1);
+                    tc_fence_after();
+                }
+                if (__any_sync(0xffffffffu, need)) {
+                    const float m_new = need ? mx : m_ref;
+                    if (j > 0) {
+                        const float alpha = need ? exp2f((m_ref - m_new) * sl2) : 1.f;
+                        uint32_t ro[32];
+                        tmem_ld32(tO, ro);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; i++) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+                        tmem_st32(tO, ro);
+                        tmem_st_wait();
+                        l_i *= alpha;
+                    }
+                    m_ref = m_new;
+                }
+                const float msc = m_ref * sl2;
+                mark(2);
+                // ---- pass 2: probabilities -> bf16 -> this half's 64-key atom of the swizzled P tile (S is still in registers)
+                float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[g]);      // both chunks are in registers: the tensor pipe may overwrite S
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    uint32_t pk[16];
+                    if (need_mask) {
+                        const int lim = lim0 - c * 32;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            const float p0 = (i > lim) ? 0.f : ex2_approx(fmaf(__uint_as_float(rr[c][i]), sl2, -msc));
+                            const float p1 = (i + 1 > lim) ? 0.f : ex2_approx(fmaf(__uint_as_float(rr[c][i + 1]), sl2, -msc));
+                            rs4[(i >> 1) & 3] += p0 + p1;
+                            pk[i >> 1] = pack2(p0, p1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            const float p0 = ex2_approx(fmaf(__uint_as_float(rr[c][i]), sl2, -msc));
+                            const float p1 = ex2_approx(fmaf(__uint_as_float(rr[c][i + 1]), sl2, -msc));
+                            rs4[(i >> 1) & 3] += p0 + p1;
+                            pk[i >> 1] = pack2(p0, p1);
+                        }
+                    }
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+                        const int chunk = c * 4 + v;
+                        *reinterpret_cast<uint4*>(sP + ((chunk ^ (row_t & 7)) << 4)) =
+                            make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+                    }
+                }
+                mark(4);
+                l_i += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[g]);
+                mark(5);
+            }
+            // ---- epilogue of the item: the two halves of a row add their sums, then O / l -> bf16 (32 columns per thread)
+            float* lslot = mxg + (tg & 1) * 256;          // the slot the last tile did not use
+            lslot[half * 128 + row_t] = l_i;
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            const float l_row = lslot[row_t] + lslot[128 + row_t];
+            mbar_wait(&pv_done[g], (tg - 1) & 1);
+            tc_fence_after();
+            const float inv = l_row > 0.f ? 1.f / l_row : 0.f;
+            bf16* dst = p.o + it.b * p.o_b + (long long)row * p.o_r + it.h * D + half * 32;
+            {
+                uint32_t ro[32];
+                tmem_ld32(tO, ro);
+                tmem_ld_wait();
+                if (row < p.Sq) {
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+                        float f[8];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) f[i] = __uint_as_float(ro[v * 8 + i]) * inv;
+                        *reinterpret_cast<uint4*>(dst + v * 8) = pack8(f);
+                    }
+                }
+            }
+            if (p.lse && half == 0 && row < p.Sq)
+                p.lse[((long long)it.b * p.n_heads + it.h) * p.Sq + row] = m_ref * p.scale + logf(l_row);
+            // the next item's first P.V (accumulate = 0) overwrites O only after this thread's p_full arrival: ordered;
+            // its first maximum goes to the other slot, and the pair barrier of that tile orders the reuse of this one
+            tc_fence_before();
+        }
+        if (PROF && lane == 0 && p.dbg) {
+            mark(6);
+            for (int k = 0; k < 7; k++) atomicAdd((unsigned long long*)&p.dbg[g * 16 + k], (unsigned long long)pf[k]);
+            atomicAdd((unsigned long long*)&p.dbg[g * 16 + 7], (unsigned long long)(clock64() - pstart));
+            atomicAdd((unsigned long long*)&p.dbg[g * 16 + 8], (unsigned long long)tg);
+            atomicAdd((unsigned long long*)&p.dbg[g * 16 + 9], 1ull);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 3) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+static int f3_launch(bool pingpong, bool prof, int grid, cudaStream_t stream, const CUtensorMap& tmQ, const CUtensorMap& tmK,
+                     const CUtensorMap& tmV, const FwdParams& p) {
+    static bool init = false;
+    if (!init) {
+        int bad = 0;
+        bad |= cudaFuncSetAttribute(attn_fwd_tc05_v3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM) != cudaSuccess;
+        bad |= cudaFuncSetAttribute(attn_fwd_tc05_v3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM) != cudaSuccess;
+        bad |= cudaFuncSetAttribute(attn_fwd_tc05_v3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM) != cudaSuccess;
+        bad |= cudaFuncSetAttribute(attn_fwd_tc05_v3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM) != cudaSuccess;
+        B200_CHECK_ARG(!bad, "attn_causal_fwd_tc: cannot set the shared-memory size of the v3 kernel");
+        init = true;
+    }
+    if (prof) {      // phase profile (tools/attn_fwd_profile.py): instrumented instantiation
+        if (pingpong) attn_fwd_tc05_v3_kernel<true, true><<<grid, F3_THREADS, F3_SMEM, stream>>>(tmQ, tmK, tmV, p);
+        else attn_fwd_tc05_v3_kernel<false, true><<<grid, F3_THREADS, F3_SMEM, stream>>>(tmQ, tmK, tmV, p);
+    } else if (pingpong) attn_fwd_tc05_v3_kernel<true, false><<<grid, F3_THREADS, F3_SMEM, stream>>>(tmQ, tmK, tmV, p);
+    else attn_fwd_tc05_v3_kernel<false, false><<<grid, F3_THREADS, F3_SMEM, stream>>>(tmQ, tmK, tmV, p);
+    return B200_OK;
+}
 }   // namespace
+
+static long long* g_attn_dbg = nullptr;
 
 // 3-D bf16 tensor map {cols, rows per sequence, batch} with 128B swizzle: rows outside a sequence are zero-filled
 int tc05_make_tmap_3d(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t row_pitch,
@@ -804,21 +1178,37 @@ extern "C" int b200_attn_causal_fwd_tc(const void* q, const void* k, const void*
     p.batch = batch; p.n_heads = n_heads; p.Sq = Sq; p.Sk = Sk; p.H = (int)W;
     p.q_col0 = p.k_col0 = p.v_col0 = 0;
     p.scale = scale;
+    p.dbg = nullptr;
     static int gen = 0;
+    static bool pingpong = true;
     if (!gen) {
         // B200_ATTN_FWD_TC=v1 / v2 select the earlier generations (see the file header)
         const char* e = getenv("B200_ATTN_FWD_TC");
-        gen = (e && !strcmp(e, "v1")) ? 1 : (e && !strcmp(e, "v2")) ? 2 : 3;
+        gen = (e && !strcmp(e, "v1")) ? 1 : (e && !strcmp(e, "v2")) ? 2 : (e && !strcmp(e, "v4")) ? 4 : 3;
+        B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc05_v4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM), "attn_tc v4 smem");
+        B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc05_v4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F4_SMEM), "attn_tc v4 smem");
         B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES), "attn_tc smem");
         B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc05_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                        cudaSharedmemCarveoutMaxShared), "attn_tc carveout");
         B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc05_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM), "attn_tc v2 smem");
-        B200_CUDA(cudaFuncSetAttribute(attn_fwd_tc05_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM), "attn_tc v3 smem");
+        const char* pp = getenv("B200_ATTN_FWD_PINGPONG");
+        pingpong = !(pp && pp[0] == '0');
+    }
+    if (gen == 4) {
+        const long long items = (long long)(((Sq + BQ - 1) / BQ + 1) / 2) * batch * n_heads;
+        const int g4 = (int)(items < b200_num_sms() ? items : b200_num_sms());
+        p.dbg = g_attn_dbg;
+        if (p.dbg) attn_fwd_tc05_v4_kernel<true><<<g4, F4_THREADS, F4_SMEM, stream>>>(tmQ, tmK, tmV, p);
+        else attn_fwd_tc05_v4_kernel<false><<<g4, F4_THREADS, F4_SMEM, stream>>>(tmQ, tmK, tmV, p);
+        B200_CHECK_LAUNCH("attn_causal_fwd_tc");
+        return B200_OK;
     }
     if (gen == 3) {
         const long long items = (long long)(((Sq + BQ - 1) / BQ + 1) / 2) * batch * n_heads;
         const int g3 = (int)(items < b200_num_sms() ? items : b200_num_sms());
-        attn_fwd_tc05_v3_kernel<<<g3, F3_THREADS, F3_SMEM, stream>>>(tmQ, tmK, tmV, p);
+        p.dbg = g_attn_dbg;
+        const int rc3 = f3_launch(pingpong, p.dbg != nullptr, g3, stream, tmQ, tmK, tmV, p);
+        if (rc3) return rc3;
         B200_CHECK_LAUNCH("attn_causal_fwd_tc");
         return B200_OK;
     }
@@ -1023,12 +1413,16 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int qc0 = hb * 64 + cgi * 32;            // first query column (inside the tile) of this thread
         uint8_t* sP = smem + SB_P + hb * 16384 + key_t * 128;
         uint8_t* sDS = smem + SB_DS + hb * 16384 + key_t * 128;
-        // lse / delta of this group's 64 queries: one value per thread of the group's first 4 warps, fetched one
-        // iteration ahead so the global load latency hides behind the previous iteration
-        auto fetch_ld = [&](int it_) -> float {
-            const int qi = (i0 + it_) * BQ + hb * 64 + (gtid & 63);
-            if (gtid >= 128 || it_ >= n_it || qi >= p.Sq) return 0.f;
-            return gtid < 64 ? lse_g[qi] * LOG2E : delta_g[qi];
+        // lse / delta of this warp's 32 query columns (lane i -> column qc0 + i), fetched one iteration ahead so the global load
+        // latency hides behind the previous iteration.  Every warp stages the values it reads itself (the four quarter-warps
+        // that share the columns write identical words), so a __syncwarp orders the stores against the broadcast loads and
+        // no group-wide barrier sits on the critical path; the slot parity covers the one iteration two warps can be apart
+        // (S_{it+1} of this half tile is issued only after all eight warps arrived on pds_full for it).
+        auto fetch_ld = [&](int it_, float& lse_v, float& delta_v) {
+            const int qi = (i0 + it_) * BQ + qc0 + lane;
+            const bool ok = it_ < n_it && qi < p.Sq;
+            lse_v = ok ? lse_g[qi] * LOG2E : 0.f;
+            delta_v = ok ? delta_g[qi] : 0.f;
         };
         // dQ tile of a finished iteration, drained by group 0: TMEM lane = query row, this thread owns 32 columns
         auto drain_dq = [&](int q0_tile) {
@@ -1048,7 +1442,9 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                                    __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
                 }
             } else {
-                // the staging tile was released by the leader's wait_group.read ahead of this iteration's group barrier
+                // the previous TMA reduce must have finished reading the staging tile before it is overwritten
+                if (gtid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 uint8_t* dst = smem + SB_DQ + cgi * 16384 + key_t * 128;
 #pragma unroll
                 for (int v = 0; v < 8; v++)
@@ -1063,13 +1459,14 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             }
         };
         const bool drainer = WITH_DQ && grp == 0;
-        float ld_next = fetch_ld(0);
+        float lse_next, delta_next;
+        fetch_ld(0, lse_next, delta_next);
         for (int it = 0; it < n_it; it++) {
             const int q0 = (i0 + it) * BQ;
-            if (gtid < 128) (gtid < 64 ? lse_s : delta_s)[(it & 1) * 128 + hb * 64 + (gtid & 63)] = ld_next;
-            ld_next = fetch_ld(it + 1);
-            if (DQ_MODE == 2 && drainer && gtid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory");
+            lse_s[(it & 1) * 128 + qc0 + lane] = lse_next;
+            delta_s[(it & 1) * 128 + qc0 + lane] = delta_next;
+            fetch_ld(it + 1, lse_next, delta_next);
+            __syncwarp();
             const bool need_mask = (k0 + BK - 1 > q0 + off) || (k0 + BK > p.Sk) || (q0 + BQ > p.Sq);
             const float* lse_t = lse_s + (it & 1) * 128 + qc0;
             const float* delta_t = delta_s + (it & 1) * 128 + qc0;
@@ -1138,10 +1535,6 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             mbar_wait(dq_full, (uint32_t)((n_it - 1) & 1));   // last tile's MMAs
             tc_fence_after();
             if (drainer) {
-                if (DQ_MODE == 2) {
-                    if (gtid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                }
                 drain_dq((i0 + n_it - 1) * BQ);
                 if (DQ_MODE == 2 && gtid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             }
@@ -1460,8 +1853,8 @@ __global__ void attn_bwd_dq_finalize_kernel(const float* __restrict__ acc, bf16*
 
 }   // namespace
 
-static long long* g_attn_dbg = nullptr;
-// bring-up hook: device buffer of 128 int64 receiving a clock64 trace of CTA (0,0) of the dQ kernel (NULL = off)
+// bring-up hook: device buffer of 128 int64 receiving a clock64 trace of CTA (0,0) of the dQ kernel, or the per-phase
+// cycle sums of the forward kernel's softmax warps (NULL = off)
 extern "C" void b200_attn_debug_trace(long long* buf) { g_attn_dbg = buf; }
 
 // defined in attn_flash.cu
