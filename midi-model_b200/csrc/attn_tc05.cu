@@ -1243,7 +1243,8 @@ constexpr int SB_DS = SB_P + 32768;              // dS^T: same layout
 constexpr int SB_DQ = SB_DS + 32768;             // fp32 dQ tile for the TMA reduce: two 32-column boxes of [128 q x 128 B], 128B-swizzled
 constexpr int SB_LSE = SB_DQ + 32768;            // float [2][2][128]: lse, delta per stage parity
 constexpr int SB_BAR = SB_LSE + 2048;
-constexpr int SMEM_BWD_BYTES = SB_BAR + 128;
+constexpr int SMEM_BWD_BYTES = SB_BAR + 192;
+constexpr int BWD_DEFAULT_UNITS = 2;
 
 struct BwdParams {
     const float* lse;
@@ -1272,7 +1273,11 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* tm, uint32_
 
 // DQ_MODE: 0 = dK/dV only (dQ by the separate kernel below), 1 = dQ through red.global.add.v4.f32,
 //          2 = dQ tile staged in shared memory and added with cp.reduce.async.bulk.tensor
-template <int DQ_MODE>
+// NU: pipeline units per query tile.  2 = half tiles (64 queries): two math groups of 8 warps.  4 = quarter tiles (32 queries):
+//     four math groups of 4 warps, one warp of every group on each SM sub-partition, i.e. four independent dependent chains
+//     per scheduler instead of two lockstepped pairs (same thread -> element mapping, same TMEM / shared-memory layout; only
+//     the hand-over granularity between the MMA-issuing thread and the math warps changes, and S^T / dP^T become N = 32 UMMAs).
+template <int DQ_MODE, int NU>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -1283,11 +1288,11 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     uint64_t* kv_full = bars + 0;
     uint64_t* q_full = bars + 1;      // [QS]
     uint64_t* q_empty = bars + 5;     // [QS]
-    uint64_t* s_full = bars + 9;      // [2]  one per half-tile buffer (64 query columns)
-    uint64_t* pds_full = bars + 11;   // [2]
-    uint64_t* dq_full = bars + 13;
-    uint64_t* dq_empty = bars + 14;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+    uint64_t* s_full = bars + 9;      // [NU]  one per pipeline unit of a tile
+    uint64_t* pds_full = bars + 13;   // [NU]
+    uint64_t* dq_full = bars + 17;
+    uint64_t* dq_empty = bars + 18;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
     float* lse_s = reinterpret_cast<float*>(smem + SB_LSE);          // [2][128]
     float* delta_s = lse_s + 256;                                      // [2][128]
 
@@ -1306,7 +1311,7 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmdO);
         mbar_init(kv_full, 1);
         for (int s = 0; s < QS; s++) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(&s_full[s], 1); mbar_init(&pds_full[s], BWD_CWARPS / 2); }
+        for (int s = 0; s < NU; s++) { mbar_init(&s_full[s], 1); mbar_init(&pds_full[s], BWD_CWARPS / NU); }
         mbar_init(dq_full, 1); mbar_init(dq_empty, BWD_CWARPS / 2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1335,7 +1340,7 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
     } else if (warp == 1) {
         if (lane == 0 && n_it > 0) {
-            constexpr uint32_t id_s = make_idesc(128, 64, false, false);      // S^T, dP^T of one half tile (64 queries)
+            constexpr uint32_t id_s = make_idesc(128, 128 / NU, false, false);  // S^T, dP^T of one unit (64 or 32 queries)
             constexpr uint32_t id_kv = make_idesc(128, 64, false, true);      // dV, dK : A K-major (smem P^T/dS^T), B MN-major
             constexpr uint32_t id_dq = make_idesc(128, 64, true, true);       // dQ     : A = dS (MN-major view of dS^T), B = K MN-major
             const uint32_t sK = smem_u32(smem + SB_K), sV = smem_u32(smem + SB_V);
@@ -1348,39 +1353,44 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             // The pipeline unit is a half tile: 64 queries x 128 keys.  Unit u = (tile u/2, half u&1) owns TMEM buffer
             // u&1 and P^T/dS^T atom u&1, so S^T/dP^T of unit u+2 are produced while the math warps work on unit u+1
             // and the tensor pipe never sits on the critical path.
-            const int n_units = 2 * n_it;
+            const int n_units = NU * n_it;
             auto issue_s = [&](int u) {
-                const int it_ = u >> 1, hb = u & 1, st = it_ % QS;
-                if (hb == 0) mbar_wait(&q_full[st], (uint32_t)((it_ / QS) & 1));
-                const uint32_t sQ = smem_u32(smem + SB_Q + st * 32768) + hb * 8192;     // 64 query rows x 128 B
+                const int it_ = u / NU, g = u % NU, st = it_ % QS;
+                const int hb = (NU == 4) ? (g >> 1) : g, cgi = (NU == 4) ? (g & 1) : 0;
+                if (g == 0) mbar_wait(&q_full[st], (uint32_t)((it_ / QS) & 1));
+                const uint32_t sQ = smem_u32(smem + SB_Q + st * 32768) + hb * 8192 + cgi * 4096;   // 64 / 32 query rows x 128 B
                 const uint64_t dQk = make_smem_desc(sQ, 16, 1024), dOk = make_smem_desc(sQ + 16384, 16, 1024);
-                const uint32_t tS = tSB + hb * 128, tdP = tS + 64;
+                const uint32_t tS = tSB + hb * 128 + cgi * 32, tdP = tS + 64;
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < D / 16; k++) umma_f16(tS, desc_adv(dKk, k * 32), desc_adv(dQk, k * 32), id_s, k > 0);
 #pragma unroll
                 for (int k = 0; k < D / 16; k++) umma_f16(tdP, desc_adv(dVk, k * 32), desc_adv(dOk, k * 32), id_s, k > 0);
-                umma_commit(&s_full[hb]);
+                umma_commit(&s_full[g]);
             };
-            issue_s(0);
-            issue_s(1);
+#pragma unroll
+            for (int u = 0; u < NU; u++)
+                if (u < n_units) issue_s(u);
             for (int u = 0; u < n_units; u++) {
-                const int it = u >> 1, hb = u & 1, st_cur = it % QS;
+                const int it = u / NU, g = u % NU, st_cur = it % QS;
+                const int hb = (NU == 4) ? (g >> 1) : g, cgi = (NU == 4) ? (g & 1) : 0;
                 const uint32_t sQ = smem_u32(smem + SB_Q + st_cur * 32768);
                 const uint64_t dQmn = make_smem_desc(sQ, 16384, 1024), dOmn = make_smem_desc(sQ + 16384, 16384, 1024);
-                mbar_wait(&pds_full[hb], (uint32_t)(it & 1));   // P^T / dS^T atom hb written; TMEM buffer hb is free
+                mbar_wait(&pds_full[g], (uint32_t)(it & 1));    // P^T / dS^T columns of this unit written; its TMEM buffer is free
                 tc_fence_after();
 #pragma unroll
-                for (int k4 = 0; k4 < 4; k4++) {
-                    const int kk = hb * 4 + k4;                // 16 query rows per step, this half = steps 4*hb .. +3
-                    umma_f16(tdV, desc_adv(dPk, hb * 16384 + k4 * 32), desc_adv(dOmn, kk * 2048), id_kv, (u > 0 || k4 > 0) ? 1u : 0u);
+                for (int k = 0; k < 8 / NU; k++) {
+                    const int k4 = cgi * 2 + k;                // 16 query rows per step inside the half's 64-query atom
+                    const int kk = hb * 4 + k4;
+                    umma_f16(tdV, desc_adv(dPk, hb * 16384 + k4 * 32), desc_adv(dOmn, kk * 2048), id_kv, (u > 0 || k > 0) ? 1u : 0u);
                 }
 #pragma unroll
-                for (int k4 = 0; k4 < 4; k4++) {
+                for (int k = 0; k < 8 / NU; k++) {
+                    const int k4 = cgi * 2 + k;
                     const int kk = hb * 4 + k4;
-                    umma_f16(tdK, desc_adv(dDSk, hb * 16384 + k4 * 32), desc_adv(dQmn, kk * 2048), id_kv, (u > 0 || k4 > 0) ? 1u : 0u);
+                    umma_f16(tdK, desc_adv(dDSk, hb * 16384 + k4 * 32), desc_adv(dQmn, kk * 2048), id_kv, (u > 0 || k > 0) ? 1u : 0u);
                 }
-                if (hb == 1) {
+                if (g == NU - 1) {
                     if (WITH_DQ) {
                         mbar_wait(dq_empty, (uint32_t)((it & 1) ^ 1));      // previous dQ tile drained
                         tc_fence_after();
@@ -1391,7 +1401,7 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     umma_commit(dq_full);
                     umma_commit(&q_empty[st_cur]);
                 }
-                if (u + 2 < n_units) issue_s(u + 2);           // two units ahead: not urgent, goes after this unit's dV/dK/dQ
+                if (u + NU < n_units) issue_s(u + NU);         // one tile ahead: not urgent, goes after this unit's dV/dK/dQ
             }
         }
     } else {
@@ -1400,7 +1410,8 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         // + fence) the other is in its exp2/FMA stretch.  thread = (key row, 32 of the 64 query columns).
         const int cw = warp - 2;                       // 0..15
         const int quarter = warp & 3;
-        const int grp = cw >> 3;                       // math group == half tile index hb
+        const int grp = cw >> 3;                       // half tile index hb
+        const int ug = (NU == 4) ? (cw >> 2) : grp;    // pipeline unit == math group of this warp
         const int cgi = (cw >> 2) & 1;                 // which 32 query columns of the half tile
         const int gtid = (cw & 7) * 32 + lane;         // 0..255 inside the group
         const int key_t = quarter * 32 + lane;         // key row inside the tile == TMEM lane
@@ -1470,7 +1481,7 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const bool need_mask = (k0 + BK - 1 > q0 + off) || (k0 + BK > p.Sk) || (q0 + BQ > p.Sq);
             const float* lse_t = lse_s + (it & 1) * 128 + qc0;
             const float* delta_t = delta_s + (it & 1) * 128 + qc0;
-            mbar_wait(&s_full[hb], (uint32_t)(it & 1));
+            mbar_wait(&s_full[ug], (uint32_t)(it & 1));
             tc_fence_after();
             uint32_t pk[16], dk_[16];
 #pragma unroll
@@ -1528,7 +1539,7 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             tc_fence_before();
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&pds_full[hb]);
+            if (lane == 0) mbar_arrive(&pds_full[ug]);
             if (drainer && it > 0) drain_dq(q0 - BQ);   // off the critical path
         }
         if (n_it > 0) {
@@ -1910,10 +1921,15 @@ extern "C" int b200_attn_causal_bwd_tc(const void* q, const void* k, const void*
         dq_mode = (e && !strcmp(e, "red")) ? 1 : (e && !strcmp(e, "split")) ? 0 : 2;
     }
     static bool configured = false;
+    static int units = 2;
     if (!configured) {
-        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
-        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
-        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
+        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
+        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
+        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
+        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
+        // B200_ATTN_BWD_UNITS = 2 | 4: pipeline units per query tile of the default (TMA reduce) kernel
+        const char* u = getenv("B200_ATTN_BWD_UNITS");
+        units = (u && u[0] == '2') ? 2 : (u && u[0] == '4') ? 4 : BWD_DEFAULT_UNITS;
         B200_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DQ_BYTES), "attn_bwd_dq smem");
         configured = true;
     }
@@ -1922,8 +1938,9 @@ extern "C" int b200_attn_causal_bwd_tc(const void* q, const void* k, const void*
         CUtensorMap tmDQ;
         if ((rc = tc05_make_tmap_3d_f32(&tmDQ, dq_acc, W, Sq, batch, W, (long long)Sq * W, 32, BQ))) return rc;
         B200_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)batch * Sq * W * sizeof(float), stream), "attn_bwd_tc memset");
-        if (dq_mode == 2) attn_bwd_tc05_kernel<2><<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
-        else attn_bwd_tc05_kernel<1><<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
+        if (dq_mode == 2 && units == 4) attn_bwd_tc05_kernel<2, 4><<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
+        else if (dq_mode == 2) attn_bwd_tc05_kernel<2, 2><<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
+        else attn_bwd_tc05_kernel<1, 2><<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
         B200_CHECK_LAUNCH("attn_causal_bwd_tc");
         const long long rows = (long long)batch * Sq;
         long long nthr = rows * (W / 16);
@@ -1933,7 +1950,7 @@ extern "C" int b200_attn_causal_bwd_tc(const void* q, const void* k, const void*
                                                                 (const bf16*)rope_cos, (const bf16*)rope_sin);
         B200_CHECK_LAUNCH("attn_bwd_dq_finalize");
     } else {
-        attn_bwd_tc05_kernel<0><<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmQ, p);
+        attn_bwd_tc05_kernel<0, 2><<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmQ, p);
         B200_CHECK_LAUNCH("attn_causal_bwd_tc_dkv");
         DqParams dp;
         dp.lse = lse; dp.delta = delta; dp.dq = (bf16*)dq; dp.dq_b = strides[15]; dp.dq_r = strides[16];
