@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 from midi_b200 import ops  # noqa: E402
 
 worst = 0.0
-for (B, S, nh) in ((1, 128, 2), (1, 200, 2), (2, 384, 2)):
+for (B, S, nh) in ((1, 128, 4), (1, 200, 4), (2, 384, 4)):
     D, H = 64, nh * 64
     g = torch.Generator(device="cuda").manual_seed(S)
     qkv = torch.randn(B * S, 3 * H, device="cuda", generator=g).to(torch.bfloat16)

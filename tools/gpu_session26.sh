@@ -12,6 +12,11 @@ for k,v in d['hbm_kernels']['kernels'].items(): print('  ',k, v['us'], v['frac']
 g=d['generate']; print({k:(v['events_per_s'],v.get('graph_loop_events_per_s'),v['roofline']['frac']) for k,v in g.items() if k.startswith('batch')})
 PY
 timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2
+# e2e vs device-resident A/B of the attention forward generations (the e2e leg syncs on the loss every step)
+for gen in v3 v2 v3; do
+  B200_ATTN_FWD_TC=$gen timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-generate --no-hbm-kernels > gpurun_out/s26_bench_$gen.json 2>/dev/null
+  python -c "import json;d=json.load(open('gpurun_out/s26_bench_$gen.json'));print('$gen', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], d['clocks']['sm_mhz'])"
+done
 for t in memcheck racecheck; do
   timeout 600 compute-sanitizer --tool $t --error-exitcode 7 python tools/attn_small.py > gpurun_out/s26_${t}_attn.log 2>&1; echo "$t attn rc=$?"
   grep -E "SUMMARY|worst" gpurun_out/s26_${t}_attn.log | tail -3
