@@ -1245,6 +1245,7 @@ constexpr int SB_LSE = SB_DQ + 32768;            // float [2][2][128]: lse, delt
 constexpr int SB_BAR = SB_LSE + 2048;
 constexpr int SMEM_BWD_BYTES = SB_BAR + 192;
 constexpr int BWD_DEFAULT_UNITS = 2;
+constexpr int BWD_DEFAULT_LDM = 2;
 
 struct BwdParams {
     const float* lse;
@@ -1277,7 +1278,12 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* tm, uint32_
 //     four math groups of 4 warps, one warp of every group on each SM sub-partition, i.e. four independent dependent chains
 //     per scheduler instead of two lockstepped pairs (same thread -> element mapping, same TMEM / shared-memory layout; only
 //     the hand-over granularity between the MMA-issuing thread and the math warps changes, and S^T / dP^T become N = 32 UMMAs).
-template <int DQ_MODE, int NU>
+// LDM: how the math warps get lse / delta of their 32 query columns.  0 = every warp stages them in shared memory itself (the four
+//     quarter-warps that share the columns write identical words; __syncwarp only).  1 = no staging: uniform 16-byte loads from
+//     global memory (L1 hits; the lines are prefetched one iteration ahead).  2 = one writer warp per column group stages the
+//     NEXT iteration's values before its pds_full arrival: the MMA thread issues S^T of that iteration only after all arrivals
+//     and the readers acquire s_full, so the hand-over is ordered by the mbarriers that are there anyway.
+template <int DQ_MODE, int NU, int LDM>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -1316,6 +1322,15 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (LDM == 2 && warp >= 2 && (warp & 3) == 0) {
+        // writer warps (row quarter 0): lse / delta of the first iteration, visible to everyone through the barrier below
+        const int cw_ = warp - 2, qc_ = (cw_ >> 3) * 64 + ((cw_ >> 2) & 1) * 32;
+        const int qi = i0 * BQ + qc_ + lane;
+        const bool ok = n_it > 0 && qi < p.Sq;
+        const long long rowb = ((long long)b * p.n_heads + h) * p.Sq;
+        lse_s[qc_ + lane] = ok ? p.lse[rowb + qi] * LOG2E : 0.f;
+        delta_s[qc_ + lane] = ok ? p.delta[rowb + qi] : 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -1470,14 +1485,23 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             }
         };
         const bool drainer = WITH_DQ && grp == 0;
-        float lse_next, delta_next;
-        fetch_ld(0, lse_next, delta_next);
+        float lse_next = 0.f, delta_next = 0.f;
+        const bool writer = (LDM == 2) && quarter == 0;
+        if (LDM == 0) fetch_ld(0, lse_next, delta_next);
         for (int it = 0; it < n_it; it++) {
             const int q0 = (i0 + it) * BQ;
-            lse_s[(it & 1) * 128 + qc0 + lane] = lse_next;
-            delta_s[(it & 1) * 128 + qc0 + lane] = delta_next;
-            fetch_ld(it + 1, lse_next, delta_next);
-            __syncwarp();
+            if (LDM == 0) {
+                lse_s[(it & 1) * 128 + qc0 + lane] = lse_next;
+                delta_s[(it & 1) * 128 + qc0 + lane] = delta_next;
+                fetch_ld(it + 1, lse_next, delta_next);
+                __syncwarp();
+            } else if (LDM == 2) {
+                if (writer) fetch_ld(it + 1, lse_next, delta_next);     // stored before this iteration's pds_full arrival
+            } else if (lane < 2 && it + 1 < n_it) {
+                // pull the next iteration's line of lse (lane 0) / delta (lane 1) into L1
+                const int qn = (i0 + it + 1) * BQ + qc0;
+                if (qn < p.Sq) asm volatile("prefetch.global.L1 [%0];" ::"l"((lane ? delta_g : lse_g) + qn));
+            }
             const bool need_mask = (k0 + BK - 1 > q0 + off) || (k0 + BK > p.Sk) || (q0 + BQ > p.Sq);
             const float* lse_t = lse_s + (it & 1) * 128 + qc0;
             const float* delta_t = delta_s + (it & 1) * 128 + qc0;
@@ -1487,6 +1511,26 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
             for (int hc = 0; hc < 2; hc++) {               // two chunks of 16 columns keep the register footprint flat
                 uint32_t rs[16], rd[16];
+                float lse_r[16], delta_r[16];              // LDM == 1: this chunk's values straight from global memory
+                if (LDM == 1) {
+                    const int qb = q0 + qc0 + hc * 16;
+                    if (qb + 16 <= p.Sq) {
+#pragma unroll
+                        for (int v = 0; v < 4; v++) {
+                            const float4 a4 = __ldg(reinterpret_cast<const float4*>(lse_g + qb) + v);
+                            const float4 d4 = __ldg(reinterpret_cast<const float4*>(delta_g + qb) + v);
+                            lse_r[4 * v] = a4.x * LOG2E; lse_r[4 * v + 1] = a4.y * LOG2E; lse_r[4 * v + 2] = a4.z * LOG2E; lse_r[4 * v + 3] = a4.w * LOG2E;
+                            delta_r[4 * v] = d4.x; delta_r[4 * v + 1] = d4.y; delta_r[4 * v + 2] = d4.z; delta_r[4 * v + 3] = d4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            const bool ok = qb + i < p.Sq;
+                            lse_r[i] = ok ? __ldg(lse_g + qb + i) * LOG2E : 0.f;
+                            delta_r[i] = ok ? __ldg(delta_g + qb + i) : 0.f;
+                        }
+                    }
+                }
                 tmem_ld16(tSB + hb * 128 + lane_addr + cgi * 32 + hc * 16, rs);
                 tmem_ld16(tSB + hb * 128 + 64 + lane_addr + cgi * 32 + hc * 16, rd);
                 tmem_ld_wait();
@@ -1500,10 +1544,10 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
                         for (int e = 0; e < 2; e++) {
                             const int qq = hc * 16 + i + e;
-                            float pr = ex2_approx(fmaf(__uint_as_float(rs[i + e]), sl2, -lse_t[qq]));
+                            float pr = ex2_approx(fmaf(__uint_as_float(rs[i + e]), sl2, -(LDM == 1 ? lse_r[i + e] : lse_t[qq])));
                             if (qq < lo || qq >= hi) pr = 0.f;
                             pv[e] = pr;
-                            dsv[e] = pr * (__uint_as_float(rd[i + e]) - delta_t[qq]);
+                            dsv[e] = pr * (__uint_as_float(rd[i + e]) - (LDM == 1 ? delta_r[i + e] : delta_t[qq]));
                         }
                         pk[hc * 8 + (i >> 1)] = pack2(pv[0], pv[1]);
                         dk_[hc * 8 + (i >> 1)] = pack2(dsv[0], dsv[1]);
@@ -1516,9 +1560,9 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
                         for (int e = 0; e < 2; e++) {
                             const int qq = hc * 16 + i + e;
-                            const float pr = ex2_approx(fmaf(__uint_as_float(rs[i + e]), sl2, -lse_t[qq]));
+                            const float pr = ex2_approx(fmaf(__uint_as_float(rs[i + e]), sl2, -(LDM == 1 ? lse_r[i + e] : lse_t[qq])));
                             pv[e] = pr;
-                            dsv[e] = pr * (__uint_as_float(rd[i + e]) - delta_t[qq]);
+                            dsv[e] = pr * (__uint_as_float(rd[i + e]) - (LDM == 1 ? delta_r[i + e] : delta_t[qq]));
                         }
                         pk[hc * 8 + (i >> 1)] = pack2(pv[0], pv[1]);
                         dk_[hc * 8 + (i >> 1)] = pack2(dsv[0], dsv[1]);
@@ -1535,6 +1579,10 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 const int sw = ((cgi * 4 + v) ^ (key_t & 7)) << 4;
                 *reinterpret_cast<uint4*>(sP + sw) = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
                 *reinterpret_cast<uint4*>(sDS + sw) = make_uint4(dk_[4 * v], dk_[4 * v + 1], dk_[4 * v + 2], dk_[4 * v + 3]);
+            }
+            if (writer && it + 1 < n_it) {
+                lse_s[((it + 1) & 1) * 128 + qc0 + lane] = lse_next;
+                delta_s[((it + 1) & 1) * 128 + qc0 + lane] = delta_next;
             }
             tc_fence_before();
             fence_proxy_async_smem();
@@ -1921,12 +1969,17 @@ extern "C" int b200_attn_causal_bwd_tc(const void* q, const void* k, const void*
         dq_mode = (e && !strcmp(e, "red")) ? 1 : (e && !strcmp(e, "split")) ? 0 : 2;
     }
     static bool configured = false;
-    static int units = 2;
+    static int units = 2, ldm = 0;
     if (!configured) {
-        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
-        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
-        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
-        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
+        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel<0, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
+        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel<1, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
+        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel<2, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
+        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel<2, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
+        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel<2, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
+        // B200_ATTN_BWD_LSE = warp | direct | writer: how lse / delta reach the math warps (see the kernel's LDM parameter)
+        const char* l = getenv("B200_ATTN_BWD_LSE");
+        ldm = (l && !strcmp(l, "warp")) ? 0 : (l && !strcmp(l, "direct")) ? 1 : (l && !strcmp(l, "writer")) ? 2 : BWD_DEFAULT_LDM;
+        B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc05_kernel<2, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD_BYTES), "attn_bwd_tc smem");
         // B200_ATTN_BWD_UNITS = 2 | 4: pipeline units per query tile of the default (TMA reduce) kernel
         const char* u = getenv("B200_ATTN_BWD_UNITS");
         units = (u && u[0] == '2') ? 2 : (u && u[0] == '4') ? 4 : BWD_DEFAULT_UNITS;
@@ -1938,9 +1991,11 @@ extern "C" int b200_attn_causal_bwd_tc(const void* q, const void* k, const void*
         CUtensorMap tmDQ;
         if ((rc = tc05_make_tmap_3d_f32(&tmDQ, dq_acc, W, Sq, batch, W, (long long)Sq * W, 32, BQ))) return rc;
         B200_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)batch * Sq * W * sizeof(float), stream), "attn_bwd_tc memset");
-        if (dq_mode == 2 && units == 4) attn_bwd_tc05_kernel<2, 4><<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
-        else if (dq_mode == 2) attn_bwd_tc05_kernel<2, 2><<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
-        else attn_bwd_tc05_kernel<1, 2><<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
+        if (dq_mode == 2 && units == 4) attn_bwd_tc05_kernel<2, 4, 0><<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
+        else if (dq_mode == 2 && ldm == 1) attn_bwd_tc05_kernel<2, 2, 1><<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
+        else if (dq_mode == 2 && ldm == 2) attn_bwd_tc05_kernel<2, 2, 2><<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
+        else if (dq_mode == 2) attn_bwd_tc05_kernel<2, 2, 0><<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
+        else attn_bwd_tc05_kernel<1, 2, 0><<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
         B200_CHECK_LAUNCH("attn_causal_bwd_tc");
         const long long rows = (long long)batch * Sq;
         long long nthr = rows * (W / 16);
@@ -1950,7 +2005,7 @@ extern "C" int b200_attn_causal_bwd_tc(const void* q, const void* k, const void*
                                                                 (const bf16*)rope_cos, (const bf16*)rope_sin);
         B200_CHECK_LAUNCH("attn_bwd_dq_finalize");
     } else {
-        attn_bwd_tc05_kernel<0, 2><<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmQ, p);
+        attn_bwd_tc05_kernel<0, 2, 0><<<grid, BWD_THREADS, SMEM_BWD_BYTES, stream>>>(tmQ, tmK, tmV, tmdO, tmQ, p);
         B200_CHECK_LAUNCH("attn_causal_bwd_tc_dkv");
         DqParams dp;
         dp.lse = lse; dp.delta = delta; dp.dq = (bf16*)dq; dp.dq_b = strides[15]; dp.dq_r = strides[16];
