@@ -78,6 +78,11 @@ int b200_rope_qk(void* qkv, const void* cos_t, const void* sin_t, int rows, int 
 int b200_swiglu_fwd(const void* gu, void* act, long long rows, int I, cudaStream_t s);
 int b200_swiglu_bwd(const void* gu, const void* dact, void* dgu, long long rows, int I, cudaStream_t s);
 
+/* ---- LoRA scaling (train.py:439-449 -> peft lora/layer.py Linear.forward `* scaling`): y = bf16(x * scale) over n
+ *      elements.  The adapter itself runs on b200_gemm_bf16: t = x A^T, y += (scale t) B^T through the residual
+ *      epilogue, and the four gradient GEMMs (midi_b200/engine.py::StackEngine._lora_fwd/_lora_bwd). */
+int b200_scale_bf16(const void* x, void* y, long long n, float scale, cudaStream_t s);
+
 /* ---- tensor-core GEMM (tcgen05 / TMEM / TMA): every nn.Linear of hf modeling_llama.py:177-184,
  *      238-264, 288 and lm_head (midi_model.py:135), plus their dgrad / wgrad.
  *      C[M,N] = A . B^T, fp32 accumulate, bf16 out.  a_mn_major / b_mn_major = operand stored [K, rows].

@@ -518,6 +518,21 @@ __global__ void swiglu_fwd_kernel(const bf16* __restrict__ gu, bf16* __restrict_
         *reinterpret_cast<uint4*>(act + r * I + c) = pack8(o);
     }
 }
+// y = bf16(x * s): the LoRA scaling lora_alpha / r applied to the rank-r down-projection and to its gradient
+// (peft lora/layer.py Linear.forward: `lora_B(lora_A(x)) * scaling`); 16-byte vectors, scalar tail
+__global__ void scale_bf16_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, size_t n, float s) {
+    const size_t nvec = n / 8;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+        float v[8];
+        unpack8(ld_nc16(x + i * 8), v);
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] *= s;
+        *reinterpret_cast<uint4*>(y + i * 8) = pack8(v);
+    }
+    if (blockIdx.x == 0)
+        for (size_t i = nvec * 8 + threadIdx.x; i < n; i += blockDim.x)
+            y[i] = __float2bfloat16_rn(__bfloat162float(x[i]) * s);
+}
 // dg = dact * u * silu'(g), du = dact * silu(g)
 __global__ void swiglu_bwd_kernel(const bf16* __restrict__ gu, const bf16* __restrict__ dact, bf16* __restrict__ dgu,
                                   size_t rows, int I) {
@@ -751,6 +766,14 @@ extern "C" int b200_swiglu_fwd(const void* gu, void* act, long long rows, int I,
     if (rows == 0) return B200_OK;
     swiglu_fwd_kernel<<<grid_for((size_t)rows * (I / 8), 256), 256, 0, stream>>>((const bf16*)gu, (bf16*)act, rows, I);
     B200_CHECK_LAUNCH("swiglu_fwd");
+    return B200_OK;
+}
+
+extern "C" int b200_scale_bf16(const void* x, void* y, long long n, float s, cudaStream_t stream) {
+    B200_CHECK_ARG(n >= 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0, "scale: operands must be 16-byte aligned");
+    if (n == 0) return B200_OK;
+    scale_bf16_kernel<<<grid_for((size_t)n / 8 + 1, 256), 256, 0, stream>>>((const bf16*)x, (bf16*)y, (size_t)n, s);
+    B200_CHECK_LAUNCH("scale_bf16");
     return B200_OK;
 }
 

@@ -37,6 +37,7 @@ SIGNATURES = {
     "b200_rope_qk": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
     "b200_swiglu_fwd": (i32, [vp, vp, i64, i32, vp]),
     "b200_swiglu_bwd": (i32, [vp, vp, vp, i64, i32, vp]),
+    "b200_scale_bf16": (i32, [vp, vp, i64, f32, vp]),
     "b200_gemm_workspace_bytes": (sz, [i32, i32, i32]),
     "b200_gemm_tail_workspace_bytes": (sz, [i32, i32, i32, i32]),
     "b200_gemm_suggest_splits": (i32, [i32, i32, i32, i32]),

@@ -144,6 +144,16 @@ def swiglu_bwd(gu: torch.Tensor, dact: torch.Tensor) -> torch.Tensor:
     return dgu
 
 
+def scale(x: torch.Tensor, s: float) -> torch.Tensor:
+    """bf16(x * s) as a new tensor (x itself when s == 1): the LoRA scaling lora_alpha / r (peft lora/layer.py: `* scaling`)."""
+    if s == 1.0:
+        return x
+    _check(x, "scale input")
+    y = torch.empty_like(x)
+    lib.call("b200_scale_bf16", x.data_ptr(), y.data_ptr(), x.numel(), float(s), lib.stream())
+    return y
+
+
 # ------------------------------------------------------------------ GEMM
 _plan_cache: dict = {}
 

@@ -32,8 +32,9 @@ from transformers import DynamicCache, LlamaConfig, LlamaModel, PretrainedConfig
 from midi_b200 import decode as _dec
 from midi_b200 import engine as _engine
 from midi_b200 import lib as _lib
+from midi_b200 import lora as _lora
 from midi_b200 import ops as _ops
-from midi_b200.engine import ParamStore, StackCfg, StackEngine
+from midi_b200.engine import MergedStack, ParamStore, StackCfg, StackEngine
 from midi_b200.tokenizer_tables import make_tokenizer
 
 config_name_list = ["tv1-medium", "tv2-medium", "tv2o-medium", "tv2-large", "tv2o-large"]
@@ -104,15 +105,27 @@ class MIDIModelConfig(PretrainedConfig):
 # ---------------------------------------------------------------------------------------------
 class _Runtime:
     def __init__(self, model: "MIDIModel"):
+        # LoRA adapters injected by peft or by MIDIModel.add_adapter (train.py:439-449): projection path -> A, B, scaling
+        self.lora_sites = _lora.find_sites(model)
+        for path in self.lora_sites:
+            if not (path.startswith("net.layers.") or path.startswith("net_token.layers.")):
+                raise _lib.B200Error(f"LoRA on {path} is not supported (adapters go on the decoder layers' projections)")
         self.store = ParamStore(model)
         nc, tc = model.config.net_config, model.config.net_token_config
         self.outer = StackEngine(self.store, StackCfg("net", nc.num_hidden_layers, nc.num_attention_heads, nc.hidden_size,
-                                                      nc.intermediate_size, nc.rms_norm_eps), tiny_attention=False)
+                                                      nc.intermediate_size, nc.rms_norm_eps), tiny_attention=False,
+                                 lora_sites=self.lora_sites)
         self.inner = StackEngine(self.store, StackCfg("net_token", tc.num_hidden_layers, tc.num_attention_heads,
                                                       tc.hidden_size, tc.intermediate_size, tc.rms_norm_eps),
-                                 tiny_attention=True)
+                                 tiny_attention=True, lora_sites=self.lora_sites)
+        self.has_lora = self.outer.has_lora or self.inner.has_lora
+        self.peft_flag = bool(getattr(model, "_hf_peft_config_loaded", False))
+        self.lora_params = [p for n, p in model.named_parameters() if ".lora_" in n]
+        self.lora_step = 0                      # bumped by the fused optimizer (raw-pointer updates have no _version)
+        self.merged_version = None              # adapter version the merged decode weights were folded at
         self.lm_head = self.store.views["lm_head.weight"]
-        self.g_lm_head = self.store.gviews["lm_head.weight"]
+        self.tr_lm_head = self.store.trainable("lm_head.weight")
+        self.g_lm_head = self.store.gviews["lm_head.weight"] if self.tr_lm_head else None
         self.V = self.lm_head.shape[0]
         self.pitch = (self.V + 7) // 8 * 8
         self.H = nc.hidden_size
@@ -126,6 +139,10 @@ class _Runtime:
         # then returns it.  `pool_lock` only guards the free list.
         self.gen_pool = {}                      # key -> [idle GraphGenerator]
         self.pool_lock = threading.Lock()
+
+    def lora_version(self):
+        """Changes whenever an adapter matrix was updated (torch optimizers bump _version; the fused AdamW bumps lora_step)."""
+        return (self.lora_step, sum(p._version for p in self.lora_params))
 
 
 def _flat_ids(x: torch.Tensor) -> torch.Tensor:
@@ -155,10 +172,11 @@ class _OuterFn(torch.autograd.Function):
         g = rt.outer.fresh_grads()
         dy2 = dy.reshape(B * S, -1).to(torch.bfloat16).contiguous()
         de = rt.outer.backward(ctx.sv, dy2, g, accumulate=False)
-        _ops.embed_bwd(ctx.ids.view(-1), de, g.embed, per_row=T, row_stride=1, row_inner=0, row_off=0,
-                       pad_id=model.config.net_config.pad_token_id, accumulate=False)
+        if g.embed is not None:
+            _ops.embed_bwd(ctx.ids.view(-1), de, g.embed, per_row=T, row_stride=1, row_inner=0, row_off=0,
+                           pad_id=model.config.net_config.pad_token_id, accumulate=False)
         ctx.sv = None
-        return (None, None, *g.named(rt.store, rt.outer.names))
+        return (None, None, *g.named(rt.outer.names))
 
 
 class _InnerFn(torch.autograd.Function):
@@ -191,11 +209,10 @@ class _InnerFn(torch.autograd.Function):
             dl = torch.zeros((N * L, rt.pitch), dtype=torch.bfloat16, device=dlogits.device)
             dl[:, :rt.V] = dlogits.reshape(N * L, rt.V)
         g = rt.inner.fresh_grads()
-        g_head = torch.empty_like(rt.lm_head)
+        g_head = torch.empty_like(rt.lm_head) if rt.tr_lm_head else None
         dhidden, = _inner_backward(rt, model, ctx.sv, ctx.hs, dl, ctx.ids, N, L, n_ids, has_hidden, g, g_head, False)
         ctx.sv = ctx.hs = None
-        lm = [g_head] if model.lm_head.weight.requires_grad else [None]
-        return (None, dhidden, None, *g.named(rt.store, rt.inner.names), *lm)
+        return (None, dhidden, None, *g.named(rt.inner.names), g_head)
 
 
 def _as_pitched(t: torch.Tensor, rows: int, pitch: int):
@@ -280,10 +297,13 @@ def _inner_backward(rt, model, sv, hs, dlogits, ids, N, L, n_ids, has_hidden, g,
     """dlogits [N*L, pitch] -> grads of lm_head, the token-level stack, its embedding; returns (dhidden,)."""
     # lm_head weight gradient on the engine's side stream (joined at the end of rt.inner.backward)
     side = _engine._side_stream(dlogits.device) if _engine.WGRAD_STREAM else None
-    _engine._wgrad(dlogits, hs, g_head, accumulate, side)
+    if g_head is not None:                       # None: lm_head is frozen (LoRA run, train.py:440)
+        _engine._wgrad(dlogits, hs, g_head, accumulate, side)
     dhs = _ops.linear_dgrad(dlogits, rt.lm_head)
     dx = rt.inner.backward(sv, dhs, g, accumulate=accumulate)
-    if n_ids > 0:
+    if g.embed is None:
+        pass
+    elif n_ids > 0:
         _ops.embed_bwd(ids.view(-1), dx, g.embed, per_row=n_ids, row_stride=L, row_inner=1, row_off=1 if has_hidden else 0,
                        pad_id=model.config.net_token_config.pad_token_id, accumulate=accumulate)
     else:
@@ -326,14 +346,61 @@ class MIDIModel(PreTrainedModel):
     # ------------------------------------------------------------------ plumbing
     def _rt(self) -> _Runtime:
         rt = self.__dict__.get("_b200_rt")
-        if rt is None or not rt.store.valid():
-            if getattr(self, "_hf_peft_config_loaded", False):
-                raise _lib.B200Error("LoRA adapters are injected: merge them first (load_merge_lora); the sm_100a "
-                                     "kernels read the base weights only")
+        if rt is None or not rt.store.valid() or rt.peft_flag != bool(getattr(self, "_hf_peft_config_loaded", False)):
             _lib.load()
             rt = _Runtime(self)
             self.__dict__["_b200_rt"] = rt
         return rt
+
+    # ------------------------------------------------------------------ LoRA (train.py:439-449, 234-244, 263-264)
+    def add_adapter(self, adapter_config, adapter_name: Optional[str] = None):
+        """`model.add_adapter(LoraConfig(...))` as train.py:449 calls it.  With peft installed this is transformers' own
+        PeftAdapterMixin.add_adapter; without it the adapter modules are created natively in peft's layout
+        (midi_b200/lora.py): either way the engine finds `<proj>.lora_A/.lora_B.<adapter>.weight` next to
+        `<proj>.base_layer.weight`, computes y = W x + (lora_alpha / r) B A x in both stacks and trains A, B only."""
+        try:
+            import peft  # noqa: F401
+            have_peft = True
+        except ImportError:
+            have_peft = False
+        if have_peft:
+            out = super().add_adapter(adapter_config, adapter_name)
+            self.__dict__["_b200_rt"] = None
+            return out
+        adapter_name = adapter_name or "default"
+        cfg = _lora.LoraAdapterConfig.from_any(adapter_config)
+        if not self._hf_peft_config_loaded:
+            self._hf_peft_config_loaded = True
+            self.peft_config = {}
+        elif adapter_name in self.peft_config:
+            raise ValueError(f"Adapter with name {adapter_name} already exists. Please use a different name.")
+        _lora.inject(self, cfg, adapter_name)
+        self.peft_config[adapter_name] = cfg
+        self.__dict__["_b200_native_lora"] = adapter_name
+        self.__dict__["_b200_rt"] = None
+
+    def active_adapters(self):
+        if self.__dict__.get("_b200_native_lora") is not None:
+            return [self.__dict__["_b200_native_lora"]]
+        return super().active_adapters()
+
+    def get_adapter_state_dict(self, adapter_name: Optional[str] = None, state_dict=None):
+        if self.__dict__.get("_b200_native_lora") is not None:
+            return _lora.adapter_state_dict(self, adapter_name or self.active_adapters()[0])
+        return super().get_adapter_state_dict(adapter_name) if state_dict is None else \
+            super().get_adapter_state_dict(adapter_name, state_dict)
+
+    def load_adapter_weights(self, adapter_dir_or_state_dict, adapter_name: Optional[str] = None) -> None:
+        """Resume LoRA training: load `adapter_model.safetensors` (train.py:241-244) / a state dict into the injected
+        adapter WITHOUT merging (load_merge_lora is the inference-side merge)."""
+        sd = adapter_dir_or_state_dict
+        if not isinstance(sd, dict):
+            from safetensors.torch import load_file
+            sd = load_file(os.path.join(sd, "adapter_model.safetensors"))
+        _lora.load_adapter_state_dict(self, sd, adapter_name or self.active_adapters()[0])
+        rt = self.__dict__.get("_b200_rt")
+        if rt is not None:
+            rt.lora_step += 1
 
     def load_merge_lora(self, model_id):
         """midi_model.py:109-114: merge a LoRA adapter into the base weights and return the merged model.
@@ -429,15 +496,32 @@ class MIDIModel(PreTrainedModel):
             setattr(cache, "_b200_" + which, st)
         return st.kv
 
-    def _cached_stack(self, which: str):
+    def _refresh_merged(self, rt) -> None:
+        """Inference on a model with injected adapters (train.py:216-233 samples from the LoRA model while it trains): the
+        decode kernels read private merged copies W + scale * B A (engine.MergedStack), re-folded whenever an adapter
+        changed -- which also retires the idle generate loops built on the old copies."""
+        if not rt.has_lora:
+            return
+        ver = rt.lora_version()
+        if rt.merged_version != ver:
+            with rt.pool_lock:
+                rt.merged_version = ver
+                rt.cached_outer = rt.cached_inner = None
+                rt.gen_pool.clear()
+
+    def _cached_stack(self, which: str, refresh: bool = True):
         rt = self._rt()
+        if refresh:
+            self._refresh_merged(rt)
         if which == "outer":
             if rt.cached_outer is None:
-                rt.cached_outer = _dec.CachedStack(rt.outer, self.config.net_config.max_position_embeddings,
+                eng = MergedStack(rt.outer) if rt.outer.has_lora else rt.outer
+                rt.cached_outer = _dec.CachedStack(eng, self.config.net_config.max_position_embeddings,
                                                    self.net.rotary_emb.inv_freq)
             return rt.cached_outer
         if rt.cached_inner is None:
-            rt.cached_inner = _dec.CachedStack(rt.inner, 8, self.net_token.rotary_emb.inv_freq)
+            eng = MergedStack(rt.inner) if rt.inner.has_lora else rt.inner
+            rt.cached_inner = _dec.CachedStack(eng, 8, self.net_token.rotary_emb.inv_freq)
         return rt.cached_inner
 
     # ------------------------------------------------------------------ reference API
@@ -535,6 +619,7 @@ class MIDIModel(PreTrainedModel):
         gen_dev = generator.device if generator is not None else torch.device("cpu")
         seed = int(torch.randint(0, 2 ** 62, (1,), generator=generator, device=gen_dev).item())
         key = (batch_size, max_len, float(temp), float(top_p), int(top_k))
+        self._refresh_merged(rt)
         with rt.pool_lock:
             idle = rt.gen_pool.get(key)
             gg = idle.pop() if idle else None
@@ -543,7 +628,7 @@ class MIDIModel(PreTrainedModel):
                     del rt.gen_pool[k]
                 if rt.grammar is None:
                     rt.grammar = _dec.GrammarLUT(self.tokenizer, rt.store.device)
-                outer, inner = self._cached_stack("outer"), self._cached_stack("inner")
+                outer, inner = self._cached_stack("outer", refresh=False), self._cached_stack("inner", refresh=False)
         if gg is None:
             gg = _dec.GraphGenerator(outer, inner, rt.lm_head, rt.pitch, rt.V, self.tokenizer, rt.grammar, batch_size,
                                      max_len, temp, top_p, top_k, seed)
@@ -701,12 +786,15 @@ class MIDIModel(PreTrainedModel):
             dhidden, = _inner_backward(rt, self, sv_i, hs, logits, ids_in, B * S, T, T - 1, True, g_i, rt.g_lm_head,
                                        accumulate)
             del logits, hs
-            if grad_ready is not None:
-                grad_ready(rt.inner.seg_start, rt.store.numel)
+            # Gradient hand-over to a data-parallel trainer.  Base parameters that train (full training): slices of the flat
+            # buffer as backward finishes them.  Adapter matrices (LoRA, train.py:439-449) sit in the tail
+            # [base_numel, numel) and are handed over in one piece at the end (40 MB for r = 64 on tv2o-medium).
+            base_sync = grad_ready is not None and (rt.inner.base_trainable or rt.outer.base_trainable or rt.tr_lm_head)
+            if base_sync:
+                grad_ready(rt.inner.seg_start, rt.store.base_numel)
             layer_done = None
-            if grad_ready is not None:
+            if base_sync:
                 # event-level stack: hand finished gradients over in groups of 3 layers while backward continues
-                nl = rt.outer.cfg.n_layer
                 hi = [rt.inner.seg_start]
 
                 def layer_done(li):
@@ -718,48 +806,65 @@ class MIDIModel(PreTrainedModel):
                         grad_ready(lo, hi[0])
                         hi[0] = lo
             de = rt.outer.backward(sv_o, dhidden, g_o, accumulate=accumulate, layer_done=layer_done)
-            _ops.embed_bwd(x.view(-1), de, g_o.embed, per_row=T, row_stride=1, row_inner=0, row_off=0,
-                           pad_id=self.config.net_config.pad_token_id, accumulate=accumulate)
-            if grad_ready is not None:
+            if g_o.embed is not None:
+                _ops.embed_bwd(x.view(-1), de, g_o.embed, per_row=T, row_stride=1, row_inner=0, row_off=0,
+                               pad_id=self.config.net_config.pad_token_id, accumulate=accumulate)
+            if base_sync:
                 grad_ready(0, hi[0])          # embedding table (+ whatever is left)
+            if grad_ready is not None and rt.store.numel > rt.store.base_numel:
+                grad_ready(rt.store.base_numel, rt.store.numel)
             rt.store.publish_grads()
         return loss
 
     def _opt_state(self, rt):
-        """AdamW moments over the flat parameter buffer (fp32).  They live on the MODEL, not on the runtime, so they
-        survive a runtime rebuild (the flat layout is a function of named_parameters() only); a model whose parameter
-        list changed gets fresh moments and says so."""
+        """AdamW moments (fp32) over the trainable span of the flat parameter buffer -- everything in full training, the
+        adapter tail in a LoRA run.  They live on the MODEL, not on the runtime, so they survive a runtime rebuild (the flat
+        layout is a function of named_parameters() only); a model whose trainable span changed gets fresh moments and says
+        so."""
+        store = rt.store
+        if not store.train_dense:
+            raise _lib.B200Error("fused optimizer: frozen parameters sit between trainable ones in the flat buffer (it "
+                                 "supports full training and LoRA-only training); use a torch optimizer on "
+                                 "model.parameters() for other mixes")
         st = self.__dict__.get("_b200_opt")
-        n, dev = rt.store.numel, rt.store.device
-        if st is not None and (st["m"].numel() != n or st["m"].device != dev):
-            if st["m"].numel() != n:
+        lo, hi, dev = store.train_lo, store.train_hi, store.device
+        n = hi - lo
+        if st is not None and (st["m"].numel() != n or st.get("span") != (lo, hi) or st["m"].device != dev):
+            if st["m"].numel() != n or st.get("span") != (lo, hi):
                 import warnings
-                warnings.warn("fused AdamW: the parameter list changed; optimizer moments restart from zero")
+                warnings.warn("fused AdamW: the set of trainable parameters changed; optimizer moments restart from zero")
                 st = None
             else:
-                st = {k: v.to(dev) for k, v in st.items()}
+                st = {k: (v.to(dev) if isinstance(v, torch.Tensor) and k != "step" else v) for k, v in st.items()}
                 self.__dict__["_b200_opt"] = st
         if st is None:
             st = dict(m=torch.zeros(n, dtype=torch.float32, device=dev), v=torch.zeros(n, dtype=torch.float32, device=dev),
-                      nc=torch.zeros(2, dtype=torch.float32, device=dev), step=torch.zeros(1, dtype=torch.int64))
+                      nc=torch.zeros(2, dtype=torch.float32, device=dev), step=torch.zeros(1, dtype=torch.int64),
+                      span=(lo, hi))
             self.__dict__["_b200_opt"] = st
         return st
 
     def fused_optimizer_step(self, lr: float, step: int, weight_decay: float = 0.01, betas=(0.9, 0.99), eps: float = 1e-8,
                              max_grad_norm: float = 1.0):
-        """Global-norm clip (train.py:464) + AdamW with the no-decay split (train.py:121-138) over the flat
-        parameter / gradient buffers: two small reductions and one update launch."""
+        """Global-norm clip (train.py:464) + AdamW with the no-decay split (train.py:121-138) over the trainable span of
+        the flat parameter / gradient buffers: two small reductions and one update launch."""
         rt = self._rt()
         st = self._opt_state(rt)
-        n = rt.store.numel
+        lo, hi = st["span"]
+        n = hi - lo
+        if n == 0:
+            raise _lib.B200Error("fused optimizer: the model has no trainable parameters")
+        align = _engine.ALIGN
         parts = _lib.query("b200_gradnorm_parts")
         ws = _ops._ws("gradnorm", parts * 4, rt.store.device)
-        _lib.call("b200_grad_clip_coef", rt.store.gflat.data_ptr(), n, float(max_grad_norm), st["nc"].data_ptr(),
+        gptr, pptr = rt.store.gflat.data_ptr() + 2 * lo, rt.store.flat.data_ptr() + 2 * lo
+        _lib.call("b200_grad_clip_coef", gptr, n, float(max_grad_norm), st["nc"].data_ptr(),
                   ws.data_ptr(), ws.numel(), _lib.stream())
-        _lib.call("b200_adamw_step", rt.store.flat.data_ptr(), rt.store.gflat.data_ptr(), st["m"].data_ptr(),
-                  st["v"].data_ptr(), rt.store.nodecay.data_ptr(), n, float(lr), float(betas[0]), float(betas[1]),
+        _lib.call("b200_adamw_step", pptr, gptr, st["m"].data_ptr(),
+                  st["v"].data_ptr(), rt.store.nodecay.data_ptr() + lo // align, n, float(lr), float(betas[0]), float(betas[1]),
                   float(eps), float(weight_decay), int(step), st["nc"].data_ptr(), _lib.stream())
         st["step"][0] = int(step)
+        rt.lora_step += 1
         return st["nc"]
 
     def optimizer_state_dict(self) -> Dict[str, Any]:
@@ -769,9 +874,12 @@ class MIDIModel(PreTrainedModel):
         if st is None:
             return {"step": 0, "state": {}}
         rt = self._rt()
+        lo, hi = st["span"]
         out = {}
         for name in rt.store.names:
-            o, v = rt.store.offsets[name], rt.store.views[name]
+            o, v = rt.store.offsets[name] - lo, rt.store.views[name]
+            if not (lo <= rt.store.offsets[name] < hi):
+                continue                                   # frozen (e.g. the base of a LoRA run): no moments
             out[name] = {"exp_avg": st["m"][o:o + v.numel()].view(v.shape).cpu().clone(),
                          "exp_avg_sq": st["v"][o:o + v.numel()].view(v.shape).cpu().clone()}
         return {"step": int(st["step"][0]), "state": out}
@@ -782,10 +890,13 @@ class MIDIModel(PreTrainedModel):
         st = self._opt_state(rt)
         st["m"].zero_()
         st["v"].zero_()
+        lo, hi = st["span"]
         for name, ent in sd.get("state", {}).items():
             if name not in rt.store.offsets:
                 raise KeyError(f"load_optimizer_state_dict: unknown parameter {name}")
-            o, v = rt.store.offsets[name], rt.store.views[name]
+            if not (lo <= rt.store.offsets[name] < hi):
+                raise KeyError(f"load_optimizer_state_dict: {name} is not trainable in this model")
+            o, v = rt.store.offsets[name] - lo, rt.store.views[name]
             if tuple(ent["exp_avg"].shape) != tuple(v.shape):
                 raise ValueError(f"load_optimizer_state_dict: {name}: shape {tuple(ent['exp_avg'].shape)} vs {tuple(v.shape)}")
             st["m"][o:o + v.numel()].view(v.shape).copy_(ent["exp_avg"])

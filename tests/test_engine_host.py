@@ -1,0 +1,208 @@
+"""Host logic of the engine on CPU: the layer schedule, gradient placement, LoRA composition (train.py:439-449), the
+optimizer span and the autograd Functions, run over the CPU stand-in for the kernel layer (tests/mock_kernels.py) and
+compared with the oracle's autograd.  The CUDA kernels themselves are checked on the GPU (tests/gpu_checks.py)."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import mock_kernels
+
+BF = torch.bfloat16
+TARGETS = ["q_proj", "o_proj", "k_proj", "v_proj", "gate_proj", "up_proj", "down_proj"]      # train.py:443
+
+
+def _tiny_model(seed=0):
+    import midi_model as mm
+    torch.manual_seed(seed)
+    cfg = mm.MIDIModelConfig.get_config("v2", True, n_layer=4, n_head=4, n_embd=256, n_inner=512)
+    return mm, cfg, mm.MIDIModel(cfg).to(BF).train()
+
+
+def _batch(model, B=2, S1=6, seed=1):
+    from midi_b200.synth import synth_batch
+    return synth_batch(model.tokenizer, B, S1, seed=seed)
+
+
+def _oracle_grads(model, batch, lora_scale=None):
+    """Loss and gradients from the oracle (fp32 autograd over the bf16-rounded weights).  With adapters: the effective
+    weight W + scale * B A is formed differentiably, so the gradients of A and B are those of peft's unmerged forward."""
+    from oracle import midi_oracle as O
+    leaf = {n: p.detach().float().requires_grad_(True) for n, p in model.named_parameters()}
+    sd = {}
+    for n, t in leaf.items():
+        if ".lora_" in n:
+            continue
+        if n.endswith(".base_layer.weight"):
+            path = n[:-len(".base_layer.weight")]
+            a = [k for k in leaf if k.startswith(path + ".lora_A.")][0]
+            b = [k for k in leaf if k.startswith(path + ".lora_B.")][0]
+            sd[path + ".weight"] = t + lora_scale * (leaf[b] @ leaf[a])
+        else:
+            sd[n] = t
+    loss = O.train_loss(sd, O.cfg_from_hf(model.config), batch)
+    loss.backward()
+    return float(loss.detach()), {n: t.grad for n, t in leaf.items()}
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+def test_engine_schedule_matches_oracle_autograd(monkeypatch):
+    mock_kernels.install(monkeypatch)
+    mm, cfg, model = _tiny_model()
+    batch = _batch(model)
+    ref_loss, ref = _oracle_grads(model, batch)
+    loss = model.training_loss(batch)
+    assert abs(float(loss) - ref_loss) < 3e-2
+    num = sum(float((p.grad.double() - ref[n].double()).pow(2).sum()) for n, p in model.named_parameters())
+    den = sum(float(ref[n].double().pow(2).sum()) for n in ref)
+    assert (num / den) ** 0.5 < 3e-2
+    rt = model._rt()
+    assert rt.store.base_numel == rt.store.numel and rt.store.train_dense and (rt.store.train_lo, rt.store.train_hi) == (0, rt.store.numel)
+
+
+def _lora_model(monkeypatch, r=8, alpha=16, seed=0):
+    from midi_b200 import lora
+    mock_kernels.install(monkeypatch)
+    mm, cfg, model = _tiny_model(seed)
+    model.requires_grad_(False)                                              # train.py:440
+    model.add_adapter(lora.LoraAdapterConfig(r=r, lora_alpha=alpha, target_modules=TARGETS, lora_dropout=0, bias="none",
+                                             task_type="CAUSAL_LM"))          # train.py:441-449
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():                                                    # B = 0 at init would zero dA: make it non-trivial
+        for n, p in model.named_parameters():
+            if ".lora_B." in n:
+                p.copy_((torch.randn(p.shape, generator=g) * 0.02).to(BF))
+    return mm, model
+
+
+def test_lora_container_layout_and_flat_store(monkeypatch):
+    mm, model = _lora_model(monkeypatch)
+    names = [n for n, _ in model.named_parameters()]
+    assert "net.layers.0.self_attn.q_proj.base_layer.weight" in names
+    assert "net.layers.0.self_attn.q_proj.lora_A.default.weight" in names
+    assert "net_token.layers.0.mlp.down_proj.lora_B.default.weight" in names
+    assert all(p.requires_grad == (".lora_" in n) for n, p in model.named_parameters())
+    assert model._hf_peft_config_loaded and model.active_adapters() == ["default"]
+    sd = model.get_adapter_state_dict("default")
+    assert "net.layers.0.self_attn.q_proj.lora_A.weight" in sd and len(sd) == 2 * 7 * 5           # 4 + 1 layers
+    rt = model._rt()
+    st = rt.store
+    # adapters form the contiguous trainable tail of the flat buffer; base layout unchanged (fused q|k|v, gate|up views)
+    assert st.base_numel < st.numel and (st.train_lo, st.train_hi) == (st.base_numel, st.numel) and st.train_dense
+    assert all((st.offsets[n] >= st.base_numel) == (".lora_" in n) for n in st.names)
+    a = "net.layers.2.self_attn."
+    aq, ak, av = (st.views[a + f"{p}_proj.lora_A.default.weight"] for p in "qkv")
+    assert ak.data_ptr() == aq.data_ptr() + aq.numel() * 2 and av.data_ptr() == ak.data_ptr() + ak.numel() * 2
+    assert rt.outer.layers[2].qkv.shape == (3 * 256, 256) and not rt.outer.layers[2].tr_qkv
+    assert set(rt.outer.layers[0].lora) == {"q", "k", "v", "o", "gate", "up", "down"} and rt.has_lora
+    assert rt.outer.main_grads.layers[0].qkv is None and rt.outer.main_grads.embed is None
+
+
+def test_lora_fused_training_matches_oracle(monkeypatch):
+    mm, model = _lora_model(monkeypatch)
+    batch = _batch(model)
+    ref_loss, ref = _oracle_grads(model, batch, lora_scale=2.0)
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    calls = []
+    loss = model.training_loss(batch, grad_ready=lambda a, b: calls.append((a, b)))
+    assert abs(float(loss) - ref_loss) < 3e-2
+    rt = model._rt()
+    assert calls == [(rt.store.base_numel, rt.store.numel)]                  # one hand-over: the adapter tail
+    worst = 0.0
+    for n, p in model.named_parameters():
+        if ".lora_" in n:
+            assert p.grad is not None and ref[n].abs().max() > 0
+            worst = max(worst, _rel(p.grad.float(), ref[n]))
+        else:
+            assert p.grad is None
+    assert worst < 6e-2, worst
+    # the fused optimizer runs over the adapter tail only: frozen base bit-identical, every adapter matrix moved
+    model.fused_optimizer_step(lr=1e-2, step=1)
+    for n, p in model.named_parameters():
+        assert torch.equal(p, before[n]) != (".lora_" in n), n
+    osd = model.optimizer_state_dict()
+    assert osd["step"] == 1 and set(osd["state"]) == {n for n in before if ".lora_" in n}
+    model.load_optimizer_state_dict(osd)
+
+
+def test_lora_dropin_autograd_path_matches_fused(monkeypatch):
+    mm, model = _lora_model(monkeypatch)
+    batch = _batch(model)
+    model.training_loss(batch)
+    fused = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    for p in model.parameters():
+        p.grad = None
+    x, y = batch[:, :-1].contiguous(), batch[:, 1:].contiguous()             # train.py:169-185
+    hidden = model.forward(x)
+    hidden = hidden.reshape(-1, hidden.shape[-1])
+    y = y.reshape(-1, y.shape[-1])
+    logits = model.forward_token(hidden, y[:, :-1])
+    loss = F.cross_entropy(logits.view(-1, model.tokenizer.vocab_size), y.view(-1), reduction="mean",
+                           ignore_index=model.tokenizer.pad_id)
+    loss.backward()
+    for n, p in model.named_parameters():
+        if ".lora_" in n:
+            assert _rel(p.grad.float(), fused[n].float()) < 2e-2, n
+        else:
+            assert p.grad is None, n
+
+
+def test_lora_save_merge_roundtrip_and_merged_decode_weights(monkeypatch, tmp_path):
+    """train.py:234-244 writes adapter_config.json + adapter_model.safetensors; midi_model.py:109-114 merges them.  The
+    merged weights the decode path folds on the device (engine.MergedStack) must be the same W + scale * B A."""
+    from safetensors.torch import save_file
+    from midi_b200.engine import MergedStack
+    mm, model = _lora_model(monkeypatch)
+    d = str(tmp_path / "lora")
+    name = model.active_adapters()[0]
+    model.peft_config[name].save_pretrained(d)
+    save_file(model.get_adapter_state_dict(name), os.path.join(d, "adapter_model.safetensors"), metadata={"format": "pt"})
+    base_sd = {n.replace(".base_layer", ""): p.detach().clone() for n, p in model.named_parameters() if ".lora_" not in n}
+    fresh = mm.MIDIModel(model.config).to(BF)
+    fresh.load_state_dict(base_sd)
+    merged = fresh.load_merge_lora(d)
+    rt = model._rt()
+    ms = MergedStack(rt.outer)
+    H = 256
+    for li in (0, 3):
+        a = f"net.layers.{li}.self_attn."
+        for j, pn in enumerate(("q_proj", "k_proj", "v_proj")):
+            W = dict(merged.named_parameters())[a + pn + ".weight"]
+            got = ms.layers[li].qkv[j * H:(j + 1) * H]
+            assert not torch.equal(W, base_sd[a + pn + ".weight"])
+            assert _rel(got.float(), W.float()) < 1e-2                       # double vs single rounding of the sum
+        Wd = dict(merged.named_parameters())[f"net.layers.{li}.mlp.down_proj.weight"]
+        assert _rel(ms.layers[li].down.float(), Wd.float()) < 1e-2
+    assert ms.layers[0].ln1 is rt.outer.layers[0].ln1 and ms.norm is rt.outer.norm
+    # resume: adapter weights load back into an injected model without merging
+    from midi_b200 import lora
+    fresh2 = mm.MIDIModel(model.config).to(BF)
+    fresh2.load_state_dict(base_sd)
+    fresh2.requires_grad_(False)
+    fresh2.add_adapter(lora.LoraAdapterConfig.from_pretrained(d))
+    fresh2.load_adapter_weights(d)
+    for (n1, p1), (n2, p2) in zip(model.named_parameters(), fresh2.named_parameters()):
+        assert n1 == n2 and torch.equal(p1, p2), n1
+
+
+def test_lora_rejects_what_the_engine_does_not_implement():
+    import midi_model as mm
+    from midi_b200 import lora
+    from midi_b200.lib import B200Error
+    torch.manual_seed(0)
+    model = mm.MIDIModel(mm.MIDIModelConfig.get_config("v2", True, n_layer=4, n_head=4, n_embd=256, n_inner=512))
+    with pytest.raises(B200Error):
+        model.add_adapter(lora.LoraAdapterConfig(r=8, target_modules=TARGETS, lora_dropout=0.1))
+    with pytest.raises(B200Error):
+        model.add_adapter(lora.LoraAdapterConfig(r=6, target_modules=TARGETS))
+    with pytest.raises(ValueError):
+        model.add_adapter(lora.LoraAdapterConfig(r=8, target_modules=["no_such_proj"]))
+    model.add_adapter(dict(r=8, lora_alpha=16, target_modules=["q_proj", "v_proj"]))
+    with pytest.raises(ValueError):
+        model.add_adapter(dict(r=8, lora_alpha=16, target_modules=["q_proj"]))          # same adapter name again
+    with pytest.raises(B200Error):
+        model.net.layers[0].self_attn.q_proj(torch.zeros(1, 256))                      # containers do not compute
