@@ -1292,6 +1292,127 @@ def check_model_medium_long():
     return out
 
 
+def check_lora_train():
+    """LoRA training (train.py:439-449: r = 64, lora_alpha = 128, all seven projections, frozen base) on the sm_100a engine.
+    (a) the rank-r GEMM shapes the adapters add, through the C ABI, incl. the in-place strided residual epilogue;
+    (b) loss and adapter gradients vs the oracle's autograd over W + scale * B A (= peft's unmerged forward in exact
+    arithmetic); the frozen base gets no gradient and is bit-identical after the fused optimizer step; drop-in autograd path
+    == fused path; (c) inference with injected adapters (merged decode weights) == the training-path forward."""
+    from midi_b200.synth import synth_batch
+    from midi_b200 import lora
+    from transformers import DynamicCache
+    out = {}
+    r = 64
+    # ---- (a) adapter GEMM shapes (rows not a multiple of 128, N = r and K = r smaller than a tile)
+    for i, rows in enumerate((1000, 4096)):
+        x, A, Bm = randn(rows, 1024, seed=200 + i), randn(r, 1024, scale=0.05, seed=210 + i), randn(1024, r, scale=0.05, seed=220 + i)
+        t = ops.linear(x, A)                                                        # [rows, r]
+        out[f"lora_gemm_down_{rows}"] = rel(t.float(), x.float() @ A.float().T)
+        ts = ops.scale(t, 2.0)
+        out[f"lora_scale_mismatch_{rows}"] = float((ts != (t.float() * 2.0).to(BF)).sum())
+        y = randn(rows, 3072, seed=230 + i)
+        y0 = y.clone()
+        yv = y[:, 1024:2048]
+        ops.gemm(ts, Bm, rows, 1024, r, lda=r, ldb=r, out=yv, ldc=3072, residual=yv)    # in place on the k third
+        ref = ((ts.float() @ Bm.float().T).to(BF).float() + y0[:, 1024:2048].float())
+        out[f"lora_gemm_up_inplace_{rows}"] = rel(y[:, 1024:2048].float(), ref)
+        out[f"lora_gemm_up_untouched_{rows}"] = float((y[:, :1024] != y0[:, :1024]).sum() + (y[:, 2048:] != y0[:, 2048:]).sum())
+        dy = randn(rows, 3072, seed=240 + i)
+        dyv = dy[:, 2048:]
+        dts = ops.gemm(dyv, Bm, rows, r, 1024, lda=3072, ldb=r, b_mn=True)          # dy . B  -> [rows, r]
+        out[f"lora_gemm_dts_{rows}"] = rel(dts.float(), dyv.float() @ Bm.float())
+        gB = torch.empty(1024, r, device=DEV, dtype=BF)
+        ops.gemm(dyv, ts, 1024, r, rows, lda=3072, ldb=r, a_mn=True, b_mn=True, out=gB, ldc=r, allow_split=True)
+        out[f"lora_gemm_gB_{rows}"] = rel(gB.float(), dyv.float().T @ ts.float())
+        gA = torch.empty(r, 1024, device=DEV, dtype=BF)
+        ops.gemm(dts, x, r, 1024, rows, lda=r, ldb=1024, a_mn=True, b_mn=True, out=gA, ldc=1024, allow_split=True)
+        refA = dts.float().T @ x.float()
+        out[f"lora_gemm_gA_{rows}"] = rel(gA.float(), refA)
+        ops.gemm(dts, x, r, 1024, rows, lda=r, ldb=1024, a_mn=True, b_mn=True, out=gA, ldc=1024, accumulate=True, allow_split=True)
+        out[f"lora_gemm_gA_accumulate_{rows}"] = rel(gA.float(), 2 * refA)
+        dx = randn(rows, 1024, seed=250 + i)
+        dx0 = dx.clone()
+        ops.gemm(dts, A, rows, 1024, r, lda=r, ldb=1024, b_mn=True, out=dx, ldc=1024, residual=dx)
+        out[f"lora_gemm_dx_inplace_{rows}"] = rel(dx.float(), (dts.float() @ A.float()).to(BF).float() + dx0.float())
+        print(f"lora: adapter GEMM shapes at {rows} rows done", flush=True)
+    torch.cuda.synchronize()
+    # ---- (b) a 4-layer model of the real width: train.py:439-449
+    mm, model = _model(4)
+    model = model.to(DEV, dtype=BF).train()
+    model.requires_grad_(False)
+    model.add_adapter(lora.LoraAdapterConfig(r=r, lora_alpha=128, target_modules=["q_proj", "o_proj", "k_proj", "v_proj",
+                                             "gate_proj", "up_proj", "down_proj"], lora_dropout=0, bias="none", task_type="CAUSAL_LM"))
+    g = torch.Generator(device="cpu").manual_seed(5)
+    with torch.no_grad():                                     # B = 0 at init would make dA vanish: give it trained-like values
+        for n, p in model.named_parameters():
+            if ".lora_B." in n:
+                p.copy_((torch.randn(p.shape, generator=g) * 0.02).to(DEV, BF))
+    ocfg = O.cfg_from_hf(model.config)
+    batch = synth_batch(model.tokenizer, 2, 66, seed=77, pad_tail=3).to(DEV)
+    leaf = {n: p.detach().float().requires_grad_(True) for n, p in model.named_parameters()}
+    sd = {}
+    for n, t in leaf.items():
+        if ".lora_" in n:
+            continue
+        if n.endswith(".base_layer.weight"):
+            path = n[:-len(".base_layer.weight")]
+            sd[path + ".weight"] = t + 2.0 * (leaf[path + ".lora_B.default.weight"] @ leaf[path + ".lora_A.default.weight"])
+        else:
+            sd[n] = t
+    ref = O.train_loss(sd, ocfg, batch)
+    ref.backward()
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    loss = model.training_loss(batch)
+    out["lora_loss_abs"] = float((loss - ref.detach()).abs())
+    print("lora: fused training step done, loss", float(loss), "oracle", float(ref.detach()), flush=True)
+    tot_n = tot_d = worst = 0.0
+    base_grads = 0
+    for n, p in model.named_parameters():
+        if ".lora_" not in n:
+            base_grads += int(p.grad is not None)
+            continue
+        gref = leaf[n].grad
+        tot_n += float((p.grad.float() - gref).double().pow(2).sum())
+        tot_d += float(gref.double().pow(2).sum())
+        worst = max(worst, rel(p.grad.float(), gref))
+    out["lora_grad_global_rel"] = math.sqrt(tot_n / tot_d)
+    out["lora_grad_worst_rel_info"] = worst
+    out["lora_base_grads_present"] = float(base_grads)
+    fused = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    model.fused_optimizer_step(lr=1e-3, step=1)
+    torch.cuda.synchronize()
+    out["lora_frozen_changed"] = float(sum(int(not torch.equal(p, before[n])) for n, p in model.named_parameters() if ".lora_" not in n))
+    out["lora_adapters_changed"] = float(sum(int(not torch.equal(p, before[n])) for n, p in model.named_parameters() if ".lora_" in n))
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            p.copy_(before[n])
+    for p in model.parameters():
+        p.grad = None
+    x, y = batch[:, :-1].contiguous(), batch[:, 1:].contiguous()
+    hidden = model.forward(x)
+    yy = y.reshape(-1, y.shape[-1])
+    logits = model.forward_token(hidden.reshape(-1, hidden.shape[-1]), yy[:, :-1])
+    l2 = F.cross_entropy(logits.view(-1, model.tokenizer.vocab_size), yy.view(-1), reduction="mean", ignore_index=model.tokenizer.pad_id)
+    l2.backward()
+    num = sum(float((p.grad.float() - fused[n].float()).double().pow(2).sum()) for n, p in model.named_parameters() if n in fused)
+    den = sum(float(fused[n].float().double().pow(2).sum()) for n in fused)
+    out["lora_dropin_vs_fused_grad_rel"] = math.sqrt(num / den)
+    print("lora: drop-in step done", flush=True)
+    out["lora_dropin_base_grads_present"] = float(sum(int(p.grad is not None) for n, p in model.named_parameters() if ".lora_" not in n))
+    # ---- (c) inference with injected adapters: KV-cached forward (merged decode weights) vs the training-path forward
+    model.eval()
+    with torch.no_grad():
+        full = model.forward(x[:, :40])
+        c = DynamicCache()
+        parts = [model.forward(x[:, :30], cache=c)] + [model.forward(x[:, t:t + 1], cache=c) for t in range(30, 40)]
+        out["lora_cached_vs_full_hidden"] = rel(torch.cat(parts, 1).float(), full.float())
+        href = O.forward({k: v.detach() for k, v in sd.items()}, ocfg, x[:, :40], inv_freq=model.net.rotary_emb.inv_freq)
+        out["lora_hidden_vs_oracle32"] = rel(full.float(), href)
+    ids = model.generate(batch_size=2, max_len=8, top_k=1)
+    out["lora_generate_len"] = float(ids.shape[1])
+    return out
+
+
 GROUPS = {
     "gemm_fwd": check_gemm_fwd, "gemm_swiglu": check_gemm_swiglu, "gemm_dgrad": check_gemm_dgrad, "gemm_wgrad": check_gemm_wgrad,
     "elementwise": check_elementwise, "fused_rope": check_fused_rope, "attn_flash": check_attn_flash, "attn_tc05": check_attn_tc05, "attn_tiny": check_attn_tiny,
@@ -1299,11 +1420,16 @@ GROUPS = {
     "model_layer_tf": check_model_layer_teacher_forced, "model_train": check_model_train,
     "model_generate": check_model_generate, "model_peaked_greedy": check_model_peaked_greedy, "model_large": check_model_large,
     "gemm_exact": check_gemm_exact, "decode_paged": check_decode_paged, "model_vs_hf": check_model_vs_hf,
-    "model_medium_long": check_model_medium_long,
+    "model_medium_long": check_model_medium_long, "lora_train": check_lora_train,
 }
 
 # metric-name prefix -> upper bound (first matching prefix wins); "min:" entries are lower bounds
 THRESH = [
+    # LoRA (train.py:439-449): rank-64 GEMM shapes, adapter gradients vs the oracle's autograd, frozen base untouched
+    ("lora_scale_mismatch", 0.0), ("lora_gemm_up_untouched", 0.0), ("lora_gemm_", 4e-3), ("lora_loss_abs", 3e-2),
+    ("lora_grad_global_rel", 6e-2), ("lora_base_grads_present", 0.0), ("lora_frozen_changed", 0.0), ("min:lora_adapters_changed", 70.0),
+    ("lora_dropin_vs_fused_grad_rel", 2e-2), ("lora_dropin_base_grads_present", 0.0), ("lora_cached_vs_full_hidden", 3e-2),
+    ("lora_hidden_vs_oracle32", 3e-2), ("min:lora_generate_len", 2.0),
     # round 2: exactness of the GEMM at benchmark shapes (fraction of non-correctly-rounded elements; fp32 summation order
     # alone moves ~1e-3 of them by one ulp, long-K split sums a few 1e-3), fused decode attention across pages, HF GPU path
     # (measured: 5.6e-4 forward K=1024, 1.7e-3..4.3e-3 dgrad K=3072/8192, 3e-3..2.2e-2 wgrad over 16 384 / 131 072 rows)

@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 GROUP_NAMES = ["gemm_fwd", "gemm_swiglu", "gemm_dgrad", "gemm_wgrad", "elementwise", "fused_rope", "attn_flash", "attn_tc05", "attn_tiny", "loss_optim", "decode",
                "model_forward", "model_layer_tf", "model_train", "model_generate", "model_peaked_greedy", "model_large",
-               "gemm_exact", "decode_paged", "model_vs_hf", "model_medium_long"]
+               "gemm_exact", "decode_paged", "model_vs_hf", "model_medium_long", "lora_train"]
 
 
 @pytest.mark.gpu
