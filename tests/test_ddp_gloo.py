@@ -67,3 +67,90 @@ def test_bucket_ranges_cover_exactly():
     assert all(e - s <= 256 for s, e in r)
     assert any(e == 300 for _, e in r) and any(e == 650 for _, e in r)
     assert ddp.bucket_ranges(0, [], 16) == []
+
+
+def _trainer_worker(rank, world, port, q, lora_mode):
+    """The fused trainer's data-parallel path end to end on CPU: training_loss(grad_ready=GradSync.ready) ->
+    GradSync.wait -> fused_optimizer_step, over the CPU stand-in for the kernel layer (tests/mock_kernels.py)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    for p in (os.path.join(ROOT, "midi-model_b200"), ROOT, os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    import pytest
+    import mock_kernels
+    mock_kernels.install(pytest.MonkeyPatch())
+    import midi_model as mm
+    from midi_b200 import ddp, lora
+    from midi_b200.synth import synth_batch
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)                                     # identical weights on every rank (as bench.py / train.py)
+    model = mm.MIDIModel(mm.MIDIModelConfig.get_config("v2", True, n_layer=4, n_head=4, n_embd=256, n_inner=512))
+    model = model.to(torch.bfloat16).train()
+    if lora_mode:
+        model.requires_grad_(False)
+        model.add_adapter(lora.LoraAdapterConfig(r=8, lora_alpha=16, target_modules=["q_proj", "v_proj", "down_proj"]))
+        g = torch.Generator().manual_seed(3)
+        with torch.no_grad():
+            for n, p in model.named_parameters():
+                if ".lora_B." in n:
+                    p.copy_((torch.randn(p.shape, generator=g) * 0.02).to(torch.bfloat16))
+    batch = synth_batch(model.tokenizer, 2, 6, seed=1234 + rank)          # per-rank shard
+    rt = model._rt()
+    st = rt.store
+    model.training_loss(batch)                                            # local gradients, no averaging
+    local = st.gflat.clone()
+    calls = []
+    sync = ddp.GradSync(st.gflat)
+
+    def ready(a, b):
+        calls.append((a, b))
+        sync.ready(a, b)
+
+    model.training_loss(batch, grad_ready=ready)
+    sync.wait()
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    mean = (sum(t.float() for t in gathered) / world)
+    lo, hi = st.train_lo, st.train_hi
+    # every trainable element was handed over exactly once; nothing outside the trainable span was touched
+    cover = torch.zeros(st.numel, dtype=torch.int32)
+    for a, b in calls:
+        cover[a:b] += 1
+    ok_cover = bool((cover[lo:hi] == 1).all()) and (not lora_mode or bool((cover[:lo] == 0).all()))
+    ok_avg = torch.allclose(st.gflat[lo:hi].float(), mean[lo:hi], rtol=2e-2, atol=1e-6)
+    before = st.flat.clone()
+    model.fused_optimizer_step(lr=1e-2, step=1)
+    flats = [torch.zeros_like(st.flat) for _ in range(world)]
+    dist.all_gather(flats, st.flat)
+    ok_same = torch.equal(flats[0], flats[1])                             # ranks stay bit-identical after the update
+    # the update touched the trainable span and nothing else (the frozen base of a LoRA run stays bit-identical)
+    moved = bool((st.flat[lo:hi] != before[lo:hi]).any()) and torch.equal(st.flat[:lo], before[:lo]) \
+        and torch.equal(st.flat[hi:], before[hi:])
+    if rank == 0:
+        q.put((ok_cover, ok_avg, ok_same, len(calls), bool(moved)))
+    dist.destroy_process_group()
+
+
+def _run_trainer(lora_mode, port_off):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + port_off) % 500
+    procs = [ctx.Process(target=_trainer_worker, args=(r, 2, port, q, lora_mode)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=300)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    return res
+
+
+def test_fused_trainer_world2_full_training():
+    ok_cover, ok_avg, ok_same, n_calls, moved = _run_trainer(False, 7)
+    assert (ok_cover, ok_avg, ok_same, moved) == (True, True, True, True)
+    assert n_calls >= 3          # token-level stack + lm_head first, then event-level layers, then the embedding table
+
+
+def test_fused_trainer_world2_lora():
+    ok_cover, ok_avg, ok_same, n_calls, moved = _run_trainer(True, 13)
+    assert (ok_cover, ok_avg, ok_same, moved) == (True, True, True, True)
+    assert n_calls == 1          # LoRA: one hand-over, the adapter tail
