@@ -57,7 +57,7 @@ METRIC = "train_tokens_per_sec"
 UNIT = "MIDI-event tokens/s"
 T_TOK = 8
 LR, WARMUP_STEPS = 2e-4, 1000.0
-DEFAULTS = {"model": "tv2o-medium", "events": 2048, "batch": 8}
+DEFAULTS = {"model": "tv2o-medium", "events": 2048, "batch": 8, "task": "train"}
 
 
 def peaks():
@@ -371,6 +371,13 @@ def run_native(args):
 
     torch.manual_seed(0)                                   # identical seeded-init weights on every rank
     model = mm.MIDIModel(mm.MIDIModelConfig.from_name(args.model)).to(dev, dtype=torch.bfloat16).train()
+    if args.task == "lora":
+        # train.py --task lora (train.py:439-449): frozen base, rank-64 adapters on all seven projections of both stacks
+        from midi_b200 import lora as _lora
+        model.requires_grad_(False)
+        model.add_adapter(_lora.LoraAdapterConfig(r=64, lora_alpha=128, lora_dropout=0, bias="none", task_type="CAUSAL_LM",
+                                                  target_modules=["q_proj", "o_proj", "k_proj", "v_proj", "gate_proj",
+                                                                  "up_proj", "down_proj"]))
     rt = model._rt()
     tok = model.tokenizer
     n_batches = 4
@@ -481,6 +488,8 @@ def run_native(args):
     peak_tf = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1400.0)))
     ach_tf = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     step_tf = train_flops_per_token(args.model, S_EVENTS) * (B_PER_GPU * S_EVENTS * T_TOK) / (ms_total / K / 1e3) / 1e12
+    if args.task == "lora":
+        step_tf = 0.0          # the full-training FLOP model does not describe a LoRA step (no base weight gradients)
 
     api_note = ("MIDIModel.training_loss + fused_optimizer_step" if args.api == "fused" else
                 "drop-in: forward -> forward_token -> F.cross_entropy -> backward -> clip_grad_norm_ -> torch fused AdamW (torch DDP at N>1)")
@@ -488,7 +497,9 @@ def run_native(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": workload_name(args), "api": api_note,
+        "config": {"workload": workload_name(args) if args.task == "train" else
+                   workload_name(args, "LoRA train step (train.py --task lora: r=64, alpha=128, frozen base; fwd+bwd+allreduce+clip+AdamW over the adapters)"),
+                   "api": api_note,
                    "global_batch": world * B_PER_GPU, "n_events": S_EVENTS, "tokens_per_event": T_TOK,
                    "parallelism": f"dp{world}", "weights": "seeded-init (torch.manual_seed(0))",
                    "l2": "per-step working set ~20 GB >> 126 MB L2 (no explicit flush needed); 4 distinct batches cycled"},
@@ -686,6 +697,7 @@ def main():
     ap.add_argument("--model", default=DEFAULTS["model"])
     ap.add_argument("--events", type=int, default=DEFAULTS["events"])
     ap.add_argument("--batch", type=int, default=DEFAULTS["batch"])
+    ap.add_argument("--task", default=DEFAULTS["task"], choices=["train", "lora"], help="full training or LoRA (train.py:298)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-generate", action="store_true")
     ap.add_argument("--no-hbm-kernels", action="store_true")
