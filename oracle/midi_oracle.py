@@ -223,6 +223,27 @@ def train_loss(sd, cfg: ModelCfg, batch: torch.Tensor) -> torch.Tensor:
     return F.cross_entropy(logits.view(-1, cfg.vocab), y.view(-1), reduction="mean", ignore_index=cfg.pad_id)
 
 
+def lora_effective_sd(sd: Dict[str, torch.Tensor], scaling: float, adapter: str = "default") -> Dict[str, torch.Tensor]:
+    """LoRA (train.py:439-449 -> `model.add_adapter(LoraConfig(...))`; merge: midi_model.py:109-114).  The arithmetic lives in
+    the un-vendored dependency `peft>=0.13.0` (requirements.txt:5), which is NOT in this image: **parity unpinned** against
+    peft itself.  Restated from its published algorithm (Hu et al. 2021, eq. 3; peft `tuners/lora/layer.py`
+    `Linear.forward`: `result = base_layer(x) + lora_B(lora_A(dropout(x))) * scaling`, `scaling = lora_alpha / r`,
+    `Linear.get_delta_weight`: `B @ A * scaling`): for every `<path>.base_layer.weight` with `<path>.lora_A/B.<adapter>.weight`
+    the effective weight `W + scaling * B A` under the reference's key `<path>.weight`.  Differentiable, so autograd through
+    it yields the adapter gradients of the unmerged forward (identical in exact arithmetic)."""
+    out = {}
+    for k, v in sd.items():
+        if ".lora_" in k:
+            continue
+        if k.endswith(".base_layer.weight"):
+            path = k[:-len(".base_layer.weight")]
+            a, b = sd[f"{path}.lora_A.{adapter}.weight"], sd[f"{path}.lora_B.{adapter}.weight"]
+            out[path + ".weight"] = v + scaling * (b @ a)
+        else:
+            out[k] = v
+    return out
+
+
 def sample_top_p_k(probs: torch.Tensor, p: float, k: int, generator=None, stable: bool = True) -> torch.Tensor:
     """midi_model.py:152-165.  `stable=True` breaks exact ties by ascending id
     (the reference's torch.sort is unstable; its tie order is implementation

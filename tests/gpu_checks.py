@@ -1350,15 +1350,7 @@ def check_lora_train():
     ocfg = O.cfg_from_hf(model.config)
     batch = synth_batch(model.tokenizer, 2, 66, seed=77, pad_tail=3).to(DEV)
     leaf = {n: p.detach().float().requires_grad_(True) for n, p in model.named_parameters()}
-    sd = {}
-    for n, t in leaf.items():
-        if ".lora_" in n:
-            continue
-        if n.endswith(".base_layer.weight"):
-            path = n[:-len(".base_layer.weight")]
-            sd[path + ".weight"] = t + 2.0 * (leaf[path + ".lora_B.default.weight"] @ leaf[path + ".lora_A.default.weight"])
-        else:
-            sd[n] = t
+    sd = O.lora_effective_sd(leaf, 2.0)          # scaling = lora_alpha / r = 128 / 64
     ref = O.train_loss(sd, ocfg, batch)
     ref.backward()
     before = {n: p.detach().clone() for n, p in model.named_parameters()}

@@ -30,17 +30,7 @@ def _oracle_grads(model, batch, lora_scale=None):
     weight W + scale * B A is formed differentiably, so the gradients of A and B are those of peft's unmerged forward."""
     from oracle import midi_oracle as O
     leaf = {n: p.detach().float().requires_grad_(True) for n, p in model.named_parameters()}
-    sd = {}
-    for n, t in leaf.items():
-        if ".lora_" in n:
-            continue
-        if n.endswith(".base_layer.weight"):
-            path = n[:-len(".base_layer.weight")]
-            a = [k for k in leaf if k.startswith(path + ".lora_A.")][0]
-            b = [k for k in leaf if k.startswith(path + ".lora_B.")][0]
-            sd[path + ".weight"] = t + lora_scale * (leaf[b] @ leaf[a])
-        else:
-            sd[n] = t
+    sd = O.lora_effective_sd(leaf, lora_scale) if lora_scale is not None else leaf
     loss = O.train_loss(sd, O.cfg_from_hf(model.config), batch)
     loss.backward()
     return float(loss.detach()), {n: t.grad for n, t in leaf.items()}
