@@ -384,11 +384,10 @@ class MIDIModel(PreTrainedModel):
             return [self.__dict__["_b200_native_lora"]]
         return super().active_adapters()
 
-    def get_adapter_state_dict(self, adapter_name: Optional[str] = None, state_dict=None):
+    def get_adapter_state_dict(self, adapter_name: Optional[str] = None, *args, **kwargs):
         if self.__dict__.get("_b200_native_lora") is not None:
             return _lora.adapter_state_dict(self, adapter_name or self.active_adapters()[0])
-        return super().get_adapter_state_dict(adapter_name) if state_dict is None else \
-            super().get_adapter_state_dict(adapter_name, state_dict)
+        return super().get_adapter_state_dict(adapter_name, *args, **kwargs)
 
     def load_adapter_weights(self, adapter_dir_or_state_dict, adapter_name: Optional[str] = None) -> None:
         """Resume LoRA training: load `adapter_model.safetensors` (train.py:241-244) / a state dict into the injected

@@ -309,6 +309,9 @@ def install(monkeypatch):
     monkeypatch.setattr(lib, "query", _query)
     monkeypatch.setattr(lib, "stream", lambda: None)
     monkeypatch.setattr(lib, "require_cuda", lambda t, what="tensor": None)
-    monkeypatch.setattr(engine, "_require_device", lambda n, p, dev: None if p.dtype == BF else (_ for _ in ()).throw(
-        lib.B200Error(f"parameter {n} is {p.dtype}")))
+    def require_bf16(n, p, dev):                 # the dtype half of the product's check stays; only `is_cuda` is waived
+        if p.dtype != BF:
+            raise lib.B200Error(f"parameter {n} is {p.dtype}")
+
+    monkeypatch.setattr(engine, "_require_device", require_bf16)
     monkeypatch.setattr(engine, "WGRAD_STREAM", False)
