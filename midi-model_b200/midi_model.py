@@ -11,8 +11,13 @@ all arithmetic runs in hand-written sm_100a kernels behind the C ABI in `include
 (`midi_b200/lib.py`).  There is no PyTorch / CPU fallback: parameters must be bfloat16 on a CUDA
 device, otherwise the call raises.
 
-Extra (non-reference) entry points used by the fused trainer and the benchmark:
-`training_loss(batch)`, `training_step_fused(batch, ...)`.
+LoRA (`train.py --task lora`, train.py:439-449): `add_adapter` injects adapters in peft's layout (transformers' mixin when
+peft is installed, midi_b200/lora.py otherwise); the engine then computes y = W x + (lora_alpha / r) B A x, trains A and B
+only, and `generate` reads merged copies.
+
+Extra (non-reference) entry points used by the fused trainer and the benchmark: `training_loss(batch)`,
+`fused_optimizer_step(...)`, `optimizer_state_dict()` / `load_optimizer_state_dict()`, `generate_stream(...)`
+(app.py:27-120), `load_adapter_weights(dir)`.
 """
 from __future__ import annotations
 
