@@ -196,3 +196,31 @@ def test_lora_rejects_what_the_engine_does_not_implement():
         model.add_adapter(dict(r=8, lora_alpha=16, target_modules=["q_proj"]))          # same adapter name again
     with pytest.raises(B200Error):
         model.net.layers[0].self_attn.q_proj(torch.zeros(1, 256))                      # containers do not compute
+
+
+def test_merged_decode_weights_follow_the_adapters(monkeypatch):
+    """generate() on a model with injected adapters reads merged copies (engine.MergedStack); they must be re-folded after
+    every kind of adapter update -- the fused AdamW (raw pointers), a torch optimizer (in-place ops), load_adapter_weights --
+    and idle generate loops built on the old copies must be retired."""
+    mm, model = _lora_model(monkeypatch)
+    rt = model._rt()
+    s0 = model._cached_stack("outer")
+    assert s0.eng is not rt.outer and model._cached_stack("outer") is s0          # merged view, cached while nothing changes
+    assert model._cached_stack("inner").eng is not rt.inner
+    w0 = s0.eng.layers[0].qkv.clone()
+    rt.gen_pool[("stale",)] = [object()]
+    model.training_loss(_batch(model))
+    model.fused_optimizer_step(lr=1e-2, step=1)                                      # (a) fused AdamW
+    s1 = model._cached_stack("outer")
+    assert s1 is not s0 and not torch.equal(s1.eng.layers[0].qkv, w0) and not rt.gen_pool
+    opt = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=1e-1)
+    opt.step()                                                                       # (b) torch optimizer (grads are published)
+    s2 = model._cached_stack("outer")
+    assert s2 is not s1 and not torch.equal(s2.eng.layers[0].qkv, s1.eng.layers[0].qkv)
+    sd = {k: torch.zeros_like(v) for k, v in model.get_adapter_state_dict().items()}
+    model.load_adapter_weights(sd)                                                   # (c) B = 0: merged == base
+    s3 = model._cached_stack("outer")
+    assert s3 is not s2 and torch.equal(s3.eng.layers[0].qkv, rt.outer.layers[0].qkv)
+    # a model without adapters keeps reading the engine's own weights
+    mm2, cfg2, plain = _tiny_model()
+    assert plain._cached_stack("outer").eng is plain._rt().outer
