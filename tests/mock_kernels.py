@@ -258,8 +258,124 @@ def ce_bwd_(logits, targets, lse, lac, V, ignore_index, grad_scale=1.0, grad_sca
         logits[:, V:] = 0
 
 
+
+# ------------------------------------------------------------------ decode-step entry points (pointer level)
+def _bfmat(ptr, rows, cols, ld):
+    t = _from_ptr(ptr, (rows - 1) * ld + cols, BF)
+    return torch.as_strided(t, (rows, cols), (ld, 1))
+
+
+def _pool(ptr, batch, max_pages, nh, page, D):
+    return _from_ptr(ptr, batch * max_pages * nh * page * D, BF).view(batch * max_pages, nh, page, D)
+
+
+def _gemv_bf16(x, W, res, y, B, N, K, ldx, ldw, ldr, ldy, _s):
+    acc = _f(_bfmat(x, B, K, ldx)) @ _f(_bfmat(W, N, K, ldw)).t()
+    if res:
+        acc = acc.to(BF).float() + _f(_bfmat(res, B, N, ldr))
+    out = _bfmat(y, B, ldy if ldy >= N else N, ldy)
+    out[:, :N] = acc.to(BF)
+    out[:, N:] = 0
+
+
+def _gemv_fused(x, ids, ids_stride, table, V, norm_w, eps, W, res, y, B, N_out, K, ldx, ldw, ldr, ldy, swiglu_, _s):
+    assert not ids, "mock kernel layer: the ids/table input of b200_gemv_fused is used by the graph loop only"
+    h = _bfmat(x, B, K, ldx).clone()
+    if norm_w:
+        h = rmsnorm(h, _from_ptr(norm_w, K, BF), eps)
+    rows_w = 2 * N_out if swiglu_ else N_out
+    z = (_f(h) @ _f(_bfmat(W, rows_w, K, ldw)).t())
+    if swiglu_:
+        z = _f(swiglu(z.to(BF)))
+    if res:
+        z = z.to(BF).float() + _f(_bfmat(res, B, N_out, ldr))
+    _bfmat(y, B, N_out, ldy).copy_(z.to(BF))
+
+
+def _kv_append(qkv, k_pool, v_pool, bt, max_pages, page, nh, D, batch, s_new, pos0, pos0_dev, ld, _s):
+    assert not pos0_dev
+    H = nh * D
+    q = _bfmat(qkv, batch * s_new, 3 * H, ld)
+    kp, vp = _pool(k_pool, batch, max_pages, nh, page, D), _pool(v_pool, batch, max_pages, nh, page, D)
+    table = _from_ptr(bt, batch * max_pages, torch.int32).view(batch, max_pages)
+    for b in range(batch):
+        for i in range(s_new):
+            pos = pos0 + i
+            pg = int(table[b, pos // page])
+            row = q[b * s_new + i]
+            kp[pg, :, pos % page] = row[H:2 * H].view(nh, D)
+            vp[pg, :, pos % page] = row[2 * H:].view(nh, D)
+
+
+def _gather_kv(pool, table, b, n_pos, page):
+    pages = [pool[int(table[b, j])] for j in range((n_pos + page - 1) // page)]          # each [nh, page, D]
+    return torch.cat(pages, 1)[:, :n_pos]                                               # [nh, n_pos, D]
+
+
+def _attend(q, k, v, scale):
+    # q [nh, D], k/v [nh, T, D] (fp32) -> [nh, D], probabilities rounded to bf16 before P.V like the kernels
+    p = torch.softmax((k @ q[:, :, None])[:, :, 0] * scale, -1)
+    return (p.to(BF).float()[:, None, :] @ v)[:, 0]
+
+
+def _attn_decode(q, k_pool, v_pool, bt, max_pages, page, out, batch, s_q, nh, D, past, past_dev, max_T, ldq, ldo, scale,
+                 n_split, _ws, _wsb, _s):
+    assert not past_dev
+    H = nh * D
+    qm, om = _bfmat(q, batch * s_q, H, ldq), _bfmat(out, batch * s_q, H, ldo)
+    kp, vp = _pool(k_pool, batch, max_pages, nh, page, D), _pool(v_pool, batch, max_pages, nh, page, D)
+    table = _from_ptr(bt, batch * max_pages, torch.int32).view(batch, max_pages)
+    for b in range(batch):
+        for i in range(s_q):
+            n_pos = past + i + 1
+            k, v = _f(_gather_kv(kp, table, b, n_pos, page)), _f(_gather_kv(vp, table, b, n_pos, page))
+            om[b * s_q + i] = _attend(_f(qm[b * s_q + i]).view(nh, D), k, v, scale).reshape(H).to(BF)
+
+
+def _attn_decode_fused(qkv, k_pool, v_pool, bt, max_pages, page, cos_t, sin_t, out, batch, nh, D, pos0, pos_dev, max_T, ldq,
+                       ldo, scale, n_split, _ws, _wsb, _s):
+    assert not pos_dev
+    H, half = nh * D, D // 2
+    q = _bfmat(qkv, batch, 3 * H, ldq)
+    c = _from_ptr(cos_t + pos0 * half * 2, half, BF).float()[None, None]
+    s_ = _from_ptr(sin_t + pos0 * half * 2, half, BF).float()[None, None]
+    for col0 in (0, H):
+        q[:, col0:col0 + H] = _rot(_f(q[:, col0:col0 + H]).view(batch, nh, D), c, s_, False).reshape(batch, H).to(BF)
+    _kv_append(qkv, k_pool, v_pool, bt, max_pages, page, nh, D, batch, 1, pos0, None, ldq, None)
+    _attn_decode(qkv, k_pool, v_pool, bt, max_pages, page, out, batch, 1, nh, D, pos0, None, max_T, ldq, ldo, scale, n_split,
+                 None, 0, None)
+
+
+def _sample_from_logits(logits, rows, V, ld, temp, top_p, top_k, step, event_tok, lut, n_event_types, eos_id, pad_id,
+                        dense_mask, uniforms, out, out_stride, _s):
+    assert top_k == 1 and not dense_mask, "mock kernel layer: greedy sampling only"
+    lg = _f(_bfmat(logits, rows, V, ld))
+    table = _from_ptr(lut, n_event_types * 8 * 2, torch.int32).view(n_event_types, 8, 2)
+    ev = _from_ptr(event_tok, rows, torch.int64)
+    o = _from_ptr(out, (rows - 1) * out_stride + 1, torch.int64)
+    for r in range(rows):
+        if step == 0:
+            lo, hi = eos_id, eos_id + 1 + n_event_types
+        else:
+            e = int(ev[r]) - (eos_id + 1)
+            if int(ev[r]) == eos_id or e < 0 or e >= n_event_types:
+                lo, hi = pad_id, pad_id + 1
+            else:
+                lo, hi = int(table[e, step - 1, 0]), int(table[e, step - 1, 1])
+                if hi <= lo:
+                    lo, hi = pad_id, pad_id + 1
+        o[r * out_stride] = lo + int(torch.argmax(lg[r, lo:hi]))
+
+
+_DECODE_CALLS = {"b200_gemv_bf16": _gemv_bf16, "b200_gemv_fused": _gemv_fused, "b200_kv_append": _kv_append,
+                 "b200_attn_decode": _attn_decode, "b200_attn_decode_fused": _attn_decode_fused,
+                 "b200_sample_from_logits": _sample_from_logits}
+
+
 # ------------------------------------------------------------------ raw C-ABI calls the host code issues itself
 def _call(name, *args):
+    if name in _DECODE_CALLS:
+        return _DECODE_CALLS[name](*args)
     if name == "b200_inner_input_bwd_hidden":
         dx_ptr, dh_ptr, n_events, Tin, H, _ = args
         dx = _from_ptr(dx_ptr, n_events * Tin * H, BF).view(n_events, Tin, H)
@@ -291,6 +407,8 @@ def _call(name, *args):
 def _query(name, *args):
     if name == "b200_gradnorm_parts":
         return 1
+    if name == "b200_attn_decode_workspace_bytes":
+        return 256
     raise AssertionError(f"mock kernel layer: unexpected C-ABI query {name}")
 
 

@@ -224,3 +224,82 @@ def test_merged_decode_weights_follow_the_adapters(monkeypatch):
     # a model without adapters keeps reading the engine's own weights
     mm2, cfg2, plain = _tiny_model()
     assert plain._cached_stack("outer").eng is plain._rt().outer
+
+
+def test_kv_cached_call_modes_match_the_full_forward(monkeypatch):
+    """midi_model.py:116-150 with a caller-owned DynamicCache (app.py:56-64 / midi_model.py:192-221): prefill + single-event
+    steps across a KV page boundary (64 positions) == one full forward; forward_token's three call modes chained over the
+    token-level cache == the uncached call.  Host logic (PagedKV, block tables, positions, call modes) over the mock kernels."""
+    from transformers import DynamicCache
+    mock_kernels.install(monkeypatch)
+    mm, cfg, model = _tiny_model()
+    model.eval()
+    batch = _batch(model, B=2, S1=71, seed=3)
+    with torch.no_grad():
+        x = batch[:, :70]
+        full = model.forward(x)
+        c = DynamicCache()
+        parts = [model.forward(x[:, :60], cache=c)] + [model.forward(x[:, t:t + 1], cache=c) for t in range(60, 70)]
+        cached = torch.cat(parts, 1)
+        assert _rel(cached.float(), full.float()) < 2e-2
+        assert _rel(cached[:, 60:].float(), full[:, 60:].float()) < 2e-2             # the steps past the page boundary
+        hidden = full[:, -1]
+        toks = batch[:, 70, :7]
+        ref = model.forward_token(hidden, toks)                                      # (hidden, x): [B, 8, V]
+        c2 = DynamicCache()
+        steps = [model.forward_token(hidden, None, cache=c2)]                        # (hidden, None, cache)
+        steps += [model.forward_token(None, toks[:, i:i + 1], cache=c2) for i in range(7)]      # (None, x, cache)
+        got = torch.cat(steps, 1)
+        assert got.shape == ref.shape == (2, 8, model.tokenizer.vocab_size)
+        assert _rel(got.float(), ref.float()) < 2e-2
+
+
+def test_reference_shaped_generate_loop_is_greedy_and_grammar_valid(monkeypatch):
+    """MIDIModel.generate's host-driven loop (B200_GENERATE=eager; midi_model.py:167-250: prompt handling, per-event cached
+    forward, per-token cached forward_token + grammar mask + sampling, early exit after the event's last parameter, padding)
+    over the mock kernels: every generated event parses, pads follow the parameters, and every greedy choice is the argmax of
+    the ORACLE's fp32 logits for the same prefix up to a bf16-sized margin."""
+    from oracle import midi_oracle as O
+    mock_kernels.install(monkeypatch)
+    monkeypatch.setenv("B200_GENERATE", "eager")
+    mm, cfg, model = _tiny_model()
+    model.eval()
+    tok = model.tokenizer
+    P, n_new, B = 5, 6, 2
+    prompt = _batch(model, B=B, S1=P, seed=9).numpy()
+    ids = model.generate(prompt=prompt, batch_size=B, max_len=P + n_new, top_k=1)
+    assert ids.shape == (B, P + n_new, 8) and (ids[:, :P] == prompt).all()
+    sd32 = {k: v.detach().float() for k, v in model.state_dict().items()}
+    ocfg = O.cfg_from_hf(model.config)
+    seq = torch.from_numpy(ids)
+    exact = total = 0
+    worst = 0.0
+    n_types = len(tok.event_ids)
+    for e in range(P, P + n_new):
+        with torch.no_grad():
+            hid = O.forward(sd32, ocfg, seq[:, :e], inv_freq=model.net.rotary_emb.inv_freq)[:, -1]
+            lg = O.forward_token(sd32, ocfg, hid, seq[:, e, :7], inv_freq=model.net_token.rotary_emb.inv_freq)    # [B, 8, V]
+        for b in range(B):
+            row = ids[b, e]
+            ev = int(row[0])
+            assert tok.eos_id <= ev <= tok.eos_id + n_types
+            if ev != tok.eos_id:
+                assert tok.tokens2event(row.tolist()) != [], row                       # a complete, valid event
+            name = {v: k for k, v in tok.event_ids.items()}.get(ev)
+            params = tok.events[name] if name else []
+            for t in range(8):
+                if t == 0:
+                    lo, hi = tok.eos_id, tok.eos_id + 1 + n_types
+                elif t - 1 < len(params):
+                    pid = tok.parameter_ids[params[t - 1]]
+                    lo, hi = pid[0], pid[-1] + 1
+                else:
+                    assert row[t] == tok.pad_id                                        # midi_model.py:239-241
+                    continue
+                assert lo <= row[t] < hi
+                margin = float(lg[b, t, lo:hi].max() - lg[b, t, row[t]])
+                worst = max(worst, margin)
+                exact += int(margin == 0.0)
+                total += 1
+    print("generate vs oracle fp32: worst margin", worst, "exact argmax", exact, "of", total)
+    assert worst < 0.1 and exact >= 0.8 * total, (worst, exact, total)
