@@ -292,8 +292,12 @@ def _gemv_fused(x, ids, ids_stride, table, V, norm_w, eps, W, res, y, B, N_out, 
     _bfmat(y, B, N_out, ldy).copy_(z.to(BF))
 
 
+def _dev_int(ptr):
+    return int(_from_ptr(ptr, 1, torch.int32)[0]) if ptr else 0
+
+
 def _kv_append(qkv, k_pool, v_pool, bt, max_pages, page, nh, D, batch, s_new, pos0, pos0_dev, ld, _s):
-    assert not pos0_dev
+    pos0 = pos0 + _dev_int(pos0_dev)
     H = nh * D
     q = _bfmat(qkv, batch * s_new, 3 * H, ld)
     kp, vp = _pool(k_pool, batch, max_pages, nh, page, D), _pool(v_pool, batch, max_pages, nh, page, D)
@@ -320,7 +324,7 @@ def _attend(q, k, v, scale):
 
 def _attn_decode(q, k_pool, v_pool, bt, max_pages, page, out, batch, s_q, nh, D, past, past_dev, max_T, ldq, ldo, scale,
                  n_split, _ws, _wsb, _s):
-    assert not past_dev
+    past = past + _dev_int(past_dev)
     H = nh * D
     qm, om = _bfmat(q, batch * s_q, H, ldq), _bfmat(out, batch * s_q, H, ldo)
     kp, vp = _pool(k_pool, batch, max_pages, nh, page, D), _pool(v_pool, batch, max_pages, nh, page, D)
@@ -334,7 +338,7 @@ def _attn_decode(q, k_pool, v_pool, bt, max_pages, page, out, batch, s_q, nh, D,
 
 def _attn_decode_fused(qkv, k_pool, v_pool, bt, max_pages, page, cos_t, sin_t, out, batch, nh, D, pos0, pos_dev, max_T, ldq,
                        ldo, scale, n_split, _ws, _wsb, _s):
-    assert not pos_dev
+    pos0 = pos0 + _dev_int(pos_dev)
     H, half = nh * D, D // 2
     q = _bfmat(qkv, batch, 3 * H, ldq)
     c = _from_ptr(cos_t + pos0 * half * 2, half, BF).float()[None, None]
@@ -348,8 +352,10 @@ def _attn_decode_fused(qkv, k_pool, v_pool, bt, max_pages, page, cos_t, sin_t, o
 
 def _sample_from_logits(logits, rows, V, ld, temp, top_p, top_k, step, event_tok, lut, n_event_types, eos_id, pad_id,
                         dense_mask, uniforms, out, out_stride, _s):
-    assert top_k == 1 and not dense_mask, "mock kernel layer: greedy sampling only"
-    lg = _f(_bfmat(logits, rows, V, ld))
+    assert top_k == 1, "mock kernel layer: greedy sampling only"
+    lg = _f(_bfmat(logits, rows, V, ld)).clone()
+    if dense_mask:                                    # app.py:73-87 options: [rows, V] uint8, ANDed with the grammar range
+        lg[_from_ptr(dense_mask, rows * V, torch.uint8).view(rows, V) == 0] = float("-inf")
     table = _from_ptr(lut, n_event_types * 8 * 2, torch.int32).view(n_event_types, 8, 2)
     ev = _from_ptr(event_tok, rows, torch.int64)
     o = _from_ptr(out, (rows - 1) * out_stride + 1, torch.int64)
@@ -367,7 +373,31 @@ def _sample_from_logits(logits, rows, V, ld, temp, top_p, top_k, step, event_tok
         o[r * out_stride] = lo + int(torch.argmax(lg[r, lo:hi]))
 
 
-_DECODE_CALLS = {"b200_gemv_bf16": _gemv_bf16, "b200_gemv_fused": _gemv_fused, "b200_kv_append": _kv_append,
+def _uniform_fill(u, n, seed, state, _s):
+    _from_ptr(state, 2, torch.int64)[0] += 1          # greedy mock: the draws themselves are never used
+
+
+def _event_commit(ev_t, seq, ev_next, pos_dev, B, T, max_len, _s):
+    pos = _from_ptr(pos_dev, 1, torch.int32)
+    p = int(pos[0])
+    ev = _from_ptr(ev_t, T * B, torch.int64).view(T, B).t()                # [B, T]
+    if p + 1 < max_len:
+        _from_ptr(seq, B * max_len * T, torch.int64).view(B, max_len, T)[:, p + 1] = ev
+    _from_ptr(ev_next, B * T, torch.int64).view(B, T).copy_(ev)
+    pos[0] = p + 1
+
+
+class _NoStream:
+    """torch.cuda.Stream stand-in for the CPU run of the device-resident loops (stream plumbing only)."""
+
+    def __init__(self, *a, **k):
+        self.cuda_stream = 0
+
+    def wait_stream(self, other):
+        pass
+
+
+_DECODE_CALLS = {"b200_uniform_fill": _uniform_fill, "b200_event_commit": _event_commit, "b200_gemv_bf16": _gemv_bf16, "b200_gemv_fused": _gemv_fused, "b200_kv_append": _kv_append,
                  "b200_attn_decode": _attn_decode, "b200_attn_decode_fused": _attn_decode_fused,
                  "b200_sample_from_logits": _sample_from_logits}
 
@@ -433,3 +463,7 @@ def install(monkeypatch):
 
     monkeypatch.setattr(engine, "_require_device", require_bf16)
     monkeypatch.setattr(engine, "WGRAD_STREAM", False)
+    import contextlib
+    monkeypatch.setattr(torch.cuda, "Stream", _NoStream)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _NoStream())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())

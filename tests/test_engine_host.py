@@ -303,3 +303,55 @@ def test_reference_shaped_generate_loop_is_greedy_and_grammar_valid(monkeypatch)
                 total += 1
     print("generate vs oracle fp32: worst margin", worst, "exact argmax", exact, "of", total)
     assert worst < 0.1 and exact >= 0.8 * total, (worst, exact, total)
+
+
+def test_device_resident_loop_and_app_stream_host_logic(monkeypatch):
+    """The device-resident loop issued from the host (B200_GENERATE=nograph: GraphGenerator state, device-side positions,
+    per-event commit, stop rule) produces the events of the reference-shaped loop; `generate_stream` (app.py:27-120) yields
+    the same events one by one, its `disable_*` options are a mask on top of the grammar, and a finished generation hands
+    its loop state back for reuse."""
+    mock_kernels.install(monkeypatch)
+    mm, cfg, model = _tiny_model()
+    model.eval()
+    tok = model.tokenizer
+    P, n_new, B = 4, 5, 2
+    prompt = _batch(model, B=B, S1=P, seed=11).numpy()
+    monkeypatch.setenv("B200_GENERATE", "eager")
+    ref = model.generate(prompt=prompt, batch_size=B, max_len=P + n_new, top_k=1)
+    monkeypatch.setenv("B200_GENERATE", "nograph")
+    ids = model.generate(prompt=prompt, batch_size=B, max_len=P + n_new, top_k=1)
+    assert ids.shape == ref.shape and (ids == ref).all()
+    evs = list(model.generate_stream(prompt=prompt, batch_size=B, max_len=P + n_new, top_k=1))
+    assert len(evs) == n_new and all(e.shape == (B, 8) and e.dtype.kind == "i" for e in evs)
+    assert (torch.from_numpy(ids[:, P:]) == torch.stack([torch.from_numpy(e) for e in evs], 1)).all()
+    rt = model._rt()
+    key = (B, P + n_new, 1.0, 0.98, 1)
+    assert len(rt.gen_pool.get(key, [])) == 1                               # the loop state went back to the pool ...
+    gg = rt.gen_pool[key][0]
+    # ... and is reused.  app.py:73-87 options are a mask on top of the grammar.  Make the plain run emit what the options can
+    # forbid: boost patch_change (an event with a channel parameter) over the event type the model currently prefers.
+    first = int(evs[0][0, 0])
+    assert first not in (tok.eos_id, tok.event_ids["patch_change"])
+    with torch.no_grad():
+        model.lm_head.weight[tok.event_ids["patch_change"]] = 8 * model.lm_head.weight[first]
+    plain = list(model.generate_stream(prompt=prompt, batch_size=B, max_len=P + n_new, top_k=1))
+    assert rt.gen_pool[key][0] is gg
+    pc = [e[0] for e in plain if int(e[0, 0]) == tok.event_ids["patch_change"]]
+    assert pc, "the boosted event type must show up in the plain run"
+    c0 = int(pc[0][4])                                                       # patch_change: time1 time2 track channel patch
+    assert c0 in tok.parameter_ids["channel"]
+    no_chan = list(model.generate_stream(prompt=prompt, batch_size=B, max_len=P + n_new, top_k=1,
+                                         disable_channels=[tok.parameter_ids["channel"].index(c0)]))
+    assert c0 not in {int(v) for e in no_chan for v in e.reshape(-1)}
+    assert any(int(e[0, 0]) == tok.event_ids["patch_change"] for e in no_chan)          # still allowed, on another channel
+    no_pc = list(model.generate_stream(prompt=prompt, batch_size=B, max_len=P + n_new, top_k=1, disable_patch_change=True,
+                                       disable_control_change=True))
+    types = {int(e[b, 0]) for e in no_pc for b in range(B)}
+    assert not (types & {tok.event_ids["patch_change"], tok.event_ids["control_change"]})
+    assert int(gg.mask.sum()) == gg.mask.numel()                                      # mask reset when the loop is handed back
+    for e in no_chan + no_pc:
+        for b in range(B):
+            assert int(e[b, 0]) == tok.eos_id or tok.tokens2event(e[b].tolist()) != []
+    # prompt already at max_len: nothing to generate (app.py / midi_model.py:183-190)
+    assert list(model.generate_stream(prompt=prompt, batch_size=B, max_len=P, top_k=1)) == []
+    assert (model.generate(prompt=prompt, batch_size=B, max_len=P, top_k=1) == prompt).all()
