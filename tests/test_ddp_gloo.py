@@ -154,3 +154,91 @@ def test_fused_trainer_world2_lora():
     ok_cover, ok_avg, ok_same, n_calls, moved = _run_trainer(True, 13)
     assert (ok_cover, ok_avg, ok_same, moved) == (True, True, True, True)
     assert n_calls == 1          # LoRA: one hand-over, the adapter tail
+
+
+def _dropin_worker(rank, world, port, q, lora_mode):
+    """What unchanged train.py gets under Lightning's DDP strategy (train.py:168-188, 461-474): the module wrapped in torch
+    DistributedDataParallel, forward -> forward_token -> F.cross_entropy -> backward.  The engine's autograd Functions take
+    the parameters as inputs, so DDP's gradient hooks fire and average the gradients; here over gloo on the mock kernel layer."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    for p in (os.path.join(ROOT, "midi-model_b200"), ROOT, os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    import pytest
+    import torch.nn.functional as F
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    import mock_kernels
+    mock_kernels.install(pytest.MonkeyPatch())
+    import midi_model as mm
+    from midi_b200 import lora
+    from midi_b200.synth import synth_batch
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = mm.MIDIModel(mm.MIDIModelConfig.get_config("v2", True, n_layer=4, n_head=4, n_embd=256, n_inner=512))
+    model = model.to(torch.bfloat16).train()
+    if lora_mode:
+        model.requires_grad_(False)
+        model.add_adapter(lora.LoraAdapterConfig(r=8, lora_alpha=16, target_modules=["q_proj", "k_proj", "up_proj"]))
+        g = torch.Generator().manual_seed(3)
+        with torch.no_grad():
+            for n, p in model.named_parameters():
+                if ".lora_B." in n:
+                    p.copy_((torch.randn(p.shape, generator=g) * 0.02).to(torch.bfloat16))
+    tok = model.tokenizer
+
+    class Step(torch.nn.Module):                                  # TrainMIDIModel.training_step's arithmetic
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, batch):
+            x, y = batch[:, :-1].contiguous(), batch[:, 1:].contiguous()
+            hidden = self.m.forward(x)
+            hidden = hidden.reshape(-1, hidden.shape[-1])
+            y = y.reshape(-1, y.shape[-1])
+            logits = self.m.forward_token(hidden, y[:, :-1])
+            return F.cross_entropy(logits.view(-1, tok.vocab_size), y.view(-1), reduction="mean", ignore_index=tok.pad_id)
+
+    batch = synth_batch(tok, 2, 6, seed=1234 + rank)
+    Step(model)(batch).backward()                                 # local gradients
+    names = [n for n, p in model.named_parameters() if p.requires_grad]
+    local = torch.cat([dict(model.named_parameters())[n].grad.float().reshape(-1) for n in names])
+    for p in model.parameters():
+        p.grad = None
+    ddp = DDP(Step(model))
+    ddp(batch).backward()
+    synced = torch.cat([dict(model.named_parameters())[n].grad.float().reshape(-1) for n in names])
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    mean = sum(gathered) / world
+    ok_avg = torch.allclose(synced, mean, rtol=2e-2, atol=1e-6)
+    both = [torch.zeros_like(synced) for _ in range(world)]
+    dist.all_gather(both, synced)
+    ok_same = torch.equal(both[0], both[1])
+    ok_frozen = all(p.grad is None for n, p in model.named_parameters() if not p.requires_grad)
+    if rank == 0:
+        q.put((ok_avg, ok_same, ok_frozen, len(names)))
+    dist.destroy_process_group()
+
+
+def _run_dropin(lora_mode, port_off):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + port_off) % 500
+    procs = [ctx.Process(target=_dropin_worker, args=(r, 2, port, q, lora_mode)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=300)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    return res
+
+
+def test_dropin_under_torch_ddp_world2():
+    ok_avg, ok_same, ok_frozen, n = _run_dropin(False, 23)
+    assert (ok_avg, ok_same, ok_frozen) == (True, True, True) and n == 50          # 5 layers x 9 + 2 final norms + 2 embeddings + lm_head
+
+
+def test_dropin_under_torch_ddp_world2_lora():
+    ok_avg, ok_same, ok_frozen, n = _run_dropin(True, 31)
+    assert (ok_avg, ok_same, ok_frozen) == (True, True, True) and n == 2 * 3 * 5    # A and B of three projections, five layers
