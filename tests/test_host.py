@@ -369,3 +369,24 @@ def test_paged_kv_grow_keeps_cached_positions():
         assert torch.equal(gather(kv.v[li], kv.block_table, 8, b, h, t), v0)
     kv.grow(10)                                          # no-op
     assert kv.capacity >= 48
+
+
+def test_header_is_plain_c_and_a_c_program_can_bind_it(tmp_path):
+    """include/midi_b200.h compiles stand-alone as C99 and as C++ (no CUDA headers), and a plain-C host program
+    (tests/abi/abi_host.c) links libmidi_b200.so and exercises the entry points that need no GPU: version / size queries and
+    the argument validation (error code + message) that precedes every launch."""
+    import shutil
+    import subprocess
+    lib = _built()
+    hdr = os.path.join(ROOT, "include", "midi_b200.h")
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr])
+    exe = str(tmp_path / "abi_host")
+    libdir = os.path.dirname(lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "abi", "abi_host.c"), "-L", libdir, "-lmidi_b200",
+                           f"-Wl,-rpath,{libdir}", "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "abi host ok" in r.stdout, r.stdout + r.stderr
