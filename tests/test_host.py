@@ -390,3 +390,29 @@ def test_header_is_plain_c_and_a_c_program_can_bind_it(tmp_path):
                            f"-Wl,-rpath,{libdir}", "-o", exe])
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "abi host ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_gemm_planner_reproduces_the_committed_sweep():
+    """The tile / split-K planner (b200_gemm_plan: a host-side cost model, needs no GPU) still makes the choices that
+    profiles/r2_gemm_plan_sweep.txt measured on a B200 for the 24 GEMM shapes of the benchmark step -- a change to the cost
+    model has to come with a new sweep."""
+    lib = _built()
+    L = lib.load()
+    n = 0
+    for line in open(os.path.join(ROOT, "profiles", "r2_gemm_plan_sweep.txt")):
+        m = re.match(r"(fwd|dgrad|wgrad)\s+rows=\s*(\d+) out=\s*(\d+) in=\s*(\d+) x\s*\d+ planner \((\d+), (\d+)\)", line)
+        if not m:
+            continue
+        kind = m.group(1)
+        R, O, I, bn, sp = map(int, m.groups()[1:])
+        M, N, K, allow = {"fwd": (R, O, I, 0), "dgrad": (R, I, O, 0), "wgrad": (O, I, R, 1)}[kind]
+        b, s = ctypes.c_int(0), ctypes.c_int(0)
+        assert L.b200_gemm_plan(M, N, K, allow, ctypes.byref(b), ctypes.byref(s)) == 0
+        assert (b.value, s.value) == (bn, sp), (kind, R, O, I, (bn, sp), (b.value, s.value))
+        n += 1
+    assert n == 24
+    # shapes the LoRA adapters add (rank 64): skinny outputs take the 128-wide tile; the long-K gradient GEMMs split
+    for M, N, K, allow, want_bn in ((131072, 64, 1024, 0, 128), (1024, 64, 131072, 1, 128), (64, 1024, 16384, 1, 128)):
+        b, s = ctypes.c_int(0), ctypes.c_int(0)
+        assert L.b200_gemm_plan(M, N, K, allow, ctypes.byref(b), ctypes.byref(s)) == 0
+        assert b.value == want_bn and (s.value > 1) == bool(allow)
