@@ -53,7 +53,7 @@ class LoraAdapterConfig:
 
     @classmethod
     def from_any(cls, cfg) -> "LoraAdapterConfig":
-        if isinstance(cls, type) and isinstance(cfg, cls):
+        if isinstance(cfg, LoraAdapterConfig):
             return cfg
         if isinstance(cfg, dict):
             return cls(**cfg)
@@ -177,8 +177,10 @@ def inject(model: nn.Module, cfg: LoraAdapterConfig, adapter_name: str = "defaul
         wrapped.append(key)
     if not wrapped:
         raise ValueError(f"Target modules {cfg.target_modules} not found in the base model")
+    # peft: _mark_only_adapters_as_trainable freezes everything that is not an adapter, set_adapter leaves only the ACTIVE
+    # adapter's matrices trainable (an earlier, now inactive adapter must not be decayed by an optimizer that sees no gradient)
     for n, p in model.named_parameters():
-        p.requires_grad_(".lora_" in n)
+        p.requires_grad_(f".lora_A.{adapter_name}." in n or f".lora_B.{adapter_name}." in n)
     return wrapped
 
 
