@@ -355,3 +355,37 @@ def test_device_resident_loop_and_app_stream_host_logic(monkeypatch):
     # prompt already at max_len: nothing to generate (app.py / midi_model.py:183-190)
     assert list(model.generate_stream(prompt=prompt, batch_size=B, max_len=P, top_k=1)) == []
     assert (model.generate(prompt=prompt, batch_size=B, max_len=P, top_k=1) == prompt).all()
+
+
+def test_concurrent_streams_own_their_loop_state(monkeypatch):
+    """gradio serves app.generate from several worker threads sharing one model and may resume a suspended generator on
+    another thread (app.py:496): two interleaved `generate_stream` generators with the same settings must each own a loop state
+    (no lock held across `yield`), produce what a lone run produces, and hand both states back to the pool."""
+    import threading
+    mock_kernels.install(monkeypatch)
+    monkeypatch.setenv("B200_GENERATE", "nograph")
+    mm, cfg, model = _tiny_model()
+    model.eval()
+    P, n_new, B = 3, 4, 1
+    p1, p2 = _batch(model, B=B, S1=P, seed=21).numpy(), _batch(model, B=B, S1=P, seed=22).numpy()
+    lone1 = list(model.generate_stream(prompt=p1, batch_size=B, max_len=P + n_new, top_k=1))
+    lone2 = list(model.generate_stream(prompt=p2, batch_size=B, max_len=P + n_new, top_k=1))
+    g1 = model.generate_stream(prompt=p1, batch_size=B, max_len=P + n_new, top_k=1)
+    g2 = model.generate_stream(prompt=p2, batch_size=B, max_len=P + n_new, top_k=1)
+    got1, got2, errors = [next(g1)], [next(g2)], []          # both suspended mid-generation on this thread ...
+
+    def drain(g, out):
+        try:
+            out.extend(g)                                      # ... and resumed on other threads
+        except Exception as e:                                 # noqa: BLE001
+            errors.append(e)
+
+    t1, t2 = threading.Thread(target=drain, args=(g1, got1)), threading.Thread(target=drain, args=(g2, got2))
+    t1.start(); t2.start(); t1.join(); t2.join()
+    assert not errors, errors
+    # (a stream ends early when its row emits EOS, app.py:119 -- the two prompts give streams of different lengths)
+    assert all((a == b).all() for a, b in zip(got1, lone1)) and 1 <= len(got1) == len(lone1) <= n_new
+    assert all((a == b).all() for a, b in zip(got2, lone2)) and 1 <= len(got2) == len(lone2) <= n_new
+    rt = model._rt()
+    idle = rt.gen_pool[(B, P + n_new, 1.0, 0.98, 1)]
+    assert len(idle) == 2 and idle[0] is not idle[1]
