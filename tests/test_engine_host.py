@@ -36,6 +36,12 @@ def _oracle_grads(model, batch, lora_scale=None):
     return float(loss.detach()), {n: t.grad for n, t in leaf.items()}
 
 
+def _stream(model, **kw):
+    """Events of generate_stream as private copies (on the CPU stand-in `.cpu()` is a view of the loop's own buffer, which the
+    next generation overwrites; on the GPU it is a copy)."""
+    return [e.copy() for e in model.generate_stream(**kw)]
+
+
 def _rel(a, b):
     return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
 
@@ -321,7 +327,7 @@ def test_device_resident_loop_and_app_stream_host_logic(monkeypatch):
     monkeypatch.setenv("B200_GENERATE", "nograph")
     ids = model.generate(prompt=prompt, batch_size=B, max_len=P + n_new, top_k=1)
     assert ids.shape == ref.shape and (ids == ref).all()
-    evs = list(model.generate_stream(prompt=prompt, batch_size=B, max_len=P + n_new, top_k=1))
+    evs = _stream(model, prompt=prompt, batch_size=B, max_len=P + n_new, top_k=1)
     assert len(evs) == n_new and all(e.shape == (B, 8) and e.dtype.kind == "i" for e in evs)
     assert (torch.from_numpy(ids[:, P:]) == torch.stack([torch.from_numpy(e) for e in evs], 1)).all()
     rt = model._rt()
@@ -334,18 +340,18 @@ def test_device_resident_loop_and_app_stream_host_logic(monkeypatch):
     assert first not in (tok.eos_id, tok.event_ids["patch_change"])
     with torch.no_grad():
         model.lm_head.weight[tok.event_ids["patch_change"]] = 8 * model.lm_head.weight[first]
-    plain = list(model.generate_stream(prompt=prompt, batch_size=B, max_len=P + n_new, top_k=1))
+    plain = _stream(model, prompt=prompt, batch_size=B, max_len=P + n_new, top_k=1)
     assert rt.gen_pool[key][0] is gg
     pc = [e[0] for e in plain if int(e[0, 0]) == tok.event_ids["patch_change"]]
     assert pc, "the boosted event type must show up in the plain run"
     c0 = int(pc[0][4])                                                       # patch_change: time1 time2 track channel patch
     assert c0 in tok.parameter_ids["channel"]
-    no_chan = list(model.generate_stream(prompt=prompt, batch_size=B, max_len=P + n_new, top_k=1,
-                                         disable_channels=[tok.parameter_ids["channel"].index(c0)]))
+    no_chan = _stream(model, prompt=prompt, batch_size=B, max_len=P + n_new, top_k=1,
+                      disable_channels=[tok.parameter_ids["channel"].index(c0)])
     assert c0 not in {int(v) for e in no_chan for v in e.reshape(-1)}
     assert any(int(e[0, 0]) == tok.event_ids["patch_change"] for e in no_chan)          # still allowed, on another channel
-    no_pc = list(model.generate_stream(prompt=prompt, batch_size=B, max_len=P + n_new, top_k=1, disable_patch_change=True,
-                                       disable_control_change=True))
+    no_pc = _stream(model, prompt=prompt, batch_size=B, max_len=P + n_new, top_k=1, disable_patch_change=True,
+                    disable_control_change=True)
     types = {int(e[b, 0]) for e in no_pc for b in range(B)}
     assert not (types & {tok.event_ids["patch_change"], tok.event_ids["control_change"]})
     assert int(gg.mask.sum()) == gg.mask.numel()                                      # mask reset when the loop is handed back
@@ -368,15 +374,15 @@ def test_concurrent_streams_own_their_loop_state(monkeypatch):
     model.eval()
     P, n_new, B = 3, 4, 1
     p1, p2 = _batch(model, B=B, S1=P, seed=21).numpy(), _batch(model, B=B, S1=P, seed=22).numpy()
-    lone1 = list(model.generate_stream(prompt=p1, batch_size=B, max_len=P + n_new, top_k=1))
-    lone2 = list(model.generate_stream(prompt=p2, batch_size=B, max_len=P + n_new, top_k=1))
+    lone1 = _stream(model, prompt=p1, batch_size=B, max_len=P + n_new, top_k=1)
+    lone2 = _stream(model, prompt=p2, batch_size=B, max_len=P + n_new, top_k=1)
     g1 = model.generate_stream(prompt=p1, batch_size=B, max_len=P + n_new, top_k=1)
     g2 = model.generate_stream(prompt=p2, batch_size=B, max_len=P + n_new, top_k=1)
-    got1, got2, errors = [next(g1)], [next(g2)], []          # both suspended mid-generation on this thread ...
+    got1, got2, errors = [next(g1).copy()], [next(g2).copy()], []          # both suspended mid-generation on this thread ...
 
     def drain(g, out):
         try:
-            out.extend(g)                                      # ... and resumed on other threads
+            out.extend(e.copy() for e in g)                    # ... and resumed on other threads
         except Exception as e:                                 # noqa: BLE001
             errors.append(e)
 
